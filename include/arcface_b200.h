@@ -1,0 +1,144 @@
+/*
+ * arcface_b200.h -- C ABI of libarcface_b200.so: the B200 (sm_100a) implementation of the ArcFace
+ * additive-angular-margin head + softmax cross-entropy (forward, argmax, backward).
+ *
+ * Reference path replaced (forrestsocool/MultimodalSimilar, read-only at /root/reference):
+ *   arcface.py:45-63   ArcMarginProduct.forward        (normalise, cosine GEMM, margin, one-hot blend, scale)
+ *   arcface.py:65-67   ArcMarginProduct.forward_test   (bare cosines)
+ *   nlp_classifier_train.py:100,120-123  nn.CrossEntropyLoss()(preds, y), loss.backward(), torch.argmax
+ * The reference has no FFI of its own (it is pure PyTorch); its "plugin API" is the nn.Module protocol of
+ * arcface.ArcMarginProduct.  multimodalsimilar_b200/head.py mirrors that protocol and binds the entry
+ * points below with ctypes; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / CUDA types (a CUDA stream is passed as void*).
+ *   - every device buffer is owned by the caller (the library allocates nothing persistent);
+ *     pointers must be 16-byte aligned and rows contiguous unless a leading dimension is given.
+ *   - all work is enqueued asynchronously on `stream`; no entry point synchronises the device,
+ *     except the *_host convenience call which waits for its own results.
+ *   - return value: ARCFACE_B200_OK (0) or a negative ARCFACE_B200_E_* code; the message is available
+ *     from arcface_b200_last_error() (thread-local).  Nothing throws or aborts.
+ *   - there is no CPU fallback: on a device that is not compute capability 10.x every compute entry
+ *     point returns ARCFACE_B200_E_ARCH.
+ *   - bf16 buffers are passed as uint16_t*.
+ *   - shapes: B batch rows (1..ARCFACE_B200_MAX_BATCH), D embedding width (D % 8 == 0), C_local classes held by this rank
+ *     (the whole C on one GPU), class_offset = first global class id of this rank's shard.
+ */
+#ifndef ARCFACE_B200_H_
+#define ARCFACE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARCFACE_B200_VERSION_MAJOR 0
+#define ARCFACE_B200_VERSION_MINOR 1
+
+#define ARCFACE_B200_OK 0
+#define ARCFACE_B200_E_ARCH (-1)      /* device is not sm_100 */
+#define ARCFACE_B200_E_SHAPE (-2)     /* unsupported B / D / C */
+#define ARCFACE_B200_E_LAYOUT (-3)    /* misaligned pointer or bad leading dimension */
+#define ARCFACE_B200_E_WORKSPACE (-4) /* workspace too small */
+#define ARCFACE_B200_E_CUDA (-5)      /* a CUDA runtime / driver call failed */
+#define ARCFACE_B200_E_ARG (-6)       /* null pointer or invalid scalar */
+
+#define ARCFACE_B200_MAX_BATCH 2048
+
+int32_t arcface_b200_version(int32_t* major, int32_t* minor);
+const char* arcface_b200_last_error(void);
+/* ARCFACE_B200_OK iff the current CUDA device can run the kernels (compute capability 10.x). */
+int32_t arcface_b200_device_ok(void);
+
+/* K1 -- fused row L2-normalise + bf16 cast.  Replaces F.normalize(x) / F.normalize(self.weight)
+ * (arcface.py:47).  dst[r, :] = bf16(src[r, :] / max(||src[r, :]||, 1e-12)), inv_norm[r] = 1 / max(||.||, 1e-12).
+ * dst_t (nullable) additionally receives the transpose, dst_t[d * ld_t + r], for the dW GEMM. */
+int32_t arcface_b200_normalize_cast(const float* src, int64_t rows, int32_t D, uint16_t* dst, float* inv_norm,
+                                    uint16_t* dst_t, int64_t ld_t, void* stream);
+
+/* Label column in fp32 + margin (arcface.py:49-55 restricted to the label column, the only place the
+ * reference's one-hot blend at :58-60 uses phi).  For every row b whose label falls in this shard:
+ *   t = <x_b, w_y> * inv_nx[b] * inv_nw[y];  sine = sqrt(max(0, 1 - t^2));  phi = t cos_m - sine sin_m
+ *   u = easy ? (t > 0 ? phi : t) : (t - th > 0 ? phi : t - mm);   z_label = s * u
+ *   dphi = d u / d t   (cos_m + t sin_m / sine on the phi branch, 1 otherwise)
+ *   label_local = label - class_offset
+ * Rows whose label lives on another rank get z_label = 0, dphi = 0, label_local = -1.
+ * A label outside [0, C_total) sets *bad_label_flag (device int32) to 1. */
+int32_t arcface_b200_label_margin(const float* x, const float* w, const float* inv_nx, const float* inv_nw,
+                                  const int64_t* label, int32_t B, int32_t D, int64_t C_local,
+                                  int64_t class_offset, int64_t C_total, float s, float cos_m, float sin_m,
+                                  float th, float mm, int32_t easy_margin, float* t_label, float* z_label,
+                                  float* dphi, int32_t* label_local, int32_t* bad_label_flag, void* stream);
+
+/* Number of per-row partial slots arcface_b200_forward_stats writes for this shape. */
+int32_t arcface_b200_forward_parts(int32_t B, int64_t C_local, int32_t* n_parts);
+
+/* K2 -- cosine-logit GEMM (tcgen05 / TMEM, TMA-fed) with the margin / scale / online-softmax epilogue.
+ * Replaces F.linear (arcface.py:47), the blend + scale (:58-61), CrossEntropyLoss' log-softmax and
+ * torch.argmax, without writing the B x C logits.  z[b, c] = s * cos[b, c], except z[b, label] = z_label[b]
+ * (pass z_label = label_local = NULL for the eval path: plain scaled cosines, arcface.py:65-67).
+ * Writes n_parts x B partial rows: running max, sum exp(z - max), local index of the first max. */
+int32_t arcface_b200_forward_stats(const uint16_t* xhat, const uint16_t* what, const float* z_label,
+                                   const int32_t* label_local, int32_t B, int32_t D, int64_t C_local, float s,
+                                   float* part_max, float* part_sum, int32_t* part_arg, int32_t n_parts,
+                                   void* stream);
+
+/* Merge partial rows of one shard (ascending class order, first max wins) into row_max / row_sum /
+ * row_arg (global class id = local + class_offset). */
+int32_t arcface_b200_combine_partials(const float* part_max, const float* part_sum, const int32_t* part_arg,
+                                      int32_t n_parts, int32_t B, int64_t class_offset, float* row_max,
+                                      float* row_sum, int64_t* row_arg, void* stream);
+
+/* Merge the per-rank rows ([n_ranks][B], rank-major; n_ranks = 1 on a single GPU) into the softmax
+ * statistics and the mean cross-entropy:  lse[b] = M + log S,  argmax[b] (lowest index on ties),
+ * z_label_out[b] = sum over ranks of z_label (only the owner is non-zero), loss = mean_b(lse - z_label). */
+int32_t arcface_b200_finalize_rows(const float* rows_max, const float* rows_sum, const int64_t* rows_arg,
+                                   const float* rows_z_label, int32_t n_ranks, int32_t B, float* lse,
+                                   int64_t* argmax, float* z_label_out, float* loss, void* stream);
+
+/* Materialise out[b, c] = scale * cos[b, c] (label column overridden by z_label when given).  Eval path
+ * (forward_test, scale = 1) and the debug / small-C path behind the lazy logits object. */
+int32_t arcface_b200_logits(const uint16_t* xhat, const uint16_t* what, const float* z_label,
+                            const int32_t* label_local, int32_t B, int32_t D, int64_t C_local, float scale,
+                            float* out, int64_t ld_out, void* stream);
+
+/* Workspace (bytes) arcface_b200_backward needs. */
+int32_t arcface_b200_backward_workspace_bytes(int32_t B, int32_t D, int64_t C_local, size_t* bytes);
+
+/* K3 -- backward of the head + cross-entropy (loss.backward() through arcface.py:45-63).
+ * Recomputes p = exp(z - lse) tile by tile from the saved row statistics, forms
+ *   dC[b, c] = s * grad_scale * p            (c != label)
+ *   dC[b, y] = s * grad_scale * (p_y - 1) * dphi[b]
+ * and runs dXhat = dC . What (accumulated into the zeroed dxhat) and dWhat = dC^T . Xhat; the epilogue of
+ * the dW GEMM applies the normalise backward  dW[c] = (dWhat[c] - (what[c] . dWhat[c]) what[c]) * inv_nw[c].
+ * grad_scale = upstream grad of the mean loss / global batch size; when grad_loss_dev (nullable, DEVICE
+ * float scalar) is given, the effective scale is grad_scale * *grad_loss_dev, so an autograd caller never
+ * has to synchronise to read the upstream gradient.  dxhat is this rank's partial (sum over its classes)
+ * and is reduce-scattered by the caller when the head is class-sharded. */
+int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* xhat_t, int64_t ld_t, const uint16_t* what,
+                              const float* inv_nw, const float* lse, const float* z_label, const float* dphi,
+                              const int32_t* label_local, int32_t B, int32_t D, int64_t C_local, float s,
+                              float grad_scale, const float* grad_loss_dev, float* dxhat, float* dw,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
+/* Normalise backward for the embeddings: dx[b] = (dxhat[b] - (xhat[b] . dxhat[b]) xhat[b]) * inv_nx[b]
+ * with xhat = x * inv_nx in fp32. */
+int32_t arcface_b200_normalize_bwd_x(const float* x, const float* inv_nx, const float* dxhat, int32_t B,
+                                     int32_t D, float* dx, void* stream);
+
+/* One-call step for hosts without torch: HOST embeddings / labels in, HOST loss / argmax / dx out; the
+ * class weights and their gradient stay resident on the device (w, dw are DEVICE pointers, fp32 [C x D]).
+ * Copies in and out are part of the call; it returns after the results have landed in the host buffers.
+ * device_ws must hold arcface_b200_step_workspace_bytes() bytes. */
+int32_t arcface_b200_step_workspace_bytes(int32_t B, int32_t D, int64_t C, size_t* bytes);
+int32_t arcface_b200_step_host(const float* x_host, const int64_t* label_host, const float* w_dev, int32_t B,
+                               int32_t D, int64_t C, float s, float m, int32_t easy_margin, float grad_loss,
+                               float* loss_host, int64_t* argmax_host, float* dx_host, float* dw_dev,
+                               void* device_ws, size_t device_ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARCFACE_B200_H_ */

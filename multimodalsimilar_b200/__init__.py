@@ -1,0 +1,16 @@
+"""multimodalsimilar_b200 -- the ArcFace head hot path of forrestsocool/MultimodalSimilar, B200-native.
+
+Public surface (mirrors /root/reference/arcface.py):
+    ArcMarginProduct         drop-in nn.Module (single GPU)
+    ShardedArcMarginProduct  the same head class-sharded over a process group (PartialFC-style)
+    ArcFaceCEFunction        the autograd.Function behind both
+    ops                      tensor-level wrappers over the C ABI (include/arcface_b200.h)
+
+The compute lives in libarcface_b200.so (hand-written sm_100a CUDA: tcgen05 / TMEM / TMA); importing the
+package does not load it, the first op does, and raises if it is missing -- there is no fallback path.
+"""
+from .head import ArcFaceCEFunction, ArcMarginProduct, FusedLogits  # noqa: F401
+from .sharded import ShardedArcMarginProduct, shard_range  # noqa: F401
+
+__all__ = ["ArcMarginProduct", "ShardedArcMarginProduct", "ArcFaceCEFunction", "FusedLogits", "shard_range"]
+__version__ = "0.1.0"

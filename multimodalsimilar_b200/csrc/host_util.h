@@ -1,0 +1,44 @@
+// Host-side helpers of libarcface_b200: status codes / thread-local error string, TMA tensor-map
+// construction through the driver entry point (no -lcuda link dependency), device queries.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/arcface_b200.h"
+
+namespace ab {
+
+int32_t set_error(int32_t code, const char* fmt, ...);
+const char* last_error();
+
+#define AB_CHECK_CUDA(expr)                                                                      \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess)                                                                   \
+            return ab::set_error(ARCFACE_B200_E_CUDA, "%s failed: %s (%s:%d)", #expr,            \
+                                 cudaGetErrorString(_e), __FILE__, __LINE__);                    \
+    } while (0)
+
+#define AB_REQUIRE(cond, code, ...)                                 \
+    do {                                                            \
+        if (!(cond)) return ab::set_error((code), __VA_ARGS__);     \
+    } while (0)
+
+// Number of SMs of the current device (cached per device); 0 on failure.
+int sm_count();
+// ARCFACE_B200_OK iff the current device is compute capability 10.x.
+int32_t check_arch();
+
+// K-major operand: global [rows][inner] bf16 with row stride `row_stride_elems`; box = {64, box_rows}.
+int32_t make_tmap_kmajor(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows,
+                         uint64_t row_stride_elems, uint32_t box_rows);
+// MN-major operand: global [k_rows][mn] bf16 (mn contiguous); box = {64 mn, 64 k rows}.  A tile is
+// fetched as tile_mn / 64 boxes which land as [mn/64][BLOCK_K][64] in shared memory.
+int32_t make_tmap_mnmajor(CUtensorMap* out, const void* base, uint64_t mn, uint64_t k_rows,
+                          uint64_t row_stride_elems);
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace ab

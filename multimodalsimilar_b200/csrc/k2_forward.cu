@@ -1,0 +1,296 @@
+// K2 -- forward of the ArcFace head: cosine-logit GEMM on tcgen05 with a fused margin / scale /
+// online-softmax / argmax epilogue (the B x C logit matrix never reaches HBM), plus the
+// materialising variant used by forward_test / the lazy-logits object.
+//
+// Reference: arcface.py:47 (F.linear of the normalised operands), :58-61 (one-hot blend, * s),
+// CrossEntropyLoss + argmax at the call sites (nlp_classifier_train.py:120-123).
+//
+// Orientation: batch rows on the accumulator rows (TMEM lanes), classes on the columns, so every
+// epilogue thread owns one batch row and the running (max, sum-exp, argmax) is a thread-local scan.
+#include "host_util.h"
+#include "gemm_core.cuh"
+
+#include <math.h>
+
+namespace ab {
+
+constexpr float LOG2E = 1.4426950408889634f;
+
+// ------------------------------------------------------------------ softmax-statistics epilogue
+struct FwdStats {
+    static constexpr int BLOCK_N = 256;
+    static constexpr int STAGES = 4;
+    static constexpr bool A_MN = false;  // xhat [B][D]
+    static constexpr bool B_MN = false;  // what [C][D]
+
+    struct Params {
+        int B, D;
+        int C;                   // classes of this shard
+        float s;
+        const float* z_label;    // nullable
+        const int* label_local;  // nullable
+        float* part_max;
+        float* part_sum;
+        int* part_arg;
+        int m_tiles, n_tiles;
+        int groups;       // class ranges; CTA (g, m) handles m-tile m of range g
+        int tiles_per_g;  // ceil(n_tiles / groups)
+    };
+
+    __device__ static void prologue(const Params&, uint8_t*, int) {}
+
+    struct Sched {
+        int m_tile, n, n_end, kblocks;
+        __device__ Sched(const Params& p, int cta, int) {
+            m_tile = cta % p.m_tiles;
+            const int g = cta / p.m_tiles;
+            n = g * p.tiles_per_g;
+            n_end = min(p.n_tiles, n + p.tiles_per_g);
+            if (g >= p.groups) n_end = n;
+            kblocks = (p.D + BLOCK_K - 1) / BLOCK_K;
+        }
+        __device__ bool next(Tile& t) {
+            if (n >= n_end) return false;
+            t.m0 = m_tile * BLOCK_M;
+            t.n0 = n * BLOCK_N;
+            t.ka0 = 0;
+            t.kb0 = 0;
+            t.kblocks = kblocks;
+            t.aux = 0;
+            ++n;
+            return true;
+        }
+    };
+
+    struct Epi {
+        const Params& p;
+        int row, g;
+        bool active;
+        float run_max, sum0, sum1, sum2, sum3;
+        int run_arg;
+        int lab;
+        float zl;
+        __device__ Epi(const Params& prm, uint8_t*, int ew, int lane, int cta) : p(prm) {
+            const int m_tile = cta % p.m_tiles;
+            g = cta / p.m_tiles;
+            row = m_tile * BLOCK_M + ew * 32 + lane;
+            active = (g < p.groups) && (row < p.B);
+            run_max = -INFINITY;
+            sum0 = sum1 = sum2 = sum3 = 0.f;
+            run_arg = 0;
+            lab = -1;
+            zl = 0.f;
+            if (active && p.label_local != nullptr) {
+                lab = p.label_local[row];
+                zl = p.z_label[row];
+            }
+        }
+        __device__ void tile(const Tile& t, uint32_t taddr) {
+            const float s = p.s;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c * 32, v);
+                tmem_ld_wait();
+                const int col0 = t.n0 + c * 32;
+                if (col0 >= p.C) break;  // warp-uniform: whole chunk past the last class
+                float z[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) z[j] = __uint_as_float(v[j]) * s;
+                if (col0 + 32 > p.C) {  // warp-uniform tail
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j >= p.C) z[j] = -INFINITY;
+                }
+                const int lr = lab - col0;
+                if (lr >= 0 && lr < 32) {  // at most once per row: margin-adjusted label logit
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j == lr) z[j] = zl;
+                }
+                float cm = z[0];
+#pragma unroll
+                for (int j = 1; j < 32; ++j) cm = fmaxf(cm, z[j]);
+                if (cm > run_max) {  // strict: an equal later maximum never displaces the first one
+                    int first = 31;
+#pragma unroll
+                    for (int j = 30; j >= 0; --j)
+                        if (z[j] == cm) first = j;
+                    run_arg = col0 + first;
+                    const float f = ex2((run_max - cm) * LOG2E);  // ex2(-inf) = 0 on the first chunk
+                    sum0 *= f; sum1 *= f; sum2 *= f; sum3 *= f;
+                    run_max = cm;
+                }
+                const float mb = run_max * LOG2E;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    sum0 += ex2(fmaf(z[j + 0], LOG2E, -mb));
+                    sum1 += ex2(fmaf(z[j + 1], LOG2E, -mb));
+                    sum2 += ex2(fmaf(z[j + 2], LOG2E, -mb));
+                    sum3 += ex2(fmaf(z[j + 3], LOG2E, -mb));
+                }
+            }
+        }
+        __device__ void finish() {
+            if (!active) return;
+            const int64_t o = static_cast<int64_t>(g) * p.B + row;
+            p.part_max[o] = run_max;
+            p.part_sum[o] = (sum0 + sum1) + (sum2 + sum3);
+            p.part_arg[o] = run_arg;
+        }
+    };
+};
+
+// ------------------------------------------------------------------ materialising epilogue
+struct FwdLogits {
+    static constexpr int BLOCK_N = 256;
+    static constexpr int STAGES = 4;
+    static constexpr bool A_MN = false;
+    static constexpr bool B_MN = false;
+
+    struct Params {
+        int B, D;
+        int C;
+        float scale;
+        const float* z_label;
+        const int* label_local;
+        float* out;
+        int64_t ld_out;
+        int m_tiles, n_tiles;
+    };
+
+    __device__ static void prologue(const Params&, uint8_t*, int) {}
+
+    struct Sched {
+        int idx, total, step, m_tiles, kblocks;
+        __device__ Sched(const Params& p, int cta, int ncta) {
+            idx = cta;
+            step = ncta;
+            m_tiles = p.m_tiles;
+            total = p.m_tiles * p.n_tiles;
+            kblocks = (p.D + BLOCK_K - 1) / BLOCK_K;
+        }
+        __device__ bool next(Tile& t) {
+            if (idx >= total) return false;
+            t.m0 = (idx % m_tiles) * BLOCK_M;
+            t.n0 = (idx / m_tiles) * BLOCK_N;
+            t.ka0 = 0;
+            t.kb0 = 0;
+            t.kblocks = kblocks;
+            t.aux = 0;
+            idx += step;
+            return true;
+        }
+    };
+
+    struct Epi {
+        const Params& p;
+        int ew, lane;
+        __device__ Epi(const Params& prm, uint8_t*, int ew_, int lane_, int) : p(prm), ew(ew_), lane(lane_) {}
+        __device__ void tile(const Tile& t, uint32_t taddr) {
+            const int row = t.m0 + ew * 32 + lane;
+            const bool rv = row < p.B;
+            int lab = -1;
+            float zl = 0.f;
+            if (rv && p.label_local != nullptr) {
+                lab = p.label_local[row];
+                zl = p.z_label[row];
+            }
+            float* orow = p.out + static_cast<int64_t>(rv ? row : 0) * p.ld_out;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c * 32, v);
+                tmem_ld_wait();
+                const int col0 = t.n0 + c * 32;
+                if (col0 >= p.C) break;
+                if (rv) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = col0 + j;
+                        if (col < p.C) orow[col] = (col == lab) ? zl : __uint_as_float(v[j]) * p.scale;
+                    }
+                }
+            }
+        }
+        __device__ void finish() {}
+    };
+};
+
+static void fwd_partition(int B, int64_t C, int nsm, int* m_tiles, int* n_tiles, int* groups, int* per) {
+    *m_tiles = (B + BLOCK_M - 1) / BLOCK_M;
+    *n_tiles = static_cast<int>((C + FwdStats::BLOCK_N - 1) / FwdStats::BLOCK_N);
+    int g = nsm / *m_tiles;
+    if (g < 1) g = 1;
+    if (g > *n_tiles) g = *n_tiles;
+    *per = (*n_tiles + g - 1) / g;
+    *groups = (*n_tiles + *per - 1) / *per;  // no empty class range
+}
+
+}  // namespace ab
+
+using namespace ab;
+
+static int32_t check_gemm_shape(const char* who, int32_t B, int32_t D, int64_t C) {
+    AB_REQUIRE(B >= 1 && B <= ARCFACE_B200_MAX_BATCH, ARCFACE_B200_E_SHAPE, "%s: B=%d outside [1, %d]", who, B,
+               ARCFACE_B200_MAX_BATCH);
+    AB_REQUIRE(D >= 8 && D % 8 == 0, ARCFACE_B200_E_SHAPE, "%s: D=%d must be a positive multiple of 8", who, D);
+    AB_REQUIRE(C >= 1 && C <= (1ll << 30), ARCFACE_B200_E_SHAPE, "%s: C_local=%lld outside [1, 2^30]", who,
+               (long long)C);
+    return ARCFACE_B200_OK;
+}
+
+extern "C" int32_t arcface_b200_forward_parts(int32_t B, int64_t C_local, int32_t* n_parts) {
+    if (int32_t rc = check_arch()) return rc;
+    AB_REQUIRE(n_parts, ARCFACE_B200_E_ARG, "forward_parts: null pointer");
+    if (int32_t rc = check_gemm_shape("forward_parts", B, 8, C_local)) return rc;
+    int mt, nt, g, per;
+    fwd_partition(B, C_local, sm_count(), &mt, &nt, &g, &per);
+    *n_parts = g;
+    return ARCFACE_B200_OK;
+}
+
+extern "C" int32_t arcface_b200_forward_stats(const uint16_t* xhat, const uint16_t* what, const float* z_label,
+                                              const int32_t* label_local, int32_t B, int32_t D, int64_t C_local,
+                                              float s, float* part_max, float* part_sum, int32_t* part_arg,
+                                              int32_t n_parts, void* stream) {
+    if (int32_t rc = check_arch()) return rc;
+    AB_REQUIRE(xhat && what && part_max && part_sum && part_arg, ARCFACE_B200_E_ARG, "forward_stats: null pointer");
+    AB_REQUIRE((z_label == nullptr) == (label_local == nullptr), ARCFACE_B200_E_ARG,
+               "forward_stats: z_label and label_local must both be given or both be null");
+    AB_REQUIRE(s > 0.f, ARCFACE_B200_E_ARG, "forward_stats: scale s must be positive");
+    if (int32_t rc = check_gemm_shape("forward_stats", B, D, C_local)) return rc;
+    FwdStats::Params p;
+    fwd_partition(B, C_local, sm_count(), &p.m_tiles, &p.n_tiles, &p.groups, &p.tiles_per_g);
+    AB_REQUIRE(n_parts == p.groups, ARCFACE_B200_E_WORKSPACE, "forward_stats: n_parts=%d, expected %d", n_parts,
+               p.groups);
+    p.B = B; p.D = D; p.C = static_cast<int>(C_local); p.s = s;
+    p.z_label = z_label; p.label_local = label_local;
+    p.part_max = part_max; p.part_sum = part_sum; p.part_arg = part_arg;
+    CUtensorMap tmA, tmB;
+    if (int32_t rc = make_tmap_kmajor(&tmA, xhat, D, B, D, BLOCK_M)) return rc;
+    if (int32_t rc = make_tmap_kmajor(&tmB, what, D, C_local, D, FwdStats::BLOCK_N)) return rc;
+    return launch_gemm<FwdStats>(tmA, tmB, p, p.groups * p.m_tiles, 0, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int32_t arcface_b200_logits(const uint16_t* xhat, const uint16_t* what, const float* z_label,
+                                       const int32_t* label_local, int32_t B, int32_t D, int64_t C_local, float scale,
+                                       float* out, int64_t ld_out, void* stream) {
+    if (int32_t rc = check_arch()) return rc;
+    AB_REQUIRE(xhat && what && out, ARCFACE_B200_E_ARG, "logits: null pointer");
+    AB_REQUIRE((z_label == nullptr) == (label_local == nullptr), ARCFACE_B200_E_ARG,
+               "logits: z_label and label_local must both be given or both be null");
+    AB_REQUIRE(ld_out >= C_local, ARCFACE_B200_E_LAYOUT, "logits: ld_out < C_local");
+    if (int32_t rc = check_gemm_shape("logits", B, D, C_local)) return rc;
+    FwdLogits::Params p;
+    p.B = B; p.D = D; p.C = static_cast<int>(C_local); p.scale = scale;
+    p.z_label = z_label; p.label_local = label_local; p.out = out; p.ld_out = ld_out;
+    p.m_tiles = (B + BLOCK_M - 1) / BLOCK_M;
+    p.n_tiles = static_cast<int>((C_local + FwdLogits::BLOCK_N - 1) / FwdLogits::BLOCK_N);
+    CUtensorMap tmA, tmB;
+    if (int32_t rc = make_tmap_kmajor(&tmA, xhat, D, B, D, BLOCK_M)) return rc;
+    if (int32_t rc = make_tmap_kmajor(&tmB, what, D, C_local, D, FwdLogits::BLOCK_N)) return rc;
+    const int64_t total = static_cast<int64_t>(p.m_tiles) * p.n_tiles;
+    const int grid = static_cast<int>(total < sm_count() ? total : sm_count());
+    return launch_gemm<FwdLogits>(tmA, tmB, p, grid, 0, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,330 @@
+// Row-wise (HBM-bound) kernels of the ArcFace head:
+//   K1  normalize_cast       fused row L2-normalise + bf16 cast        (arcface.py:47, both F.normalize calls)
+//   label_margin             fp32 label cosine + additive angular margin (arcface.py:49-55 on the label column)
+//   combine_partials / finalize_rows   softmax statistics -> lse, argmax, mean CE loss
+//   normalize_bwd_x          backward of F.normalize for the embeddings
+#include "host_util.h"
+#include "ptx.cuh"
+
+#include <math.h>
+
+namespace ab {
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// One warp per row; lane l owns the 8-float chunks l, l+32, ... (each 32 B in, 16 B out: 128-bit
+// coalesced loads and stores).  NCH chunks per lane live in registers so the row is read once.
+template <int NCH>
+__global__ void __launch_bounds__(256) normalize_cast_kernel(const float* __restrict__ src, int64_t rows, int D,
+                                                             __nv_bfloat16* __restrict__ dst,
+                                                             float* __restrict__ inv_norm,
+                                                             __nv_bfloat16* __restrict__ dst_t, int64_t ld_t) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* rp = src + row * D;
+    float4 v[NCH][2];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        const int d = (lane + 32 * i) * 8;
+        if (d < D) {
+            v[i][0] = ldg_stream(reinterpret_cast<const float4*>(rp + d));
+            v[i][1] = ldg_stream(reinterpret_cast<const float4*>(rp + d + 4));
+            ss += v[i][0].x * v[i][0].x + v[i][0].y * v[i][0].y + v[i][0].z * v[i][0].z + v[i][0].w * v[i][0].w;
+            ss += v[i][1].x * v[i][1].x + v[i][1].y * v[i][1].y + v[i][1].z * v[i][1].z + v[i][1].w * v[i][1].w;
+        }
+    }
+    ss = warp_sum(ss);
+    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    if (lane == 0) inv_norm[row] = inv;
+    __nv_bfloat16* op = dst + row * D;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        const int d = (lane + 32 * i) * 8;
+        if (d < D) {
+            uint4 o;
+            o.x = pack_bf16x2(v[i][0].x * inv, v[i][0].y * inv);
+            o.y = pack_bf16x2(v[i][0].z * inv, v[i][0].w * inv);
+            o.z = pack_bf16x2(v[i][1].x * inv, v[i][1].y * inv);
+            o.w = pack_bf16x2(v[i][1].z * inv, v[i][1].w * inv);
+            *reinterpret_cast<uint4*>(op + d) = o;
+            if (dst_t != nullptr) {
+                const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    __nv_bfloat16_raw lo, hi;
+                    lo.x = static_cast<unsigned short>(w[j] & 0xffffu);
+                    hi.x = static_cast<unsigned short>(w[j] >> 16);
+                    dst_t[static_cast<int64_t>(d + 2 * j) * ld_t + row] = __nv_bfloat16(lo);
+                    dst_t[static_cast<int64_t>(d + 2 * j + 1) * ld_t + row] = __nv_bfloat16(hi);
+                }
+            }
+        }
+    }
+}
+
+// Any D (multiple of 8): two passes, the second served by L1/L2.
+__global__ void __launch_bounds__(256) normalize_cast_generic_kernel(const float* __restrict__ src, int64_t rows, int D,
+                                                                     __nv_bfloat16* __restrict__ dst,
+                                                                     float* __restrict__ inv_norm,
+                                                                     __nv_bfloat16* __restrict__ dst_t, int64_t ld_t) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* rp = src + row * D;
+    float ss = 0.f;
+    for (int d = lane * 4; d < D; d += 128) {
+        const float4 a = *reinterpret_cast<const float4*>(rp + d);
+        ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+    }
+    ss = warp_sum(ss);
+    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    if (lane == 0) inv_norm[row] = inv;
+    __nv_bfloat16* op = dst + row * D;
+    for (int d = lane * 4; d < D; d += 128) {
+        const float4 a = *reinterpret_cast<const float4*>(rp + d);
+        uint2 o;
+        o.x = pack_bf16x2(a.x * inv, a.y * inv);
+        o.y = pack_bf16x2(a.z * inv, a.w * inv);
+        *reinterpret_cast<uint2*>(op + d) = o;
+        if (dst_t != nullptr) {
+            const float f[4] = {a.x * inv, a.y * inv, a.z * inv, a.w * inv};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst_t[static_cast<int64_t>(d + j) * ld_t + row] = __float2bfloat16_rn(f[j]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+label_margin_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ inv_nx,
+                    const float* __restrict__ inv_nw, const int64_t* __restrict__ label, int B, int D, int64_t C_local,
+                    int64_t class_offset, int64_t C_total, float s, float cos_m, float sin_m, float th, float mm,
+                    int easy, float* __restrict__ t_label, float* __restrict__ z_label, float* __restrict__ dphi,
+                    int* __restrict__ label_local, int* __restrict__ bad_flag) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const int64_t y = label[b];
+    if ((y < 0 || y >= C_total) && lane == 0 && bad_flag != nullptr) atomicExch(bad_flag, 1);
+    const int64_t loc = y - class_offset;
+    if (loc < 0 || loc >= C_local) {
+        if (lane == 0) {
+            t_label[b] = 0.f;
+            z_label[b] = 0.f;
+            dphi[b] = 0.f;
+            label_local[b] = -1;
+        }
+        return;
+    }
+    const float* xp = x + static_cast<int64_t>(b) * D;
+    const float* wp = w + loc * D;
+    float dot = 0.f;
+    for (int d = lane * 4; d < D; d += 128) {
+        const float4 a = *reinterpret_cast<const float4*>(xp + d);
+        const float4 c = *reinterpret_cast<const float4*>(wp + d);
+        dot += a.x * c.x + a.y * c.y + a.z * c.z + a.w * c.w;
+    }
+    dot = warp_sum(dot);
+    if (lane == 0) {
+        const float t = dot * inv_nx[b] * inv_nw[loc];
+        // reference: sqrt(1 - cos^2) unclamped (arcface.py:49); clamped here so |t| = 1 + ulp cannot NaN
+        const float sine = sqrtf(fmaxf(0.f, 1.f - t * t));
+        const float phi = t * cos_m - sine * sin_m;
+        const bool take_phi = easy ? (t > 0.f) : ((t - th) > 0.f);
+        const float u = take_phi ? phi : (easy ? t : (t - mm));
+        t_label[b] = t;
+        z_label[b] = u * s;
+        dphi[b] = take_phi ? (cos_m + t * sin_m / fmaxf(sine, 1e-6f)) : 1.f;
+        label_local[b] = static_cast<int>(loc);
+    }
+}
+
+__global__ void combine_partials_kernel(const float* __restrict__ pm, const float* __restrict__ ps,
+                                        const int* __restrict__ pa, int n_parts, int B, int64_t class_offset,
+                                        float* __restrict__ row_max, float* __restrict__ row_sum,
+                                        int64_t* __restrict__ row_arg) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float M = -INFINITY, S = 0.f;
+    int A = 0;
+    for (int p = 0; p < n_parts; ++p) {
+        const float m = pm[static_cast<int64_t>(p) * B + b];
+        const float s = ps[static_cast<int64_t>(p) * B + b];
+        if (m > M) {  // strict: on ties the earlier (lower class index) part wins
+            S = S * expf(M - m) + s;
+            M = m;
+            A = pa[static_cast<int64_t>(p) * B + b];
+        } else if (m > -INFINITY) {
+            S += s * expf(m - M);
+        }
+    }
+    row_max[b] = M;
+    row_sum[b] = S;
+    row_arg[b] = static_cast<int64_t>(A) + class_offset;
+}
+
+__global__ void __launch_bounds__(256)
+finalize_rows_kernel(const float* __restrict__ rm, const float* __restrict__ rs, const int64_t* __restrict__ ra,
+                     const float* __restrict__ rz, int n_ranks, int B, float* __restrict__ lse,
+                     int64_t* __restrict__ argmax, float* __restrict__ z_out, float* __restrict__ loss) {
+    __shared__ float red[256];
+    float acc = 0.f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        float M = -INFINITY, S = 0.f, Z = 0.f;
+        int64_t A = 0;
+        for (int r = 0; r < n_ranks; ++r) {
+            const float m = rm[static_cast<int64_t>(r) * B + b];
+            const float s = rs[static_cast<int64_t>(r) * B + b];
+            if (m > M) {
+                S = S * expf(M - m) + s;
+                M = m;
+                A = ra[static_cast<int64_t>(r) * B + b];
+            } else if (m > -INFINITY) {
+                S += s * expf(m - M);
+            }
+            Z += rz[static_cast<int64_t>(r) * B + b];
+        }
+        const float l = M + logf(S);
+        lse[b] = l;
+        argmax[b] = A;
+        z_out[b] = Z;
+        acc += l - Z;
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) loss[0] = red[0] / static_cast<float>(B);
+}
+
+__global__ void __launch_bounds__(256)
+normalize_bwd_x_kernel(const float* __restrict__ x, const float* __restrict__ inv_nx, const float* __restrict__ dxhat,
+                       int B, int D, float* __restrict__ dx) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const float inv = inv_nx[b];
+    const float* xp = x + static_cast<int64_t>(b) * D;
+    const float* gp = dxhat + static_cast<int64_t>(b) * D;
+    float r = 0.f;
+    for (int d = lane * 4; d < D; d += 128) {
+        const float4 a = *reinterpret_cast<const float4*>(xp + d);
+        const float4 g = *reinterpret_cast<const float4*>(gp + d);
+        r += (a.x * g.x + a.y * g.y + a.z * g.z + a.w * g.w);
+    }
+    r = warp_sum(r) * inv;  // xhat . dxhat
+    float* op = dx + static_cast<int64_t>(b) * D;
+    for (int d = lane * 4; d < D; d += 128) {
+        const float4 a = *reinterpret_cast<const float4*>(xp + d);
+        const float4 g = *reinterpret_cast<const float4*>(gp + d);
+        float4 o;
+        o.x = (g.x - r * (a.x * inv)) * inv;
+        o.y = (g.y - r * (a.y * inv)) * inv;
+        o.z = (g.z - r * (a.z * inv)) * inv;
+        o.w = (g.w - r * (a.w * inv)) * inv;
+        *reinterpret_cast<float4*>(op + d) = o;
+    }
+}
+
+}  // namespace ab
+
+using namespace ab;
+
+extern "C" int32_t arcface_b200_normalize_cast(const float* src, int64_t rows, int32_t D, uint16_t* dst,
+                                               float* inv_norm, uint16_t* dst_t, int64_t ld_t, void* stream) {
+    if (int32_t rc = check_arch()) return rc;
+    AB_REQUIRE(src && dst && inv_norm, ARCFACE_B200_E_ARG, "normalize_cast: null pointer");
+    AB_REQUIRE(rows >= 0 && D >= 8 && D % 8 == 0, ARCFACE_B200_E_SHAPE, "normalize_cast: D=%d must be a positive multiple of 8", D);
+    AB_REQUIRE(aligned16(src) && aligned16(dst), ARCFACE_B200_E_LAYOUT, "normalize_cast: pointers must be 16-byte aligned");
+    AB_REQUIRE(dst_t == nullptr || ld_t >= rows, ARCFACE_B200_E_LAYOUT, "normalize_cast: ld_t < rows");
+    if (rows == 0) return ARCFACE_B200_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int wpb = 8;
+    const int64_t nblk = (rows + wpb - 1) / wpb;
+    AB_REQUIRE(nblk < (1ll << 31), ARCFACE_B200_E_SHAPE, "normalize_cast: too many rows");
+    dim3 grid(static_cast<unsigned>(nblk)), block(wpb * 32);
+    __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst);
+    __nv_bfloat16* dt = reinterpret_cast<__nv_bfloat16*>(dst_t);
+    const int nch = (D + 255) / 256;
+    if (nch <= 1) normalize_cast_kernel<1><<<grid, block, 0, st>>>(src, rows, D, d, inv_norm, dt, ld_t);
+    else if (nch <= 2) normalize_cast_kernel<2><<<grid, block, 0, st>>>(src, rows, D, d, inv_norm, dt, ld_t);
+    else if (nch <= 4) normalize_cast_kernel<4><<<grid, block, 0, st>>>(src, rows, D, d, inv_norm, dt, ld_t);
+    else if (nch <= 8) normalize_cast_kernel<8><<<grid, block, 0, st>>>(src, rows, D, d, inv_norm, dt, ld_t);
+    else if (nch <= 12) normalize_cast_kernel<12><<<grid, block, 0, st>>>(src, rows, D, d, inv_norm, dt, ld_t);
+    else normalize_cast_generic_kernel<<<grid, block, 0, st>>>(src, rows, D, d, inv_norm, dt, ld_t);
+    AB_CHECK_CUDA(cudaGetLastError());
+    return ARCFACE_B200_OK;
+}
+
+extern "C" int32_t arcface_b200_label_margin(const float* x, const float* w, const float* inv_nx, const float* inv_nw,
+                                             const int64_t* label, int32_t B, int32_t D, int64_t C_local,
+                                             int64_t class_offset, int64_t C_total, float s, float cos_m, float sin_m,
+                                             float th, float mm, int32_t easy_margin, float* t_label, float* z_label,
+                                             float* dphi, int32_t* label_local, int32_t* bad_label_flag, void* stream) {
+    if (int32_t rc = check_arch()) return rc;
+    AB_REQUIRE(x && w && inv_nx && inv_nw && label && t_label && z_label && dphi && label_local, ARCFACE_B200_E_ARG,
+               "label_margin: null pointer");
+    AB_REQUIRE(B >= 0 && D >= 8 && D % 8 == 0 && C_local >= 1, ARCFACE_B200_E_SHAPE, "label_margin: bad shape");
+    AB_REQUIRE(aligned16(x) && aligned16(w), ARCFACE_B200_E_LAYOUT, "label_margin: x / w must be 16-byte aligned");
+    if (B == 0) return ARCFACE_B200_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    label_margin_kernel<<<(B + 7) / 8, 256, 0, st>>>(x, w, inv_nx, inv_nw, label, B, D, C_local, class_offset, C_total,
+                                                     s, cos_m, sin_m, th, mm, easy_margin, t_label, z_label, dphi,
+                                                     label_local, bad_label_flag);
+    AB_CHECK_CUDA(cudaGetLastError());
+    return ARCFACE_B200_OK;
+}
+
+extern "C" int32_t arcface_b200_combine_partials(const float* part_max, const float* part_sum, const int32_t* part_arg,
+                                                 int32_t n_parts, int32_t B, int64_t class_offset, float* row_max,
+                                                 float* row_sum, int64_t* row_arg, void* stream) {
+    if (int32_t rc = check_arch()) return rc;
+    AB_REQUIRE(part_max && part_sum && part_arg && row_max && row_sum && row_arg, ARCFACE_B200_E_ARG,
+               "combine_partials: null pointer");
+    AB_REQUIRE(n_parts >= 1 && B >= 0, ARCFACE_B200_E_SHAPE, "combine_partials: bad shape");
+    if (B == 0) return ARCFACE_B200_OK;
+    combine_partials_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        part_max, part_sum, part_arg, n_parts, B, class_offset, row_max, row_sum, row_arg);
+    AB_CHECK_CUDA(cudaGetLastError());
+    return ARCFACE_B200_OK;
+}
+
+extern "C" int32_t arcface_b200_finalize_rows(const float* rows_max, const float* rows_sum, const int64_t* rows_arg,
+                                              const float* rows_z_label, int32_t n_ranks, int32_t B, float* lse,
+                                              int64_t* argmax, float* z_label_out, float* loss, void* stream) {
+    if (int32_t rc = check_arch()) return rc;
+    AB_REQUIRE(rows_max && rows_sum && rows_arg && rows_z_label && lse && argmax && z_label_out && loss,
+               ARCFACE_B200_E_ARG, "finalize_rows: null pointer");
+    AB_REQUIRE(n_ranks >= 1 && B >= 1, ARCFACE_B200_E_SHAPE, "finalize_rows: bad shape");
+    finalize_rows_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(rows_max, rows_sum, rows_arg, rows_z_label,
+                                                                          n_ranks, B, lse, argmax, z_label_out, loss);
+    AB_CHECK_CUDA(cudaGetLastError());
+    return ARCFACE_B200_OK;
+}
+
+extern "C" int32_t arcface_b200_normalize_bwd_x(const float* x, const float* inv_nx, const float* dxhat, int32_t B,
+                                                int32_t D, float* dx, void* stream) {
+    if (int32_t rc = check_arch()) return rc;
+    AB_REQUIRE(x && inv_nx && dxhat && dx, ARCFACE_B200_E_ARG, "normalize_bwd_x: null pointer");
+    AB_REQUIRE(B >= 0 && D >= 8 && D % 8 == 0, ARCFACE_B200_E_SHAPE, "normalize_bwd_x: bad shape");
+    AB_REQUIRE(aligned16(x) && aligned16(dxhat) && aligned16(dx), ARCFACE_B200_E_LAYOUT,
+               "normalize_bwd_x: pointers must be 16-byte aligned");
+    if (B == 0) return ARCFACE_B200_OK;
+    normalize_bwd_x_kernel<<<(B + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, inv_nx, dxhat, B, D, dx);
+    AB_CHECK_CUDA(cudaGetLastError());
+    return ARCFACE_B200_OK;
+}

@@ -1,0 +1,256 @@
+"""Drop-in ArcFace head: the host-side mirror of the reference's `arcface.ArcMarginProduct`
+(/root/reference/arcface.py:17-67) over the sm_100a kernels.
+
+Same constructor, attributes, `weight` parameter, `forward(x, label)`, `forward_test(x)` and
+`update_m(delta)`; what changes is that the B x C logit matrix is never built.  `forward` returns a
+`FusedLogits` handle that answers exactly what the reference's training loops ask of `preds`
+(nlp_classifier_train.py:120-123):
+
+    loss = nn.CrossEntropyLoss()(preds, labels)   -> fused mean cross-entropy (autograd-connected)
+    loss.backward()                                -> fused dX / dW
+    torch.argmax(preds, dim=-1)                    -> fused argmax (first maximum, like torch)
+
+and materialises real logits (through the logits kernel, detached) only if anything else touches it.
+New code can call `head.loss(x, label) -> (loss, argmax)` directly.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+from torch.nn import Parameter
+
+from . import ops
+
+
+class ArcFaceCEFunction(torch.autograd.Function):
+    """loss, argmax = ArcFaceCE(x, weight, label; s, m, easy_margin).
+
+    forward : K1 (x), K1 (weight), label margin, K2 (+combine, finalize)
+    backward: K3 (dC^T producer, dW GEMM, dX GEMM) + normalise backward for x
+    Saved for backward: xhat / xhat^T / what (bf16), the inverse norms, lse, z_label, dphi, labels --
+    no B x C tensor.
+    """
+
+    @staticmethod
+    def forward(ctx, x, weight, label, s, m, easy_margin, validate_labels):
+        B, D = x.shape
+        C = weight.shape[0]
+        xhat, inv_nx, xhat_t = ops.normalize_cast(x, want_transpose=True)
+        what, inv_nw, _ = ops.normalize_cast(weight)
+        lm = ops.label_margin(x, weight, inv_nx, inv_nw, label, 0, C, s, m, easy_margin)
+        rmax, rsum, rarg = ops.forward_rows(xhat, what, lm.z_label, lm.label_local, s, 0)
+        lse, argmax, z_label, loss = ops.finalize_rows(rmax.view(1, B), rsum.view(1, B), rarg.view(1, B),
+                                                       lm.z_label.view(1, B))
+        if validate_labels and int(lm.bad_flag.item()) != 0:
+            raise IndexError("ArcMarginProduct: a label is outside [0, %d)" % C)
+        ctx.save_for_backward(x, inv_nx, xhat, xhat_t, what, inv_nw, lse, z_label, lm.dphi, lm.label_local)
+        ctx.s = s
+        ctx.mark_non_differentiable(argmax)
+        return loss, argmax
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_argmax):
+        x, inv_nx, xhat, xhat_t, what, inv_nw, lse, z_label, dphi, label_local = ctx.saved_tensors
+        B = x.shape[0]
+        g = grad_loss.to(torch.float32).contiguous()
+        dxhat, dw = ops.backward(xhat, xhat_t, what, inv_nw, lse, z_label, dphi, label_local, ctx.s, 1.0 / B,
+                                 grad_loss_dev=g)
+        dx = ops.normalize_bwd_x(x, inv_nx, dxhat) if ctx.needs_input_grad[0] else None
+        return dx, (dw if ctx.needs_input_grad[1] else None), None, None, None, None, None
+
+
+class FusedLogits:
+    """What `ArcMarginProduct.forward` returns: the logits of arcface.py:61 as a lazy handle.
+
+    `F.cross_entropy(handle, label)` / `nn.CrossEntropyLoss()(handle, label)` and
+    `torch.argmax(handle, dim=-1)` are answered from the fused kernels.  `handle.materialize()` (also
+    triggered by any other torch function) runs the logits kernel and returns a detached fp32 [B, C]
+    tensor -- the debug / small-C path.
+    """
+
+    def __init__(self, head, x, label):
+        self._head = head
+        self._x = x
+        self._label = label
+        self._fused = None
+        self._dense = None
+        self.shape = torch.Size((x.shape[0], head.out_feature))
+
+    # -- fused answers
+    def _run(self):
+        if self._fused is None:
+            self._fused = self._head.loss(self._x, self._label)
+        return self._fused
+
+    def cross_entropy(self):
+        return self._run()[0]
+
+    def argmax(self, dim=-1, keepdim=False):
+        if dim not in (-1, 1):
+            return self.materialize().argmax(dim=dim, keepdim=keepdim)
+        a = self._run()[1]
+        return a.unsqueeze(-1) if keepdim else a
+
+    def size(self, dim=None):
+        return self.shape if dim is None else self.shape[dim]
+
+    def dim(self):
+        return 2
+
+    @property
+    def device(self):
+        return self._x.device
+
+    @property
+    def dtype(self):
+        return torch.float32
+
+    def materialize(self) -> torch.Tensor:
+        if self._dense is None:
+            self._dense = self._head.logits(self._x, self._label)
+        return self._dense
+
+    def detach(self):
+        return self.materialize()
+
+    def cpu(self):
+        return self.materialize().cpu()
+
+    def float(self):
+        return self.materialize()
+
+    def __getitem__(self, idx):
+        return self.materialize()[idx]
+
+    def __repr__(self):
+        return "FusedLogits(shape=%s, device=%s)" % (tuple(self.shape), self.device)
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        if func is F.cross_entropy:
+            return cls._cross_entropy(*args, **kwargs)
+        if func in (torch.argmax, torch.Tensor.argmax) and isinstance(args[0], FusedLogits):
+            return args[0].argmax(*args[1:], **kwargs)
+        args = tuple(a.materialize() if isinstance(a, FusedLogits) else a for a in args)
+        kwargs = {k: (v.materialize() if isinstance(v, FusedLogits) else v) for k, v in kwargs.items()}
+        return func(*args, **kwargs)
+
+    @staticmethod
+    def _cross_entropy(input, target, weight=None, size_average=None, ignore_index=-100, reduce=None,
+                       reduction="mean", label_smoothing=0.0):
+        self = input
+        fused_ok = (
+            isinstance(self, FusedLogits) and weight is None and reduction == "mean" and label_smoothing == 0.0
+            and size_average is None and reduce is None and torch.is_tensor(target)
+            and target.dtype in (torch.int64, torch.int32) and target.numel() == self._label.numel()
+            and (target.data_ptr() == self._label.data_ptr() or bool(torch.equal(target.view(-1).to(self._label.dtype),
+                                                                                  self._label.view(-1))))
+        )
+        if fused_ok:
+            return self.cross_entropy()
+        if not isinstance(self, FusedLogits):
+            return F.cross_entropy(input, target.materialize() if isinstance(target, FusedLogits) else target,
+                                   weight=weight, size_average=size_average, ignore_index=ignore_index,
+                                   reduce=reduce, reduction=reduction, label_smoothing=label_smoothing)
+        if torch.is_grad_enabled() and (self._x.requires_grad or self._head.weight.requires_grad):
+            raise NotImplementedError(
+                "FusedLogits: only the reference's loss (mean cross-entropy against the labels given to forward, "
+                "no class weights / smoothing) is differentiable without the B x C logits; got other options")
+        dense = self.materialize() if isinstance(self, FusedLogits) else input
+        return F.cross_entropy(dense, target, weight=weight, size_average=size_average, ignore_index=ignore_index,
+                               reduce=reduce, reduction=reduction, label_smoothing=label_smoothing)
+
+
+class ArcMarginProduct(nn.Module):
+    """Additive angular margin head (arcface.py:17-67), B200-native.
+
+    Constructor and attributes follow the reference: positional `(in_feature, out_feature, s, m,
+    easy_margin)` (nlp_classifier.py:15, cv_classifier.py:38) or the keywords `in_feature=` /
+    `out_feature=` (multimodal_classifier.py:22); `in_features=` / `out_features=` are accepted as aliases.
+    """
+
+    def __init__(self, in_feature=128, out_feature=10575, s=64.0, m=0.40, easy_margin=False, *,
+                 in_features=None, out_features=None, validate_labels=False):
+        super().__init__()
+        if in_features is not None:
+            in_feature = in_features
+        if out_features is not None:
+            out_feature = out_features
+        self.in_feature = in_feature
+        self.out_feature = out_feature
+        self.s = s
+        self.m = m
+        self.weight = Parameter(torch.empty(out_feature, in_feature))
+        nn.init.xavier_uniform_(self.weight)  # arcface.py:24-25
+        self.easy_margin = easy_margin
+        self.validate_labels = validate_labels
+        self.cos_m, self.sin_m, self.th, self.mm = ops.margin_constants(m)
+
+    def update_m(self, delta):
+        """arcface.py:35-42: accepted only while 1e-6 <= m + delta <= 1.0, silently ignored otherwise."""
+        updated = self.m + delta
+        if updated >= 1e-6 and updated <= 1.0:
+            self.m = updated
+            self.cos_m, self.sin_m, self.th, self.mm = ops.margin_constants(self.m)
+
+    # ------------------------------------------------------------------ training path
+    def _prep(self, x, label):
+        if not x.is_cuda or not self.weight.is_cuda:
+            raise RuntimeError("multimodalsimilar_b200.ArcMarginProduct runs on a B200 only (module and inputs must be "
+                               "on a CUDA device); there is no CPU path")
+        x = x.to(torch.float32).contiguous()
+        label = label.reshape(-1).to(device=x.device, dtype=torch.int64).contiguous()
+        if x.dim() != 2 or x.shape[1] != self.in_feature or label.numel() != x.shape[0]:
+            raise ValueError("expected x [B, %d] and B labels, got %s and %s" % (self.in_feature, tuple(x.shape),
+                                                                               tuple(label.shape)))
+        return x, label
+
+    def loss(self, x, label):
+        """Fused head + mean softmax cross-entropy.  Returns (loss [], argmax int64 [B])."""
+        x, label = self._prep(x, label)
+        w = self.weight if self.weight.is_contiguous() else self.weight.contiguous()
+        return ArcFaceCEFunction.apply(x, w, label, float(self.s), float(self.m), bool(self.easy_margin),
+                                       bool(self.validate_labels))
+
+    def forward(self, x, label):
+        return FusedLogits(self, x, label)
+
+    @torch.no_grad()
+    def logits(self, x, label=None):
+        """Materialised logits (detached): arcface.py:61 when `label` is given, s * cos otherwise."""
+        if label is None:
+            x = x.to(torch.float32).contiguous()
+        else:
+            x, label = self._prep(x, label)
+        w = self.weight.detach().contiguous()
+        xhat, inv_nx, _ = ops.normalize_cast(x)
+        what, inv_nw, _ = ops.normalize_cast(w)
+        if label is None:
+            return ops.logits(xhat, what, None, None, float(self.s))
+        lm = ops.label_margin(x, w, inv_nx, inv_nw, label, 0, w.shape[0], float(self.s), float(self.m),
+                              bool(self.easy_margin))
+        return ops.logits(xhat, what, lm.z_label, lm.label_local, float(self.s))
+
+    # ------------------------------------------------------------------ eval path
+    @torch.no_grad()
+    def forward_test(self, x):
+        """arcface.py:65-67: bare cosines [B, C] (no margin, no scale), materialised like the reference."""
+        x = x.to(torch.float32).contiguous()
+        xhat, _, _ = ops.normalize_cast(x)
+        what, _, _ = ops.normalize_cast(self.weight.detach().contiguous())
+        return ops.logits(xhat, what, None, None, 1.0)
+
+    @torch.no_grad()
+    def predict(self, x):
+        """argmax_c cos[b, c] without materialising the cosines (what the eval loops do with
+        forward_test's output, nlp_classifier_train.py:143-156).  Returns (argmax int64 [B], max cosine [B])."""
+        x = x.to(torch.float32).contiguous()
+        xhat, _, _ = ops.normalize_cast(x)
+        what, _, _ = ops.normalize_cast(self.weight.detach().contiguous())
+        rmax, _, rarg = ops.forward_rows(xhat, what, None, None, 1.0, 0)
+        return rarg, rmax
+
+    def extra_repr(self):
+        return ""

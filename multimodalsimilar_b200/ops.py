@@ -1,0 +1,199 @@
+"""Tensor-level wrappers over the C ABI (include/arcface_b200.h).
+
+PyTorch is used for device memory, streams and autograd plumbing only: every function here takes CUDA
+tensors, passes `data_ptr()` + sizes + the current stream to libarcface_b200.so, and returns tensors that
+the library filled.  Nothing here computes on the host or through ATen; if the library is missing the
+import of `_lib` raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+
+MAX_BATCH = _lib.MAX_BATCH
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: multimodalsimilar_b200 has no CPU path" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise RuntimeError("%s must be contiguous" % name)
+    return t
+
+
+def margin_constants(m: float):
+    """(cos_m, sin_m, th, mm) as the reference stores them (arcface.py:28-33)."""
+    return math.cos(m), math.sin(m), math.cos(math.pi - m), math.sin(math.pi - m) * m
+
+
+def device_ok() -> None:
+    _lib.call("arcface_b200_device_ok")
+
+
+def round_up(v: int, k: int) -> int:
+    return (v + k - 1) // k * k
+
+
+def normalize_cast(src: torch.Tensor, want_transpose: bool = False):
+    """K1.  src [R, D] fp32 -> (bf16 [R, D], inv_norm fp32 [R], optional bf16 transpose [D, ld_t])."""
+    _req(src, torch.float32, "src")
+    R, D = src.shape
+    dst = torch.empty((R, D), dtype=torch.bfloat16, device=src.device)
+    inv = torch.empty((R,), dtype=torch.float32, device=src.device)
+    dst_t = None
+    ld_t = 0
+    if want_transpose:
+        ld_t = round_up(R, 64)
+        dst_t = torch.empty((D, ld_t), dtype=torch.bfloat16, device=src.device)
+    _lib.call("arcface_b200_normalize_cast", _ptr(src), R, D, _ptr(dst), _ptr(inv), _ptr(dst_t), ld_t, _stream())
+    return dst, inv, dst_t
+
+
+@dataclass
+class LabelMargin:
+    t_label: torch.Tensor      # fp32 [B] exact label cosine (0 where the label is on another rank)
+    z_label: torch.Tensor      # fp32 [B] s * margin(t)
+    dphi: torch.Tensor         # fp32 [B] d margin / d t
+    label_local: torch.Tensor  # int32 [B] label - class_offset, or -1
+    bad_flag: torch.Tensor     # int32 [1] set when a label is outside [0, C_total)
+
+
+def label_margin(x, w, inv_nx, inv_nw, label, class_offset, c_total, s, m, easy_margin) -> LabelMargin:
+    _req(x, torch.float32, "x")
+    _req(w, torch.float32, "weight")
+    _req(label, torch.int64, "label")
+    B, D = x.shape
+    dev = x.device
+    out = LabelMargin(
+        torch.empty(B, dtype=torch.float32, device=dev),
+        torch.empty(B, dtype=torch.float32, device=dev),
+        torch.empty(B, dtype=torch.float32, device=dev),
+        torch.empty(B, dtype=torch.int32, device=dev),
+        torch.zeros(1, dtype=torch.int32, device=dev),
+    )
+    cos_m, sin_m, th, mm = margin_constants(m)
+    _lib.call("arcface_b200_label_margin", _ptr(x), _ptr(w), _ptr(inv_nx), _ptr(inv_nw), _ptr(label), B, D,
+              w.shape[0], class_offset, c_total, s, cos_m, sin_m, th, mm, int(bool(easy_margin)),
+              _ptr(out.t_label), _ptr(out.z_label), _ptr(out.dphi), _ptr(out.label_local), _ptr(out.bad_flag), _stream())
+    return out
+
+
+def forward_parts(B: int, c_local: int) -> int:
+    n = ctypes.c_int32(0)
+    _lib.call("arcface_b200_forward_parts", B, c_local, ctypes.byref(n))
+    return n.value
+
+
+def forward_rows(xhat, what, z_label, label_local, s: float, class_offset: int = 0):
+    """K2 + per-shard combine.  Returns (row_max fp32 [B], row_sum fp32 [B], row_arg int64 [B])."""
+    _req(xhat, torch.bfloat16, "xhat")
+    _req(what, torch.bfloat16, "what")
+    B, D = xhat.shape
+    C = what.shape[0]
+    dev = xhat.device
+    n_parts = forward_parts(B, C)
+    pmax = torch.empty((n_parts, B), dtype=torch.float32, device=dev)
+    psum = torch.empty((n_parts, B), dtype=torch.float32, device=dev)
+    parg = torch.empty((n_parts, B), dtype=torch.int32, device=dev)
+    _lib.call("arcface_b200_forward_stats", _ptr(xhat), _ptr(what), _ptr(z_label), _ptr(label_local), B, D, C, s,
+              _ptr(pmax), _ptr(psum), _ptr(parg), n_parts, _stream())
+    rmax = torch.empty(B, dtype=torch.float32, device=dev)
+    rsum = torch.empty(B, dtype=torch.float32, device=dev)
+    rarg = torch.empty(B, dtype=torch.int64, device=dev)
+    _lib.call("arcface_b200_combine_partials", _ptr(pmax), _ptr(psum), _ptr(parg), n_parts, B, class_offset,
+              _ptr(rmax), _ptr(rsum), _ptr(rarg), _stream())
+    return rmax, rsum, rarg
+
+
+def finalize_rows(rows_max, rows_sum, rows_arg, rows_z):
+    """Merge [R, B] per-rank rows -> (lse [B], argmax int64 [B], z_label [B], loss [])."""
+    R, B = rows_max.shape
+    dev = rows_max.device
+    lse = torch.empty(B, dtype=torch.float32, device=dev)
+    arg = torch.empty(B, dtype=torch.int64, device=dev)
+    z = torch.empty(B, dtype=torch.float32, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    _lib.call("arcface_b200_finalize_rows", _ptr(_req(rows_max, torch.float32, "rows_max")),
+              _ptr(_req(rows_sum, torch.float32, "rows_sum")), _ptr(_req(rows_arg, torch.int64, "rows_arg")),
+              _ptr(_req(rows_z, torch.float32, "rows_z")), R, B, _ptr(lse), _ptr(arg), _ptr(z), _ptr(loss), _stream())
+    return lse, arg, z, loss
+
+
+def logits(xhat, what, z_label, label_local, scale: float) -> torch.Tensor:
+    """Materialise scale * cos (label column overridden when z_label is given): fp32 [B, C]."""
+    _req(xhat, torch.bfloat16, "xhat")
+    _req(what, torch.bfloat16, "what")
+    B, D = xhat.shape
+    C = what.shape[0]
+    out = torch.empty((B, C), dtype=torch.float32, device=xhat.device)
+    _lib.call("arcface_b200_logits", _ptr(xhat), _ptr(what), _ptr(z_label), _ptr(label_local), B, D, C, scale,
+              _ptr(out), C, _stream())
+    return out
+
+
+def backward_workspace_bytes(B: int, D: int, c_local: int) -> int:
+    n = ctypes.c_size_t(0)
+    _lib.call("arcface_b200_backward_workspace_bytes", B, D, c_local, ctypes.byref(n))
+    return n.value
+
+
+def backward(xhat, xhat_t, what, inv_nw, lse, z_label, dphi, label_local, s: float, grad_scale: float,
+             grad_loss_dev=None, dw_out=None):
+    """K3.  Returns (dxhat fp32 [B, D] partial over this shard's classes, dW fp32 [C_local, D])."""
+    B, D = xhat.shape
+    C = what.shape[0]
+    dev = xhat.device
+    dxhat = torch.empty((B, D), dtype=torch.float32, device=dev)
+    dw = dw_out if dw_out is not None else torch.empty((C, D), dtype=torch.float32, device=dev)
+    _req(dw, torch.float32, "dw")
+    nbytes = backward_workspace_bytes(B, D, C)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    if grad_loss_dev is not None:
+        grad_loss_dev = _req(grad_loss_dev.reshape(1), torch.float32, "grad_loss")
+    _lib.call("arcface_b200_backward", _ptr(xhat), _ptr(xhat_t), xhat_t.shape[1], _ptr(what), _ptr(inv_nw), _ptr(lse),
+              _ptr(z_label), _ptr(dphi), _ptr(label_local), B, D, C, s, grad_scale, _ptr(grad_loss_dev), _ptr(dxhat),
+              _ptr(dw), _ptr(ws), nbytes, _stream())
+    return dxhat, dw
+
+
+def normalize_bwd_x(x, inv_nx, dxhat) -> torch.Tensor:
+    _req(x, torch.float32, "x")
+    _req(dxhat, torch.float32, "dxhat")
+    B, D = x.shape
+    dx = torch.empty_like(x)
+    _lib.call("arcface_b200_normalize_bwd_x", _ptr(x), _ptr(inv_nx), _ptr(dxhat), B, D, _ptr(dx), _stream())
+    return dx
+
+
+def step_workspace_bytes(B: int, D: int, C: int) -> int:
+    n = ctypes.c_size_t(0)
+    _lib.call("arcface_b200_step_workspace_bytes", B, D, C, ctypes.byref(n))
+    return n.value
+
+
+def step_host(x_host, label_host, w_dev, s, m, easy_margin, grad_loss, loss_host, argmax_host, dx_host, dw_dev, ws):
+    """The one-call host-buffer step (pinned HOST x / labels in, HOST loss / argmax / dx out)."""
+    for t, name in ((x_host, "x_host"), (label_host, "label_host"), (loss_host, "loss_host"),
+                    (argmax_host, "argmax_host"), (dx_host, "dx_host")):
+        if t.is_cuda or not t.is_contiguous():
+            raise RuntimeError("%s must be a contiguous host tensor" % name)
+    B, D = x_host.shape
+    C = w_dev.shape[0]
+    _lib.call("arcface_b200_step_host", _ptr(x_host), _ptr(label_host), _ptr(_req(w_dev, torch.float32, "w")), B, D, C,
+              s, m, int(bool(easy_margin)), grad_loss, _ptr(loss_host), _ptr(argmax_host), _ptr(dx_host),
+              _ptr(_req(dw_dev, torch.float32, "dw")), _ptr(ws), ws.numel(), _stream())

@@ -1,0 +1,98 @@
+"""The oracle (oracle/arcface_numpy.py) and the timed CPU port (oracle/arcface_torch_cpu.py) against the
+golden vectors minted from the unmodified reference (tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import arcface_numpy as onp
+from oracle import arcface_torch_cpu as otc
+
+SMALL = ["base", "easy", "fallback", "easy_neg", "zero_row", "tie", "label_col", "trained", "grad10", "ragged"]
+
+
+def _case(golden, name):
+    s, m, easy, grad = golden[name + "/hp"]
+    if name == "c1":
+        x, w, y = onp.synthetic_inputs(64, 512, 1000, seed=1)
+    else:
+        x, w, y = golden[name + "/x"], golden[name + "/w"], golden[name + "/label"]
+    return x, w, y, float(s), float(m), bool(easy), float(grad)
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_forward_matches_reference(golden, name):
+    x, w, y, s, m, easy, _ = _case(golden, name)
+    z = onp.forward_logits(x, w, y, s, m, easy, dtype=np.float32)
+    np.testing.assert_allclose(z, golden[name + "/logits"], rtol=0, atol=2e-5 * s)
+    assert abs(onp.cross_entropy(z, y) - float(golden[name + "/loss"])) <= 1e-5 * max(1.0, float(golden[name + "/loss"]))
+    np.testing.assert_array_equal(onp.argmax(golden[name + "/logits"]), golden[name + "/argmax"])
+    np.testing.assert_allclose(onp.forward_test(x, w), golden[name + "/cos"], rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_backward_matches_reference(golden, name):
+    x, w, y, s, m, easy, grad = _case(golden, name)
+    dx, dw = onp.backward(x, w, y, s, m, easy, grad_loss=grad, dtype=np.float64)
+    gx, gw = golden[name + "/dx"], golden[name + "/dw"]
+    if name == "zero_row":  # dx of the zero-norm row is dXhat / 1e-12 in the reference: compare relatively
+        np.testing.assert_allclose(dx, gx, rtol=2e-3, atol=1e-5 * max(1.0, np.abs(gx).max()) * 1e-3)
+    else:
+        np.testing.assert_allclose(dx, gx, rtol=0, atol=5e-5 * max(1.0, np.abs(gx).max()))
+    np.testing.assert_allclose(dw, gw, rtol=0, atol=5e-5 * max(1.0, np.abs(gw).max()))
+
+
+def test_branches_are_exercised(golden):
+    # fallback: row 0 has cos_label < th -> s * (cos - mm); easy_neg: row 0 has cos <= 0 -> s * cos
+    x, w, y, s, m, easy, _ = _case(golden, "fallback")
+    t = onp.cosines(x, w)[0, y[0]]
+    _, _, th, mm = onp.margin_constants(m)
+    assert t < th
+    assert abs(golden["fallback/logits"][0, y[0]] - s * (t - mm)) < 1e-3
+    assert abs(golden["easy_neg/logits"][0, y[0]] - s * t) < 1e-3
+    # zero-norm row: logits 0 off the label, -s * sin(m) on it
+    zr = golden["zero_row/logits"][1]
+    yz = golden["zero_row/label"][1]
+    assert abs(zr[yz] + 30.0 * np.sin(0.5)) < 1e-4 and np.abs(np.delete(zr, yz)).max() == 0.0
+    # tie: two identical winning columns -> the lower index
+    assert golden["tie/argmax"][2] == 5
+
+
+def test_c1_config(golden):
+    x, w, y, s, m, easy, grad = _case(golden, "c1")
+    loss, am = onp.loss_and_argmax(x, w, y, s, m, easy)
+    assert abs(loss - float(golden["c1/loss"])) <= 1e-4 * float(golden["c1/loss"])
+    np.testing.assert_array_equal(am, golden["c1/argmax"])
+    rows = golden["c1/dw_rows"]
+    z = onp.forward_logits(x, w, y, s, m, easy)
+    np.testing.assert_allclose(z[:, rows], golden["c1/logits_rows"], rtol=0, atol=2e-5 * s)
+    dx, dw = onp.backward(x, w, y, s, m, easy, grad)
+    np.testing.assert_allclose(dx, golden["c1/dx"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(dw[rows], golden["c1/dw"], rtol=0, atol=2e-6)
+
+
+def test_margin_schedule(golden):
+    u = golden["update_m"]
+    m = onp.update_m(0.5, 0.04)
+    assert m == u[0]
+    np.testing.assert_allclose(onp.margin_constants(m), u[1:5], rtol=0, atol=0)
+    assert onp.update_m(m, 2.0) == u[5] == m          # rejected: above 1.0
+    assert onp.update_m(0.5, -0.6) == u[6] == 0.5     # rejected: below 1e-6
+    np.testing.assert_allclose(onp.margin_constants(0.4), golden["const_m04"], rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("name", ["base", "easy", "fallback", "trained", "grad10", "ragged"])
+def test_torch_cpu_port_matches_reference(golden, name):
+    x, w, y, s, m, easy, grad = _case(golden, name)
+    loss, pred, dx, dw = otc.head_step(torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(y), s, m, easy)
+    assert abs(float(loss) - float(golden[name + "/loss"])) <= 1e-6 * max(1.0, float(golden[name + "/loss"]))
+    np.testing.assert_array_equal(pred.numpy(), golden[name + "/argmax"])
+    np.testing.assert_allclose(dx.numpy() * grad, golden[name + "/dx"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(dw.numpy() * grad, golden[name + "/dw"], rtol=1e-5, atol=1e-6)
+
+
+def test_row_stats_consistency():
+    x, w, y = onp.synthetic_inputs(16, 32, 100, seed=3)
+    z = onp.forward_logits(x, w, y, 64.0, 0.4, False, dtype=np.float64)
+    zmax, lse = onp.row_stats(z)
+    assert abs(np.mean(lse - z[np.arange(16), y]) - onp.cross_entropy(z, y)) < 1e-9
+    assert np.all(zmax == z.max(axis=1))
