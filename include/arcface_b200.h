@@ -106,6 +106,9 @@ int32_t arcface_b200_logits(const uint16_t* xhat, const uint16_t* what, const fl
 
 /* Workspace (bytes) arcface_b200_backward needs. */
 int32_t arcface_b200_backward_workspace_bytes(int32_t B, int32_t D, int64_t C_local, size_t* bytes);
+/* How arcface_b200_backward walks the classes: classes per scratch chunk and number of chunks
+ * (each chunk is three kernel launches: dC^T producer, dW GEMM, dX GEMM). */
+int32_t arcface_b200_backward_plan(int32_t B, int32_t D, int64_t C_local, int64_t* chunk_classes, int32_t* n_chunks);
 
 /* K3 -- backward of the head + cross-entropy (loss.backward() through arcface.py:45-63).
  * Recomputes p = exp(z - lse) tile by tile from the saved row statistics, forms

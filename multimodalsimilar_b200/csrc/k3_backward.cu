@@ -357,6 +357,18 @@ extern "C" int32_t arcface_b200_backward_workspace_bytes(int32_t B, int32_t D, i
     return ARCFACE_B200_OK;
 }
 
+extern "C" int32_t arcface_b200_backward_plan(int32_t B, int32_t D, int64_t C_local, int64_t* chunk_classes,
+                                              int32_t* n_chunks) {
+    if (int32_t rc = check_arch()) return rc;
+    AB_REQUIRE(chunk_classes && n_chunks, ARCFACE_B200_E_ARG, "backward_plan: null pointer");
+    AB_REQUIRE(B >= 1 && B <= ARCFACE_B200_MAX_BATCH && D >= 8 && D % 8 == 0 && C_local >= 1 && C_local <= (1ll << 30),
+               ARCFACE_B200_E_SHAPE, "backward_plan: bad shape B=%d D=%d C=%lld", B, D, (long long)C_local);
+    const BwdPlan pl = plan_backward(B, C_local, sm_count());
+    *chunk_classes = pl.chunk_classes;
+    *n_chunks = static_cast<int32_t>((C_local + pl.chunk_classes - 1) / pl.chunk_classes);
+    return ARCFACE_B200_OK;
+}
+
 extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* xhat_t, int64_t ld_t,
                                          const uint16_t* what, const float* inv_nw, const float* lse,
                                          const float* z_label, const float* dphi, const int32_t* label_local,

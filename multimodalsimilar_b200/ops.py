@@ -152,6 +152,14 @@ def backward_workspace_bytes(B: int, D: int, c_local: int) -> int:
     return n.value
 
 
+def backward_plan(B: int, D: int, c_local: int):
+    """(classes per scratch chunk, number of chunks) of the backward walk."""
+    cc = ctypes.c_int64(0)
+    n = ctypes.c_int32(0)
+    _lib.call("arcface_b200_backward_plan", B, D, c_local, ctypes.byref(cc), ctypes.byref(n))
+    return cc.value, n.value
+
+
 def backward(xhat, xhat_t, what, inv_nw, lse, z_label, dphi, label_local, s: float, grad_scale: float,
              grad_loss_dev=None, dw_out=None):
     """K3.  Returns (dxhat fp32 [B, D] partial over this shard's classes, dW fp32 [C_local, D])."""

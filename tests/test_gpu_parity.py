@@ -1,0 +1,340 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`).  Everything goes through the C ABI
+(multimodalsimilar_b200.ops / the nn.Module) and is compared with the oracle (oracle/arcface_numpy.py),
+the golden vectors minted from the reference, or -- at sizes the oracle cannot reach -- a plain fp32
+PyTorch restatement run on the same GPU (test-only checker).
+
+Tolerances (BASELINE.json north_star): label / argmax indices bit-exact (on rows whose top-2 gap exceeds
+the logit tolerance), loss within 1e-3 relative, logits and gradients within 2e-2 absolute in the bf16
+mode; the logit tolerance is taken on z at s = 30 and on z / s * 30 otherwise.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+from oracle import arcface_numpy as onp
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_ATOL = 2e-2
+GRAD_ATOL = 2e-2
+LOSS_RTOL = 1e-3
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev())
+
+
+def torch_reference(x, w, y, s, m, easy, grad=1.0):
+    """fp32 eager restatement of arcface.py:45-63 + CrossEntropyLoss on the GPU (checker only)."""
+    x = x.detach().clone().requires_grad_(True)
+    w = w.detach().clone().requires_grad_(True)
+    c = torch.nn.functional.linear(torch.nn.functional.normalize(x), torch.nn.functional.normalize(w))
+    sn = (1.0 - c * c).clamp_min(0).sqrt()
+    ph = c * math.cos(m) - sn * math.sin(m)
+    ph = torch.where(c > 0, ph, c) if easy else torch.where(c - math.cos(math.pi - m) > 0, ph, c - math.sin(math.pi - m) * m)
+    hot = torch.zeros_like(c).scatter_(1, y.view(-1, 1), 1)
+    z = (hot * ph + (1 - hot) * c) * s
+    loss = torch.nn.functional.cross_entropy(z, y)
+    (loss * grad).backward()
+    return z.detach(), loss.detach(), x.grad, w.grad
+
+
+# ----------------------------------------------------------------------------- K1
+@pytest.mark.parametrize("rows,D", [(1000, 512), (37, 24), (513, 1024), (300, 1792), (129, 2816), (64, 3328), (5, 8)])
+def test_k1_normalize_cast(rows, D):
+    from multimodalsimilar_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(rows * 7 + D)
+    src = (torch.randn(rows, D, generator=g) * 0.3).to(dev())
+    src[rows // 2] = 0.0  # zero-norm row -> zeros, inv = 1e12
+    dst, inv, dst_t = ops.normalize_cast(src, want_transpose=True)
+    ref_n = src.norm(dim=1).clamp_min(1e-12)
+    ref = (src / ref_n[:, None])
+    # bf16 result within one bf16 ulp of the fp32 normalised value
+    err = (dst.float() - ref).abs()
+    assert float((err - ref.abs() * 2.0 ** -8).max()) <= 1e-6
+    torch.testing.assert_close(inv, 1.0 / ref_n, rtol=2e-6, atol=0)
+    assert torch.equal(dst_t[:, :rows], dst.t())
+    assert float(dst[rows // 2].float().abs().max()) == 0.0
+
+
+# ----------------------------------------------------------------------------- GEMM core, K-major operands
+@pytest.mark.parametrize("B,D,C", [(64, 512, 1000), (5, 24, 37), (200, 64, 300), (256, 1792, 2000), (512, 512, 4099),
+                                   (1024, 128, 777), (130, 2816, 600)])
+def test_logits_kernel_matches_bf16_matmul(B, D, C):
+    from multimodalsimilar_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(B + D + C)
+    xh = torch.randn(B, D, generator=g).to(dev()).bfloat16()
+    wh = torch.randn(C, D, generator=g).to(dev()).bfloat16()
+    out = ops.logits(xh, wh, None, None, 1.0)
+    ref = (xh.double() @ wh.double().t()).float()
+    tol = 2e-6 * D * float(ref.abs().max().clamp_min(1.0))  # fp32 accumulation order only
+    assert float((out - ref).abs().max()) <= tol
+
+
+# ----------------------------------------------------------------------------- golden vectors (reference outputs)
+SMALL = ["base", "easy", "fallback", "easy_neg", "zero_row", "tie", "label_col", "trained", "grad10", "ragged", "c1"]
+
+
+def _golden_case(golden, name):
+    s, m, easy, grad = golden[name + "/hp"]
+    if name == "c1":
+        x, w, y = onp.synthetic_inputs(64, 512, 1000, seed=1)
+    else:
+        x, w, y = golden[name + "/x"], golden[name + "/w"], golden[name + "/label"]
+    return x, w, y, float(s), float(m), bool(easy), float(grad)
+
+
+def _make_head(w, s, m, easy):
+    import multimodalsimilar_b200 as mm
+
+    head = mm.ArcMarginProduct(w.shape[1], w.shape[0], s=s, m=m, easy_margin=easy).to(dev())
+    with torch.no_grad():
+        head.weight.copy_(_t(w))
+    return head
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_golden_forward_backward(golden, name):
+    x, w, y, s, m, easy, grad = _golden_case(golden, name)
+    head = _make_head(w, s, m, easy)
+    xt = _t(x).requires_grad_(True)
+    yt = _t(y)
+    loss, pred = head.loss(xt, yt)
+    (loss * grad).backward()
+    gl = float(golden[name + "/loss"])
+    assert abs(float(loss) - gl) <= LOSS_RTOL * max(1.0, abs(gl)), (float(loss), gl)
+    z64 = onp.forward_logits(x, w, y, s, m, easy, dtype=np.float64)
+    top2 = np.sort(z64, axis=1)[:, -2:]
+    separated = (top2[:, 1] - top2[:, 0]) > 2 * LOGIT_ATOL * s / 30.0
+    if name == "tie":
+        separated[2] = True  # the exact tie (two identical class rows) must resolve to the first index too
+    np.testing.assert_array_equal(pred.cpu().numpy()[separated], golden[name + "/argmax"][separated])
+    if name == "c1":
+        rows = golden["c1/dw_rows"]
+        zg = head.logits(_t(x), yt).cpu().numpy()[:, rows]
+        np.testing.assert_allclose(zg, golden["c1/logits_rows"], rtol=0, atol=LOGIT_ATOL * s / 30.0)
+        np.testing.assert_allclose(head.weight.grad.cpu().numpy()[rows], golden["c1/dw"], rtol=0, atol=GRAD_ATOL)
+        np.testing.assert_allclose(xt.grad.cpu().numpy(), golden["c1/dx"], rtol=0, atol=GRAD_ATOL)
+        return
+    zg = head.logits(_t(x), yt).cpu().numpy()
+    np.testing.assert_allclose(zg, golden[name + "/logits"], rtol=0, atol=LOGIT_ATOL * s / 30.0)
+    np.testing.assert_allclose(head.forward_test(_t(x)).cpu().numpy(), golden[name + "/cos"], rtol=0, atol=LOGIT_ATOL / 30.0)
+    dw = head.weight.grad.cpu().numpy()
+    np.testing.assert_allclose(dw, golden[name + "/dw"], rtol=0, atol=GRAD_ATOL * max(1.0, grad))
+    dx = xt.grad.cpu().numpy()
+    gx = golden[name + "/dx"]
+    if name == "zero_row":  # the reference divides dXhat by eps = 1e-12 for the zero-norm row
+        keep = np.arange(len(y)) != 1
+        np.testing.assert_allclose(dx[keep], gx[keep], rtol=0, atol=GRAD_ATOL)
+        assert np.all(np.isfinite(dx[1]))
+    else:
+        np.testing.assert_allclose(dx, gx, rtol=0, atol=GRAD_ATOL * max(1.0, grad))
+    # beyond the absolute gate: relative Frobenius error of the gradients stays at bf16 level
+    if name != "zero_row":
+        assert np.linalg.norm(dx - gx) <= 3e-2 * np.linalg.norm(gx) + 1e-6
+    assert np.linalg.norm(dw - golden[name + "/dw"]) <= 3e-2 * np.linalg.norm(golden[name + "/dw"]) + 1e-6
+
+
+# ----------------------------------------------------------------------------- fused statistics vs own logits
+@pytest.mark.parametrize("B,D,C,s", [(64, 512, 1000, 30.0), (200, 64, 30000, 64.0), (512, 128, 70001, 64.0),
+                                     (1000, 64, 5000, 64.0), (3, 8, 2, 10.0)])
+def test_fused_statistics_match_materialised_logits(B, D, C, s):
+    from multimodalsimilar_b200 import ops
+
+    x, w, y = onp.synthetic_inputs(B, D, C, seed=B + C)
+    xt, wt, yt = _t(x), _t(w), _t(y)
+    xhat, inv_nx, _ = ops.normalize_cast(xt)
+    what, inv_nw, _ = ops.normalize_cast(wt)
+    lm = ops.label_margin(xt, wt, inv_nx, inv_nw, yt, 0, C, s, 0.4, False)
+    z = ops.logits(xhat, what, lm.z_label, lm.label_local, s)
+    rmax, rsum, rarg = ops.forward_rows(xhat, what, lm.z_label, lm.label_local, s, 0)
+    lse, arg, zl, loss = ops.finalize_rows(rmax.view(1, B), rsum.view(1, B), rarg.view(1, B), lm.z_label.view(1, B))
+    assert torch.equal(rmax, z.max(dim=1).values)          # same MMA sequence -> bit-identical cosines
+    first = (z == z.max(dim=1, keepdim=True).values).int().argmax(dim=1)
+    assert torch.equal(arg, first)
+    ref_lse = torch.logsumexp(z.double(), dim=1)
+    assert float((lse.double() - ref_lse).abs().max()) <= 2e-4
+    ref_loss = float((ref_lse - z.double()[torch.arange(B), yt]).mean())
+    assert abs(float(loss) - ref_loss) <= 1e-4 * max(1.0, abs(ref_loss))
+    assert int(lm.bad_flag.item()) == 0
+    assert torch.equal(lm.label_local.long(), yt)
+
+
+# ----------------------------------------------------------------------------- backward vs oracle (medium)
+@pytest.mark.parametrize("B,D,C,s,m,easy,trained", [
+    (64, 64, 1000, 30.0, 0.5, False, False),
+    (256, 128, 5000, 64.0, 0.4, False, True),
+    (100, 72, 777, 64.0, 0.2, True, False),
+    (300, 256, 2049, 64.0, 0.4, False, True),
+])
+def test_backward_matches_oracle(B, D, C, s, m, easy, trained):
+    x, w, y = onp.synthetic_inputs(B, D, C, seed=11, trained_like=trained)
+    head = _make_head(w, s, m, easy)
+    xt = _t(x).requires_grad_(True)
+    loss, pred = head.loss(xt, _t(y))
+    loss.backward()
+    z = onp.forward_logits(x, w, y, s, m, easy, dtype=np.float64)
+    ref_loss = onp.cross_entropy(z, y)
+    dx, dw = onp.backward(x, w, y, s, m, easy, dtype=np.float64)
+    assert abs(float(loss) - ref_loss) <= LOSS_RTOL * max(1.0, abs(ref_loss))
+    gdx, gdw = xt.grad.cpu().numpy(), head.weight.grad.cpu().numpy()
+    np.testing.assert_allclose(gdx, dx, rtol=0, atol=GRAD_ATOL)
+    np.testing.assert_allclose(gdw, dw, rtol=0, atol=GRAD_ATOL)
+    assert np.linalg.norm(gdx - dx) <= 3e-2 * np.linalg.norm(dx)
+    assert np.linalg.norm(gdw - dw) <= 3e-2 * np.linalg.norm(dw)
+    if trained:
+        np.testing.assert_array_equal(pred.cpu().numpy(), onp.argmax(z))
+
+
+# ----------------------------------------------------------------------------- full-size properties
+@pytest.mark.parametrize("B,D,C,s,m", [
+    (256, 1792, 100000, 64.0, 0.2),    # BASELINE config 2 (EfficientNet-B4 head)
+    (512, 512, 1000000, 64.0, 0.5),    # north-star shape: several backward chunks
+    (128, 64, 600000, 64.0, 0.4),      # small B: the chunk is > 500k classes, still two chunks
+])
+def test_full_size_against_fp32_gpu_reference_and_invariants(B, D, C, s, m):
+    x, w, y = onp.synthetic_inputs(B, D, C, seed=5, trained_like=True)
+    head = _make_head(w, s, m, False)
+    xt = _t(x).requires_grad_(True)
+    yt = _t(y)
+    loss, pred = head.loss(xt, yt)
+    loss.backward()
+    z, rloss, rdx, rdw = torch_reference(_t(x), head.weight.detach(), yt, s, m, False)
+    assert abs(float(loss) - float(rloss)) <= LOSS_RTOL * max(1.0, abs(float(rloss)))
+    top2 = torch.topk(z, 2, dim=1).values
+    sep = (top2[:, 0] - top2[:, 1]) > 2 * LOGIT_ATOL * s / 30.0
+    assert int(sep.sum()) > B // 2
+    assert torch.equal(pred[sep], torch.argmax(z, dim=1)[sep])
+    dx, dw = xt.grad, head.weight.grad
+    assert float((dx - rdx).abs().max()) <= GRAD_ATOL and float((dw - rdw).abs().max()) <= GRAD_ATOL
+    assert float((dx - rdx).norm() / rdx.norm()) <= 3e-2
+    assert float((dw - rdw).norm() / rdw.norm()) <= 3e-2
+    # size-independent invariants of the normalise backward: gradients are tangent to their rows
+    wv = head.weight.detach()
+    assert float(((dw * wv).sum(1).abs() / (dw.norm(dim=1) * wv.norm(dim=1) + 1e-30)).max()) <= 2e-2
+    assert float(((dx * xt.detach()).sum(1).abs() / (dx.norm(dim=1) * xt.detach().norm(dim=1) + 1e-30)).max()) <= 2e-2
+    # linearity in the upstream gradient
+    head.weight.grad = None
+    xt2 = _t(x).requires_grad_(True)
+    l2, _ = head.loss(xt2, yt)
+    (l2 * 3.0).backward()
+    assert float((xt2.grad - 3.0 * dx).abs().max()) <= 1e-3 * float(dx.abs().max()) * 3 + 1e-7
+    assert float((head.weight.grad - 3.0 * dw).norm() / (3.0 * dw.norm())) <= 1e-3
+
+
+# ----------------------------------------------------------------------------- host-buffer C-ABI step
+def test_step_host_matches_module():
+    from multimodalsimilar_b200 import ops
+
+    B, D, C, s, m = 96, 128, 3000, 64.0, 0.4
+    x, w, y = onp.synthetic_inputs(B, D, C, seed=2, trained_like=True)
+    head = _make_head(w, s, m, False)
+    xt = _t(x).requires_grad_(True)
+    loss, pred = head.loss(xt, _t(y))
+    (loss * 2.0).backward()
+    xh = torch.from_numpy(x).pin_memory()
+    yh = torch.from_numpy(y).pin_memory()
+    loss_h = torch.zeros(1).pin_memory()
+    arg_h = torch.zeros(B, dtype=torch.int64).pin_memory()
+    dx_h = torch.zeros(B, D).pin_memory()
+    dw = torch.empty(C, D, device=dev())
+    ws = torch.empty(ops.step_workspace_bytes(B, D, C), dtype=torch.uint8, device=dev())
+    ops.step_host(xh, yh, head.weight.detach(), s, m, False, 2.0, loss_h, arg_h, dx_h, dw, ws)
+    assert abs(float(loss_h) - float(loss)) <= 1e-6 * max(1.0, abs(float(loss)))
+    assert torch.equal(arg_h, pred.cpu())
+    torch.testing.assert_close(dx_h, xt.grad.cpu(), rtol=1e-3, atol=1e-6)   # dX uses atomics: order-dependent rounding
+    torch.testing.assert_close(dw, head.weight.grad, rtol=1e-4, atol=1e-7)   # scale folded in a different order
+
+
+# ----------------------------------------------------------------------------- drop-in flows of the callers
+def test_reference_training_loop_shape(golden):
+    """`preds = model(...); loss = CrossEntropyLoss()(preds, y); loss.backward(); argmax(preds)` unchanged
+    (nlp_classifier_train.py:116-133), including a second head on the same embedding
+    (nlp_classifier_multilabel.py:33-35 with the 10 / 5 weights of ..._v3_dist.py:164-166)."""
+    import multimodalsimilar_b200 as mm
+
+    x, w, y, s, m, easy, _ = _golden_case(golden, "base")
+    head = _make_head(w, s, m, easy)
+    head2 = mm.ArcMarginProduct(16, 12, m=0.2).to(dev())
+    y2 = _t(y) % 12
+    emb = _t(x).requires_grad_(True)
+    opt = torch.optim.AdamW(list(head.parameters()) + list(head2.parameters()), lr=1e-2)
+    crit = nn.CrossEntropyLoss()
+    preds, preds2 = head(emb, _t(y)), head2(emb, y2)
+    loss = 10 * crit(preds, _t(y)) + 5 * crit(preds2, y2)
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    acc = (torch.argmax(preds, dim=-1) == _t(y)).float().mean()
+    assert np.isfinite(float(loss)) and 0.0 <= float(acc) <= 1.0
+    # gradient of the shared embedding is the weighted sum of both heads' dx
+    e1 = _t(x).requires_grad_(True)
+    (10 * crit(_make_head(w, s, m, easy)(e1, _t(y)), _t(y))).backward()
+    assert float((emb.grad - e1.grad).abs().max()) > 0  # second head contributed
+    np.testing.assert_allclose(e1.grad.cpu().numpy(), 10 * golden["base/dx"], rtol=0, atol=GRAD_ATOL * 10)
+    # anything else materialises real logits
+    dense = preds.materialize()
+    assert tuple(dense.shape) == (8, 32)
+    np.testing.assert_allclose(dense.cpu().numpy(), head.logits(_t(x), _t(y)).cpu().numpy(), rtol=0, atol=0)
+
+
+def test_eval_path(golden):
+    x, w, y, s, m, easy, _ = _golden_case(golden, "trained")
+    head = _make_head(w, s, m, easy).eval()
+    cos = head.forward_test(_t(x))
+    np.testing.assert_allclose(cos.cpu().numpy(), golden["trained/cos"], rtol=0, atol=LOGIT_ATOL / 30.0)
+    arg, mx = head.predict(_t(x))
+    assert torch.equal(arg, torch.argmax(cos, dim=-1))
+    assert torch.equal(mx, cos.max(dim=1).values)
+
+
+def test_shape_and_label_errors():
+    import multimodalsimilar_b200 as mm
+    from multimodalsimilar_b200 import _lib
+
+    head = mm.ArcMarginProduct(12, 32).to(dev())   # D % 8 != 0
+    with pytest.raises(_lib.ArcfaceB200Error, match="E_SHAPE"):
+        head.loss(torch.randn(4, 12, device=dev()), torch.zeros(4, dtype=torch.int64, device=dev()))
+    head = mm.ArcMarginProduct(16, 32).to(dev())
+    with pytest.raises(_lib.ArcfaceB200Error, match="E_SHAPE"):
+        head.loss(torch.randn(4096, 16, device=dev()), torch.zeros(4096, dtype=torch.int64, device=dev()))
+    head = mm.ArcMarginProduct(16, 32, validate_labels=True).to(dev())
+    with pytest.raises(IndexError):
+        head.loss(torch.randn(4, 16, device=dev()), torch.tensor([0, 1, 32, 3], device=dev()))
+
+
+# ----------------------------------------------------------------------------- class-sharded head
+def test_sharded_head_single_rank_equals_dense_head():
+    import torch.distributed as dist
+
+    import multimodalsimilar_b200 as mm
+
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29631", rank=0, world_size=1)
+    try:
+        B, D, C, s, m = 64, 64, 1000, 64.0, 0.4
+        x, w, y = onp.synthetic_inputs(B, D, C, seed=4, trained_like=True)
+        dense = _make_head(w, s, m, False)
+        sh = mm.ShardedArcMarginProduct(D, C, s=s, m=m).to(dev())
+        sh.load_full_weight(_t(w))
+        a = _t(x).requires_grad_(True)
+        b = _t(x).requires_grad_(True)
+        l1, p1 = dense.loss(a, _t(y))
+        l2, p2 = sh.loss(b, _t(y))
+        l1.backward()
+        l2.backward()
+        assert float(l1) == float(l2) and torch.equal(p1, p2)
+        torch.testing.assert_close(a.grad, b.grad, rtol=1e-3, atol=1e-6)
+        assert torch.equal(dense.weight.grad, sh.weight.grad)
+        assert torch.equal(sh.gather_weight(), dense.weight.detach())
+    finally:
+        dist.destroy_process_group()
