@@ -370,10 +370,11 @@ def stage_times(torch, ops, head, x_host, y_host, dev, s, m, c_lo, c_total, iter
         ev[2].record()
         lm = ops.label_margin(x, w, inv_nx, inv_nw, y, c_lo, c_total, s, m, False)
         ev[3].record()
-        rmax, rsum, rarg = ops.forward_rows(xhat, what, lm.z_label, lm.label_local, s, c_lo)
-        lse, arg, zl, loss = ops.finalize_rows(rmax.view(1, B), rsum.view(1, B), rarg.view(1, B), lm.z_label.view(1, B))
+        rmax, rsum, rarg = ops.forward_rows(xhat, what, lm.label_local, s, c_lo)
+        lse, arg, zl, omp, loss = ops.finalize_rows(rmax.view(1, B), rsum.view(1, B), rarg.view(1, B),
+                                                    lm.z_label.view(1, B), y)
         ev[4].record()
-        dxhat, _ = ops.backward(xhat, xhat_t, what, inv_nw, lse, zl, lm.dphi, lm.label_local, s, 1.0 / B, dw_out=dw)
+        dxhat, _ = ops.backward(xhat, xhat_t, what, inv_nw, lse, omp, lm.dphi, lm.label_local, s, 1.0 / B, dw_out=dw)
         ev[5].record()
         ops.normalize_bwd_x(x, inv_nx, dxhat)
         ev[6].record()

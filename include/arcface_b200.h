@@ -77,10 +77,13 @@ int32_t arcface_b200_forward_parts(int32_t B, int64_t C_local, int32_t* n_parts)
 
 /* K2 -- cosine-logit GEMM (tcgen05 / TMEM, TMA-fed) with the margin / scale / online-softmax epilogue.
  * Replaces F.linear (arcface.py:47), the blend + scale (:58-61), CrossEntropyLoss' log-softmax and
- * torch.argmax, without writing the B x C logits.  z[b, c] = s * cos[b, c], except z[b, label] = z_label[b]
- * (pass z_label = label_local = NULL for the eval path: plain scaled cosines, arcface.py:65-67).
- * Writes n_parts x B partial rows: running max, sum exp(z - max), local index of the first max. */
-int32_t arcface_b200_forward_stats(const uint16_t* xhat, const uint16_t* what, const float* z_label,
+ * torch.argmax, without writing the B x C logits.  Streams z[b, c] = s * cos[b, c] over every column
+ * EXCEPT the row's label column (label_local[b], -1 = none on this shard): the label logit is computed
+ * in fp32 by arcface_b200_label_margin and merged exactly by arcface_b200_finalize_rows, which keeps
+ * 1 - p_label free of cancellation.  Pass label_local = NULL for the eval path (plain scaled cosines,
+ * arcface.py:65-67).  Writes n_parts x B partial rows: running max, sum exp(z - max), local index of
+ * the first max. */
+int32_t arcface_b200_forward_stats(const uint16_t* xhat, const uint16_t* what,
                                    const int32_t* label_local, int32_t B, int32_t D, int64_t C_local, float s,
                                    float* part_max, float* part_sum, int32_t* part_arg, int32_t n_parts,
                                    void* stream);
@@ -91,12 +94,16 @@ int32_t arcface_b200_combine_partials(const float* part_max, const float* part_s
                                       int32_t n_parts, int32_t B, int64_t class_offset, float* row_max,
                                       float* row_sum, int64_t* row_arg, void* stream);
 
-/* Merge the per-rank rows ([n_ranks][B], rank-major; n_ranks = 1 on a single GPU) into the softmax
- * statistics and the mean cross-entropy:  lse[b] = M + log S,  argmax[b] (lowest index on ties),
- * z_label_out[b] = sum over ranks of z_label (only the owner is non-zero), loss = mean_b(lse - z_label). */
+/* Merge the per-rank rows of the non-label columns ([n_ranks][B], rank-major; n_ranks = 1 on a single
+ * GPU) with the label logit into the softmax statistics and the mean cross-entropy:
+ *   z_label_out[b] = sum over ranks of rows_z_label (only the owner rank is non-zero)
+ *   lse[b] = log(sum_c exp z[b, c]),  argmax[b] (lowest class id on ties; label = global class ids),
+ *   one_minus_p[b] = 1 - softmax(z)[b, label]  (= S_rest / (S_rest + e^{z_label}), no cancellation),
+ *   loss = mean_b(lse - z_label). */
 int32_t arcface_b200_finalize_rows(const float* rows_max, const float* rows_sum, const int64_t* rows_arg,
-                                   const float* rows_z_label, int32_t n_ranks, int32_t B, float* lse,
-                                   int64_t* argmax, float* z_label_out, float* loss, void* stream);
+                                   const float* rows_z_label, const int64_t* label, int32_t n_ranks, int32_t B,
+                                   float* lse, int64_t* argmax, float* z_label_out, float* one_minus_p,
+                                   float* loss, void* stream);
 
 /* Materialise out[b, c] = scale * cos[b, c] (label column overridden by z_label when given).  Eval path
  * (forward_test, scale = 1) and the debug / small-C path behind the lazy logits object. */
@@ -113,7 +120,7 @@ int32_t arcface_b200_backward_plan(int32_t B, int32_t D, int64_t C_local, int64_
 /* K3 -- backward of the head + cross-entropy (loss.backward() through arcface.py:45-63).
  * Recomputes p = exp(z - lse) tile by tile from the saved row statistics, forms
  *   dC[b, c] = s * grad_scale * p            (c != label)
- *   dC[b, y] = s * grad_scale * (p_y - 1) * dphi[b]
+ *   dC[b, y] = -s * grad_scale * one_minus_p[b] * dphi[b]      (one_minus_p from arcface_b200_finalize_rows)
  * and runs dXhat = dC . What (accumulated into the zeroed dxhat) and dWhat = dC^T . Xhat; the epilogue of
  * the dW GEMM applies the normalise backward  dW[c] = (dWhat[c] - (what[c] . dWhat[c]) what[c]) * inv_nw[c].
  * grad_scale = upstream grad of the mean loss / global batch size; when grad_loss_dev (nullable, DEVICE
@@ -121,7 +128,7 @@ int32_t arcface_b200_backward_plan(int32_t B, int32_t D, int64_t C_local, int64_
  * has to synchronise to read the upstream gradient.  dxhat is this rank's partial (sum over its classes)
  * and is reduce-scattered by the caller when the head is class-sharded. */
 int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* xhat_t, int64_t ld_t, const uint16_t* what,
-                              const float* inv_nw, const float* lse, const float* z_label, const float* dphi,
+                              const float* inv_nw, const float* lse, const float* one_minus_p, const float* dphi,
                               const int32_t* label_local, int32_t B, int32_t D, int64_t C_local, float s,
                               float grad_scale, const float* grad_loss_dev, float* dxhat, float* dw,
                               void* workspace, size_t workspace_bytes, void* stream);

@@ -32,13 +32,14 @@ SIGNATURES = {
     "arcface_b200_forward_parts": (c_int32, [c_int32, c_int64, POINTER(c_int32)]),
     "arcface_b200_forward_stats": (
         c_int32,
-        [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64, c_float, c_void_p, c_void_p, c_void_p,
+        [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64, c_float, c_void_p, c_void_p, c_void_p,
          c_int32, c_void_p],
     ),
     "arcface_b200_combine_partials": (
         c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "arcface_b200_finalize_rows": (
-        c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+        c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                  c_void_p, c_void_p, c_void_p]),
     "arcface_b200_logits": (
         c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64, c_float, c_void_p, c_int64, c_void_p]),
     "arcface_b200_backward_workspace_bytes": (c_int32, [c_int32, c_int32, c_int64, POINTER(c_size_t)]),
@@ -46,7 +47,7 @@ SIGNATURES = {
     "arcface_b200_backward": (
         c_int32,
         [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
-         c_int64, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
+         c_int64, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
     ),
     "arcface_b200_normalize_bwd_x": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "arcface_b200_step_workspace_bytes": (c_int32, [c_int32, c_int32, c_int64, POINTER(c_size_t)]),

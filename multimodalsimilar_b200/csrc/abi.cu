@@ -25,7 +25,7 @@ struct StepPlan {
     size_t bwd_bytes;
     size_t off_x, off_label, off_xhat, off_xhat_t, off_inv_nx, off_what, off_inv_nw, off_t, off_z, off_dphi,
         off_lab_local, off_flag, off_pmax, off_psum, off_parg, off_rmax, off_rsum, off_rarg, off_lse, off_argmax,
-        off_zout, off_loss, off_dxhat, off_dx, off_bwd, total;
+        off_zout, off_omp, off_loss, off_dxhat, off_dx, off_bwd, total;
 };
 
 size_t bump(size_t& cur, size_t bytes) {
@@ -61,6 +61,7 @@ int32_t plan_step(int32_t B, int32_t D, int64_t C, StepPlan* pl) {
     pl->off_lse = bump(cur, b * 4);
     pl->off_argmax = bump(cur, b * 8);
     pl->off_zout = bump(cur, b * 4);
+    pl->off_omp = bump(cur, b * 4);
     pl->off_loss = bump(cur, 4);
     pl->off_dxhat = bump(cur, b * d * 4);
     pl->off_dx = bump(cur, b * d * 4);
@@ -114,6 +115,7 @@ extern "C" int32_t arcface_b200_step_host(const float* x_host, const int64_t* la
     float* lse = reinterpret_cast<float*>(ws + pl.off_lse);
     int64_t* argmax = reinterpret_cast<int64_t*>(ws + pl.off_argmax);
     float* zout = reinterpret_cast<float*>(ws + pl.off_zout);
+    float* omp = reinterpret_cast<float*>(ws + pl.off_omp);
     float* loss = reinterpret_cast<float*>(ws + pl.off_loss);
     float* dxhat = reinterpret_cast<float*>(ws + pl.off_dxhat);
     float* dx = reinterpret_cast<float*>(ws + pl.off_dx);
@@ -131,12 +133,12 @@ extern "C" int32_t arcface_b200_step_host(const float* x_host, const int64_t* la
     if (int32_t rc = arcface_b200_label_margin(x, w_dev, inv_nx, inv_nw, label, B, D, C, 0, C, s, cos_m, sin_m, th, mm,
                                                easy_margin, t_label, z_label, dphi, lab_local, flag, st))
         return rc;
-    if (int32_t rc = arcface_b200_forward_stats(xhat, what, z_label, lab_local, B, D, C, s, pmax, psum, parg,
+    if (int32_t rc = arcface_b200_forward_stats(xhat, what, lab_local, B, D, C, s, pmax, psum, parg,
                                                 pl.n_parts, st))
         return rc;
     if (int32_t rc = arcface_b200_combine_partials(pmax, psum, parg, pl.n_parts, B, 0, rmax, rsum, rarg, st)) return rc;
-    if (int32_t rc = arcface_b200_finalize_rows(rmax, rsum, rarg, z_label, 1, B, lse, argmax, zout, loss, st)) return rc;
-    if (int32_t rc = arcface_b200_backward(xhat, xhat_t, pl.Bp, what, inv_nw, lse, zout, dphi, lab_local, B, D, C, s,
+    if (int32_t rc = arcface_b200_finalize_rows(rmax, rsum, rarg, z_label, label, 1, B, lse, argmax, zout, omp, loss, st)) return rc;
+    if (int32_t rc = arcface_b200_backward(xhat, xhat_t, pl.Bp, what, inv_nw, lse, omp, dphi, lab_local, B, D, C, s,
                                            grad_loss / static_cast<float>(B), nullptr, dxhat, dw_dev, ws + pl.off_bwd,
                                            pl.bwd_bytes, st))
         return rc;

@@ -27,8 +27,7 @@ struct FwdStats {
         int B, D;
         int C;                   // classes of this shard
         float s;
-        const float* z_label;    // nullable
-        const int* label_local;  // nullable
+        const int* label_local;  // nullable: column excluded from the statistics (merged later in fp32)
         float* part_max;
         float* part_sum;
         int* part_arg;
@@ -69,7 +68,6 @@ struct FwdStats {
         float run_max, sum0, sum1, sum2, sum3;
         int run_arg;
         int lab;
-        float zl;
         __device__ Epi(const Params& prm, uint8_t*, int ew, int lane, int cta) : p(prm) {
             const int m_tile = cta % p.m_tiles;
             g = cta / p.m_tiles;
@@ -79,11 +77,7 @@ struct FwdStats {
             sum0 = sum1 = sum2 = sum3 = 0.f;
             run_arg = 0;
             lab = -1;
-            zl = 0.f;
-            if (active && p.label_local != nullptr) {
-                lab = p.label_local[row];
-                zl = p.z_label[row];
-            }
+            if (active && p.label_local != nullptr) lab = p.label_local[row];
         }
         __device__ void tile(const Tile& t, uint32_t taddr) {
             const float s = p.s;
@@ -103,14 +97,16 @@ struct FwdStats {
                         if (col0 + j >= p.C) z[j] = -INFINITY;
                 }
                 const int lr = lab - col0;
-                if (lr >= 0 && lr < 32) {  // at most once per row: margin-adjusted label logit
+                if (lr >= 0 && lr < 32) {  // at most once per row: the label column is left out here and
+                                           // merged exactly (fp32 margin logit) by finalize_rows
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (j == lr) z[j] = zl;
+                        if (j == lr) z[j] = -INFINITY;
                 }
                 float cm = z[0];
 #pragma unroll
                 for (int j = 1; j < 32; ++j) cm = fmaxf(cm, z[j]);
+                if (cm == -INFINITY) continue;  // nothing but the excluded label / padding in this chunk
                 if (cm > run_max) {  // strict: an equal later maximum never displaces the first one
                     int first = 31;
 #pragma unroll
@@ -250,14 +246,12 @@ extern "C" int32_t arcface_b200_forward_parts(int32_t B, int64_t C_local, int32_
     return ARCFACE_B200_OK;
 }
 
-extern "C" int32_t arcface_b200_forward_stats(const uint16_t* xhat, const uint16_t* what, const float* z_label,
+extern "C" int32_t arcface_b200_forward_stats(const uint16_t* xhat, const uint16_t* what,
                                               const int32_t* label_local, int32_t B, int32_t D, int64_t C_local,
                                               float s, float* part_max, float* part_sum, int32_t* part_arg,
                                               int32_t n_parts, void* stream) {
     if (int32_t rc = check_arch()) return rc;
     AB_REQUIRE(xhat && what && part_max && part_sum && part_arg, ARCFACE_B200_E_ARG, "forward_stats: null pointer");
-    AB_REQUIRE((z_label == nullptr) == (label_local == nullptr), ARCFACE_B200_E_ARG,
-               "forward_stats: z_label and label_local must both be given or both be null");
     AB_REQUIRE(s > 0.f, ARCFACE_B200_E_ARG, "forward_stats: scale s must be positive");
     if (int32_t rc = check_gemm_shape("forward_stats", B, D, C_local)) return rc;
     FwdStats::Params p;
@@ -265,7 +259,7 @@ extern "C" int32_t arcface_b200_forward_stats(const uint16_t* xhat, const uint16
     AB_REQUIRE(n_parts == p.groups, ARCFACE_B200_E_WORKSPACE, "forward_stats: n_parts=%d, expected %d", n_parts,
                p.groups);
     p.B = B; p.D = D; p.C = static_cast<int>(C_local); p.s = s;
-    p.z_label = z_label; p.label_local = label_local;
+    p.label_local = label_local;
     p.part_max = part_max; p.part_sum = part_sum; p.part_arg = part_arg;
     CUtensorMap tmA, tmB;
     if (int32_t rc = make_tmap_kmajor(&tmA, xhat, D, B, D, BLOCK_M)) return rc;

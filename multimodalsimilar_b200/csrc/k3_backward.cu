@@ -46,7 +46,7 @@ struct BwdDC {
         float coef;     // s * grad_scale
         const float* grad_dev;  // nullable device scalar multiplied into coef
         const float* lse;
-        const float* z_label;
+        const float* one_minus_p;  // 1 - p_label, cancellation-free (finalize_rows)
         const float* dphi;
         const int* label_local;
         __nv_bfloat16* dct;  // [c_blocks * 128][Bp]
@@ -68,7 +68,7 @@ struct BwdDC {
                 const int y = p.label_local[b];
                 lse2[b] = l * LOG2E_B;
                 lab[b] = y;
-                dlab[b] = (y >= 0) ? coef * (expf(p.z_label[b] - l) - 1.f) * p.dphi[b] : 0.f;
+                dlab[b] = (y >= 0) ? -coef * p.one_minus_p[b] * p.dphi[b] : 0.f;
             } else {
                 lse2[b] = INFINITY;
                 lab[b] = -1;
@@ -371,12 +371,12 @@ extern "C" int32_t arcface_b200_backward_plan(int32_t B, int32_t D, int64_t C_lo
 
 extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* xhat_t, int64_t ld_t,
                                          const uint16_t* what, const float* inv_nw, const float* lse,
-                                         const float* z_label, const float* dphi, const int32_t* label_local,
+                                         const float* one_minus_p, const float* dphi, const int32_t* label_local,
                                          int32_t B, int32_t D, int64_t C_local, float s, float grad_scale,
                                          const float* grad_loss_dev, float* dxhat, float* dw, void* workspace,
                                          size_t workspace_bytes, void* stream) {
     if (int32_t rc = check_arch()) return rc;
-    AB_REQUIRE(xhat && xhat_t && what && inv_nw && lse && z_label && dphi && label_local && dxhat && dw && workspace,
+    AB_REQUIRE(xhat && xhat_t && what && inv_nw && lse && one_minus_p && dphi && label_local && dxhat && dw && workspace,
                ARCFACE_B200_E_ARG, "backward: null pointer");
     AB_REQUIRE(B >= 1 && B <= ARCFACE_B200_MAX_BATCH, ARCFACE_B200_E_SHAPE, "backward: B=%d outside [1, %d]", B,
                ARCFACE_B200_MAX_BATCH);
@@ -418,7 +418,7 @@ extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* x
             p.B = B; p.D = D; p.C = C; p.Bp = pl.Bp;
             p.c_begin = static_cast<int>(c0); p.c_blocks = c_blocks; p.n_tiles = n_tiles;
             p.s_log2e = s * LOG2E_B; p.coef = s * grad_scale; p.grad_dev = grad_loss_dev;
-            p.lse = lse; p.z_label = z_label; p.dphi = dphi; p.label_local = label_local;
+            p.lse = lse; p.one_minus_p = one_minus_p; p.dphi = dphi; p.label_local = label_local;
             p.dct = dct; p.q = q;
             const int grid = c_blocks < nsm ? c_blocks : nsm;
             if (int32_t rc = launch_gemm<BwdDC>(tm_w_k, tm_x_k, p, grid, BwdDC::extra_bytes(n_tiles), st)) return rc;

@@ -175,32 +175,51 @@ __global__ void combine_partials_kernel(const float* __restrict__ pm, const floa
     row_arg[b] = static_cast<int64_t>(A) + class_offset;
 }
 
+// Merges the per-rank statistics of the NON-label columns with the fp32 label logit.  Keeping the label
+// out of the streamed sum makes 1 - p_label = S_rest / (S_rest + e_label) free of cancellation, which
+// matters once the head is trained (p_label -> 1) -- the reference's fp32 softmax - one_hot loses those
+// digits.
 __global__ void __launch_bounds__(256)
 finalize_rows_kernel(const float* __restrict__ rm, const float* __restrict__ rs, const int64_t* __restrict__ ra,
-                     const float* __restrict__ rz, int n_ranks, int B, float* __restrict__ lse,
-                     int64_t* __restrict__ argmax, float* __restrict__ z_out, float* __restrict__ loss) {
+                     const float* __restrict__ rz, const int64_t* __restrict__ label, int n_ranks, int B,
+                     float* __restrict__ lse, int64_t* __restrict__ argmax, float* __restrict__ z_out,
+                     float* __restrict__ one_minus_p, float* __restrict__ loss) {
     __shared__ float red[256];
     float acc = 0.f;
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
-        float M = -INFINITY, S = 0.f, Z = 0.f;
-        int64_t A = 0;
+        float Mx = -INFINITY, Sx = 0.f, Z = 0.f;
+        int64_t Ax = 0;
         for (int r = 0; r < n_ranks; ++r) {
             const float m = rm[static_cast<int64_t>(r) * B + b];
             const float s = rs[static_cast<int64_t>(r) * B + b];
-            if (m > M) {
-                S = S * expf(M - m) + s;
-                M = m;
-                A = ra[static_cast<int64_t>(r) * B + b];
+            if (m > Mx) {  // strict: the lower rank (lower class range) keeps ties
+                Sx = Sx * expf(Mx - m) + s;
+                Mx = m;
+                Ax = ra[static_cast<int64_t>(r) * B + b];
             } else if (m > -INFINITY) {
-                S += s * expf(m - M);
+                Sx += s * expf(m - Mx);
             }
             Z += rz[static_cast<int64_t>(r) * B + b];
         }
-        const float l = M + logf(S);
+        const int64_t y = label[b];
+        float l, omp, ce;
+        if (Z >= Mx) {  // label logit is the row maximum
+            const float ex = (Mx > -INFINITY) ? Sx * expf(Mx - Z) : 0.f;
+            ce = log1pf(ex);
+            l = Z + ce;
+            omp = ex / (1.f + ex);
+        } else {
+            const float ey = expf(Z - Mx);
+            const float S = Sx + ey;
+            l = Mx + logf(S);
+            ce = (Mx - Z) + logf(S);
+            omp = Sx / S;
+        }
         lse[b] = l;
-        argmax[b] = A;
+        argmax[b] = (Z > Mx || (Z == Mx && y < Ax)) ? y : Ax;
         z_out[b] = Z;
-        acc += l - Z;
+        one_minus_p[b] = omp;
+        acc += ce;
     }
     red[threadIdx.x] = acc;
     __syncthreads();
@@ -304,14 +323,17 @@ extern "C" int32_t arcface_b200_combine_partials(const float* part_max, const fl
 }
 
 extern "C" int32_t arcface_b200_finalize_rows(const float* rows_max, const float* rows_sum, const int64_t* rows_arg,
-                                              const float* rows_z_label, int32_t n_ranks, int32_t B, float* lse,
-                                              int64_t* argmax, float* z_label_out, float* loss, void* stream) {
+                                              const float* rows_z_label, const int64_t* label, int32_t n_ranks,
+                                              int32_t B, float* lse, int64_t* argmax, float* z_label_out,
+                                              float* one_minus_p, float* loss, void* stream) {
     if (int32_t rc = check_arch()) return rc;
-    AB_REQUIRE(rows_max && rows_sum && rows_arg && rows_z_label && lse && argmax && z_label_out && loss,
+    AB_REQUIRE(rows_max && rows_sum && rows_arg && rows_z_label && label && lse && argmax && z_label_out &&
+                   one_minus_p && loss,
                ARCFACE_B200_E_ARG, "finalize_rows: null pointer");
     AB_REQUIRE(n_ranks >= 1 && B >= 1, ARCFACE_B200_E_SHAPE, "finalize_rows: bad shape");
     finalize_rows_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(rows_max, rows_sum, rows_arg, rows_z_label,
-                                                                          n_ranks, B, lse, argmax, z_label_out, loss);
+                                                                          label, n_ranks, B, lse, argmax, z_label_out,
+                                                                          one_minus_p, loss);
     AB_CHECK_CUDA(cudaGetLastError());
     return ARCFACE_B200_OK;
 }

@@ -39,22 +39,22 @@ class ArcFaceCEFunction(torch.autograd.Function):
         xhat, inv_nx, xhat_t = ops.normalize_cast(x, want_transpose=True)
         what, inv_nw, _ = ops.normalize_cast(weight)
         lm = ops.label_margin(x, weight, inv_nx, inv_nw, label, 0, C, s, m, easy_margin)
-        rmax, rsum, rarg = ops.forward_rows(xhat, what, lm.z_label, lm.label_local, s, 0)
-        lse, argmax, z_label, loss = ops.finalize_rows(rmax.view(1, B), rsum.view(1, B), rarg.view(1, B),
-                                                       lm.z_label.view(1, B))
+        rmax, rsum, rarg = ops.forward_rows(xhat, what, lm.label_local, s, 0)
+        lse, argmax, _z, omp, loss = ops.finalize_rows(rmax.view(1, B), rsum.view(1, B), rarg.view(1, B),
+                                                       lm.z_label.view(1, B), label)
         if validate_labels and int(lm.bad_flag.item()) != 0:
             raise IndexError("ArcMarginProduct: a label is outside [0, %d)" % C)
-        ctx.save_for_backward(x, inv_nx, xhat, xhat_t, what, inv_nw, lse, z_label, lm.dphi, lm.label_local)
+        ctx.save_for_backward(x, inv_nx, xhat, xhat_t, what, inv_nw, lse, omp, lm.dphi, lm.label_local)
         ctx.s = s
         ctx.mark_non_differentiable(argmax)
         return loss, argmax
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_argmax):
-        x, inv_nx, xhat, xhat_t, what, inv_nw, lse, z_label, dphi, label_local = ctx.saved_tensors
+        x, inv_nx, xhat, xhat_t, what, inv_nw, lse, omp, dphi, label_local = ctx.saved_tensors
         B = x.shape[0]
         g = grad_loss.to(torch.float32).contiguous()
-        dxhat, dw = ops.backward(xhat, xhat_t, what, inv_nw, lse, z_label, dphi, label_local, ctx.s, 1.0 / B,
+        dxhat, dw = ops.backward(xhat, xhat_t, what, inv_nw, lse, omp, dphi, label_local, ctx.s, 1.0 / B,
                                  grad_loss_dev=g)
         dx = ops.normalize_bwd_x(x, inv_nx, dxhat) if ctx.needs_input_grad[0] else None
         return dx, (dw if ctx.needs_input_grad[1] else None), None, None, None, None, None
@@ -249,7 +249,7 @@ class ArcMarginProduct(nn.Module):
         x = x.to(torch.float32).contiguous()
         xhat, _, _ = ops.normalize_cast(x)
         what, _, _ = ops.normalize_cast(self.weight.detach().contiguous())
-        rmax, _, rarg = ops.forward_rows(xhat, what, None, None, 1.0, 0)
+        rmax, _, rarg = ops.forward_rows(xhat, what, None, 1.0, 0)
         return rarg, rmax
 
     def extra_repr(self):

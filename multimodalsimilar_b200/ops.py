@@ -99,8 +99,9 @@ def forward_parts(B: int, c_local: int) -> int:
     return n.value
 
 
-def forward_rows(xhat, what, z_label, label_local, s: float, class_offset: int = 0):
-    """K2 + per-shard combine.  Returns (row_max fp32 [B], row_sum fp32 [B], row_arg int64 [B])."""
+def forward_rows(xhat, what, label_local, s: float, class_offset: int = 0):
+    """K2 + per-shard combine over every column except the row's label column (label_local, or None for
+    the eval path).  Returns (row_max fp32 [B], row_sum fp32 [B], row_arg int64 [B])."""
     _req(xhat, torch.bfloat16, "xhat")
     _req(what, torch.bfloat16, "what")
     B, D = xhat.shape
@@ -110,7 +111,7 @@ def forward_rows(xhat, what, z_label, label_local, s: float, class_offset: int =
     pmax = torch.empty((n_parts, B), dtype=torch.float32, device=dev)
     psum = torch.empty((n_parts, B), dtype=torch.float32, device=dev)
     parg = torch.empty((n_parts, B), dtype=torch.int32, device=dev)
-    _lib.call("arcface_b200_forward_stats", _ptr(xhat), _ptr(what), _ptr(z_label), _ptr(label_local), B, D, C, s,
+    _lib.call("arcface_b200_forward_stats", _ptr(xhat), _ptr(what), _ptr(label_local), B, D, C, s,
               _ptr(pmax), _ptr(psum), _ptr(parg), n_parts, _stream())
     rmax = torch.empty(B, dtype=torch.float32, device=dev)
     rsum = torch.empty(B, dtype=torch.float32, device=dev)
@@ -120,18 +121,21 @@ def forward_rows(xhat, what, z_label, label_local, s: float, class_offset: int =
     return rmax, rsum, rarg
 
 
-def finalize_rows(rows_max, rows_sum, rows_arg, rows_z):
-    """Merge [R, B] per-rank rows -> (lse [B], argmax int64 [B], z_label [B], loss [])."""
+def finalize_rows(rows_max, rows_sum, rows_arg, rows_z, label):
+    """Merge [R, B] per-rank rows of the non-label columns with the label logits ->
+    (lse [B], argmax int64 [B], z_label [B], one_minus_p [B], loss [])."""
     R, B = rows_max.shape
     dev = rows_max.device
     lse = torch.empty(B, dtype=torch.float32, device=dev)
     arg = torch.empty(B, dtype=torch.int64, device=dev)
     z = torch.empty(B, dtype=torch.float32, device=dev)
+    omp = torch.empty(B, dtype=torch.float32, device=dev)
     loss = torch.empty((), dtype=torch.float32, device=dev)
     _lib.call("arcface_b200_finalize_rows", _ptr(_req(rows_max, torch.float32, "rows_max")),
               _ptr(_req(rows_sum, torch.float32, "rows_sum")), _ptr(_req(rows_arg, torch.int64, "rows_arg")),
-              _ptr(_req(rows_z, torch.float32, "rows_z")), R, B, _ptr(lse), _ptr(arg), _ptr(z), _ptr(loss), _stream())
-    return lse, arg, z, loss
+              _ptr(_req(rows_z, torch.float32, "rows_z")), _ptr(_req(label, torch.int64, "label")), R, B, _ptr(lse),
+              _ptr(arg), _ptr(z), _ptr(omp), _ptr(loss), _stream())
+    return lse, arg, z, omp, loss
 
 
 def logits(xhat, what, z_label, label_local, scale: float) -> torch.Tensor:
@@ -160,7 +164,7 @@ def backward_plan(B: int, D: int, c_local: int):
     return cc.value, n.value
 
 
-def backward(xhat, xhat_t, what, inv_nw, lse, z_label, dphi, label_local, s: float, grad_scale: float,
+def backward(xhat, xhat_t, what, inv_nw, lse, one_minus_p, dphi, label_local, s: float, grad_scale: float,
              grad_loss_dev=None, dw_out=None):
     """K3.  Returns (dxhat fp32 [B, D] partial over this shard's classes, dW fp32 [C_local, D])."""
     B, D = xhat.shape
@@ -174,7 +178,7 @@ def backward(xhat, xhat_t, what, inv_nw, lse, z_label, dphi, label_local, s: flo
     if grad_loss_dev is not None:
         grad_loss_dev = _req(grad_loss_dev.reshape(1), torch.float32, "grad_loss")
     _lib.call("arcface_b200_backward", _ptr(xhat), _ptr(xhat_t), xhat_t.shape[1], _ptr(what), _ptr(inv_nw), _ptr(lse),
-              _ptr(z_label), _ptr(dphi), _ptr(label_local), B, D, C, s, grad_scale, _ptr(grad_loss_dev), _ptr(dxhat),
+              _ptr(one_minus_p), _ptr(dphi), _ptr(label_local), B, D, C, s, grad_scale, _ptr(grad_loss_dev), _ptr(dxhat),
               _ptr(dw), _ptr(ws), nbytes, _stream())
     return dxhat, dw
 

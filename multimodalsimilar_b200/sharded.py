@@ -81,11 +81,11 @@ class ShardedArcFaceCE(torch.autograd.Function):
         what, inv_nw, _ = K.normalize_cast(w_shard)
         lm = K.label_margin(x_all, w_shard, inv_nx, inv_nw, y_all, head.class_lo, head.out_feature, float(head.s),
                             float(head.m), bool(head.easy_margin))
-        rmax, rsum, rarg = K.forward_rows(xhat, what, lm.z_label, lm.label_local, float(head.s), head.class_lo)
+        rmax, rsum, rarg = K.forward_rows(xhat, what, lm.label_local, float(head.s), head.class_lo)
         packed = _all_gather_rows(_pack_rows(rmax, rsum, lm.z_label, rarg), group)
         rows_max, rows_sum, rows_z, rows_arg = _unpack_rows(packed, B)
-        lse, argmax, z_label, loss = K.finalize_rows(rows_max, rows_sum, rows_arg, rows_z)
-        ctx.save_for_backward(x_local, inv_nx, xhat, xhat_t, what, inv_nw, lse, z_label, lm.dphi, lm.label_local)
+        lse, argmax, _z, omp, loss = K.finalize_rows(rows_max, rows_sum, rows_arg, rows_z, y_all)
+        ctx.save_for_backward(x_local, inv_nx, xhat, xhat_t, what, inv_nw, lse, omp, lm.dphi, lm.label_local)
         ctx.head = head
         ctx.B = B
         argmax_local = argmax[rank * b_loc:(rank + 1) * b_loc].contiguous()
@@ -94,13 +94,13 @@ class ShardedArcFaceCE(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_argmax):
-        x_local, inv_nx, xhat, xhat_t, what, inv_nw, lse, z_label, dphi, label_local = ctx.saved_tensors
+        x_local, inv_nx, xhat, xhat_t, what, inv_nw, lse, omp, dphi, label_local = ctx.saved_tensors
         head = ctx.head
         K, group = head.kernels, head.process_group
         rank = dist.get_rank(group)
         b_loc = x_local.shape[0]
         g = grad_loss.to(torch.float32).contiguous()
-        dxhat_part, dw = K.backward(xhat, xhat_t, what, inv_nw, lse, z_label, dphi, label_local, float(head.s),
+        dxhat_part, dw = K.backward(xhat, xhat_t, what, inv_nw, lse, omp, dphi, label_local, float(head.s),
                                     1.0 / ctx.B, grad_loss_dev=g)
         dx = None
         if ctx.needs_input_grad[0]:

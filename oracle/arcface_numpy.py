@@ -145,7 +145,8 @@ def backward(x, w, label, s=64.0, m=0.40, easy_margin=False, grad_loss=1.0, dtyp
     z = forward_logits(x, w, label, s, m, easy_margin, dtype)
     p = np.exp(log_softmax(z))
     g = p
-    g[rows, label] -= 1.0
+    g[rows, label] = 0.0
+    g[rows, label] = -np.sum(g, axis=1)  # p_y - 1 = -(sum of the other probabilities): no cancellation
     g *= grad_loss / B
     dcos = g * s
     t = cosine[rows, label]

@@ -37,44 +37,45 @@ def label_margin(x, w, inv_nx, inv_nw, label, class_offset, c_total, s, m, easy_
     )
 
 
-def _local_logits(xhat, what, z_label, label_local, s):
+def forward_rows(xhat, what, label_local, s, class_offset=0):
+    """Statistics over every local column except the row's label column (merged later by finalize_rows)."""
     z = (xhat @ what.t()) * s
-    if z_label is not None:
+    if label_local is not None:
         rows = torch.nonzero(label_local >= 0).flatten()
-        z[rows, label_local[rows].long()] = z_label[rows].double()
-    return z
-
-
-def forward_rows(xhat, what, z_label, label_local, s, class_offset=0):
-    z = _local_logits(xhat, what, z_label, label_local, s)
-    rmax, rarg = z.max(dim=1)
-    # torch.max returns an arbitrary index on ties for some backends; take the first maximum explicitly
-    rarg = (z == rmax[:, None]).int().argmax(dim=1)
-    rsum = (z - rmax[:, None]).exp().sum(1)
+        z[rows, label_local[rows].long()] = float("-inf")
+    rmax = z.max(dim=1).values
+    rarg = (z == rmax[:, None]).int().argmax(dim=1)  # first maximum
+    rsum = torch.where(torch.isinf(rmax), torch.zeros_like(rmax), (z - rmax[:, None]).exp().sum(1))
     return rmax.float(), rsum.float(), (rarg + class_offset).long()
 
 
-def finalize_rows(rows_max, rows_sum, rows_arg, rows_z):
-    M, r = rows_max.double().max(dim=0)
-    r = (rows_max.double() == M[None]).int().argmax(dim=0)  # lowest rank (= lowest class range) on ties
-    S = (rows_sum.double() * (rows_max.double() - M[None]).exp()).sum(0)
+def finalize_rows(rows_max, rows_sum, rows_arg, rows_z, label):
+    rm = rows_max.double()
+    Mx = rm.max(dim=0).values
+    r = (rm == Mx[None]).int().argmax(dim=0)  # lowest rank (= lowest class range) on ties
+    scale = torch.where(torch.isinf(rm), torch.zeros_like(rm), (rm - Mx[None]).exp())
+    Sx = (rows_sum.double() * scale).sum(0)
+    Ax = rows_arg.gather(0, r[None]).squeeze(0)
+    Z = rows_z.double().sum(0)
+    M = torch.maximum(Mx, Z)
+    ex = torch.where(torch.isinf(Mx), torch.zeros_like(Mx), Sx * (Mx - M).exp())
+    ey = (Z - M).exp()
+    S = ex + ey
     lse = M + S.log()
-    z = rows_z.double().sum(0)
-    arg = rows_arg.gather(0, r[None]).squeeze(0)
-    return lse.float(), arg, z.float(), (lse - z).mean().float()
+    omp = ex / S
+    arg = torch.where((Z > Mx) | ((Z == Mx) & (label < Ax)), label, Ax)
+    return lse.float(), arg, Z.float(), omp.float(), (lse - Z).mean().float()
 
 
-def backward(xhat, xhat_t, what, inv_nw, lse, z_label, dphi, label_local, s, grad_scale, grad_loss_dev=None,
+def backward(xhat, xhat_t, what, inv_nw, lse, one_minus_p, dphi, label_local, s, grad_scale, grad_loss_dev=None,
              dw_out=None):
     g = grad_scale * (float(grad_loss_dev) if grad_loss_dev is not None else 1.0)
     cos = xhat @ what.t()
-    z = cos * s
+    p = (cos * s - lse.double()[:, None]).exp()
+    dc = p * (s * g)
     rows = torch.nonzero(label_local >= 0).flatten()
     cols = label_local[rows].long()
-    z[rows, cols] = z_label[rows].double()
-    p = (z - lse.double()[:, None]).exp()
-    dc = p * (s * g)
-    dc[rows, cols] = (p[rows, cols] - 1.0) * (s * g) * dphi[rows].double()
+    dc[rows, cols] = -one_minus_p[rows].double() * (s * g) * dphi[rows].double()
     dxhat = dc @ what
     dwh = dc.t() @ xhat
     q = (dc * cos).sum(0)

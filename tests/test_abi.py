@@ -32,6 +32,15 @@ def test_every_declared_symbol_is_exported_and_bound():
     assert sorted(_lib.SIGNATURES) == names
 
 
+def test_ctypes_arity_matches_header():
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    for name, params in re.findall(r"\b(arcface_b200_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src):
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert len(_lib.SIGNATURES[name][1]) == n, "%s: header has %d parameters, ctypes table %d" % (
+            name, n, len(_lib.SIGNATURES[name][1]))
+
+
 def test_version_and_error_string():
     lib = _lib.load()
     major, minor = ctypes.c_int32(-1), ctypes.c_int32(-1)

@@ -156,15 +156,23 @@ def test_fused_statistics_match_materialised_logits(B, D, C, s):
     what, inv_nw, _ = ops.normalize_cast(wt)
     lm = ops.label_margin(xt, wt, inv_nx, inv_nw, yt, 0, C, s, 0.4, False)
     z = ops.logits(xhat, what, lm.z_label, lm.label_local, s)
-    rmax, rsum, rarg = ops.forward_rows(xhat, what, lm.z_label, lm.label_local, s, 0)
-    lse, arg, zl, loss = ops.finalize_rows(rmax.view(1, B), rsum.view(1, B), rarg.view(1, B), lm.z_label.view(1, B))
-    assert torch.equal(rmax, z.max(dim=1).values)          # same MMA sequence -> bit-identical cosines
+    rmax, rsum, rarg = ops.forward_rows(xhat, what, lm.label_local, s, 0)
+    lse, arg, zl, omp, loss = ops.finalize_rows(rmax.view(1, B), rsum.view(1, B), rarg.view(1, B),
+                                                lm.z_label.view(1, B), yt)
+    # the streamed statistics leave the label column out; same MMA sequence -> bit-identical cosines
+    z_rest = z.clone()
+    z_rest[torch.arange(B), yt] = float("-inf")
+    assert torch.equal(rmax, z_rest.max(dim=1).values)
     first = (z == z.max(dim=1, keepdim=True).values).int().argmax(dim=1)
     assert torch.equal(arg, first)
+    assert torch.equal(zl, z[torch.arange(B), yt])
     ref_lse = torch.logsumexp(z.double(), dim=1)
     assert float((lse.double() - ref_lse).abs().max()) <= 2e-4
     ref_loss = float((ref_lse - z.double()[torch.arange(B), yt]).mean())
     assert abs(float(loss) - ref_loss) <= 1e-4 * max(1.0, abs(ref_loss))
+    ref_omp = 1.0 - (z.double()[torch.arange(B), yt] - ref_lse).exp()
+    ref_omp_stable = torch.logsumexp(z_rest.double(), dim=1).sub(ref_lse).exp() if C > 1 else ref_omp
+    assert float(((omp.double() - ref_omp_stable).abs() / ref_omp_stable.clamp_min(1e-30)).max()) <= 1e-3
     assert int(lm.bad_flag.item()) == 0
     assert torch.equal(lm.label_local.long(), yt)
 

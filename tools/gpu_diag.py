@@ -62,8 +62,9 @@ def stage_stats():
     c = _setup(200, 64, 3000)
     torch, ops, onp, np = c["torch"], c["ops"], c["onp"], c["np"]
     B = c["B"]
-    rmax, rsum, rarg = ops.forward_rows(c["xhat"], c["what"], c["lm"].z_label, c["lm"].label_local, c["s"], 0)
-    lse, arg, zl, loss = ops.finalize_rows(rmax.view(1, B), rsum.view(1, B), rarg.view(1, B), c["lm"].z_label.view(1, B))
+    rmax, rsum, rarg = ops.forward_rows(c["xhat"], c["what"], c["lm"].label_local, c["s"], 0)
+    lse, arg, zl, omp, loss = ops.finalize_rows(rmax.view(1, B), rsum.view(1, B), rarg.view(1, B),
+                                                c["lm"].z_label.view(1, B), c["yt"])
     torch.cuda.synchronize()
     z = onp.forward_logits(c["x"], c["w"], c["y"], c["s"], c["m"], False, dtype=np.float64)
     zmax, rlse = onp.row_stats(z)
@@ -76,9 +77,10 @@ def stage_stats():
 def _bwd(c):
     torch, ops = c["torch"], c["ops"]
     B = c["B"]
-    rmax, rsum, rarg = ops.forward_rows(c["xhat"], c["what"], c["lm"].z_label, c["lm"].label_local, c["s"], 0)
-    lse, arg, zl, loss = ops.finalize_rows(rmax.view(1, B), rsum.view(1, B), rarg.view(1, B), c["lm"].z_label.view(1, B))
-    dxhat, dw = ops.backward(c["xhat"], c["xhat_t"], c["what"], c["inv_nw"], lse, zl, c["lm"].dphi, c["lm"].label_local,
+    rmax, rsum, rarg = ops.forward_rows(c["xhat"], c["what"], c["lm"].label_local, c["s"], 0)
+    lse, arg, zl, omp, loss = ops.finalize_rows(rmax.view(1, B), rsum.view(1, B), rarg.view(1, B),
+                                                c["lm"].z_label.view(1, B), c["yt"])
+    dxhat, dw = ops.backward(c["xhat"], c["xhat_t"], c["what"], c["inv_nw"], lse, omp, c["lm"].dphi, c["lm"].label_local,
                              c["s"], 1.0 / B)
     dx = ops.normalize_bwd_x(c["xt"], c["inv_nx"], dxhat)
     torch.cuda.synchronize()
