@@ -109,6 +109,47 @@ def stage_bwd_dx():
             shape, np.abs(gdx - rdx).max(), np.linalg.norm(gdx - rdx) / np.linalg.norm(rdx), np.abs(rdx).max()))
 
 
+def stage_full():
+    """Large shapes against the fp32 torch restatement on the GPU; prints where the errors sit."""
+    import numpy as np
+    import torch
+    import multimodalsimilar_b200 as mm
+    from oracle import arcface_numpy as onp
+    from tests.test_gpu_parity import torch_oracle
+    for (B, D, C, s, m) in [(256, 1792, 100000, 64.0, 0.2), (128, 64, 600000, 64.0, 0.4), (512, 512, 200000, 64.0, 0.5)]:
+        for trained in (False, True):
+            x, w, y = onp.synthetic_inputs(B, D, C, seed=5, trained_like=trained)
+            head = mm.ArcMarginProduct(D, 8, s=s, m=m)
+            head.out_feature = C
+            head.weight = torch.nn.Parameter(torch.from_numpy(w).cuda())
+            xt = torch.from_numpy(x).cuda().requires_grad_(True)
+            yt = torch.from_numpy(y).cuda()
+            loss, pred = head.loss(xt, yt)
+            loss.backward()
+            torch.cuda.synchronize()
+            rloss, _rp, z, rdx, rdw = torch_oracle(xt.detach(), head.weight.detach(), yt, s, m, False)
+            dw, dx = head.weight.grad, xt.grad
+            ew = (dw - rdw).abs()
+            ex = (dx - rdx).abs()
+            print("full B=%d D=%d C=%d trained=%s: loss %.6f ref %.6f | dx max err %.3e rel fro %.3e (max |dx| %.3e) | "
+                  "dw max err %.3e rel fro %.3e (max |dw| %.3e) nan %d" % (
+                      B, D, C, trained, float(loss), float(rloss), float(ex.max()), float((dx - rdx).norm() / rdx.norm()),
+                      float(rdx.abs().max()), float(ew.max()), float((dw - rdw).norm() / rdw.norm()),
+                      float(rdw.abs().max()), int(torch.isnan(dw).sum())))
+            thr = max(1e-3 * float(rdw.abs().max()), 10 * float(ew.median()))
+            bad = torch.nonzero(ew > max(thr, 1e-9))
+            if bad.numel():
+                rows = bad[:, 0].unique()
+                print("   dw: %d bad elems in %d rows; first rows %s ; rows %% 128: %s ; cols min/max %d/%d ; label rows? %s" % (
+                    bad.shape[0], rows.numel(), rows[:12].tolist(), (rows % 128).unique()[:20].tolist(),
+                    int(bad[:, 1].min()), int(bad[:, 1].max()),
+                    bool(torch.isin(rows, yt).all())))
+                r0 = int(rows[0])
+                print("   row %d: got %s ref %s" % (r0, dw[r0, :4].tolist(), rdw[r0, :4].tolist()))
+            del head, z, rdw, rdx, dw, dx
+            torch.cuda.empty_cache()
+
+
 def stage_module():
     import __graft_entry__ as g
     g.smoke()
