@@ -299,8 +299,10 @@ def test_full_size_against_gpu_oracle_and_invariants(B, D, C, s, m, trained):
     xt2 = _t(x).requires_grad_(True)
     l2, _ = head.loss(xt2, yt)
     (l2 * 3.0).backward()
-    assert float((xt2.grad - 3.0 * dx).norm() / (3.0 * dx.norm())) <= 1e-3
-    assert float((head.weight.grad - 3.0 * dw).norm() / (3.0 * dw.norm())) <= 1e-3
+    # (dC is rounded to bf16 after the scale is applied: 3x is not a power of two, so the two runs round
+    # differently, by at most one bf16 ulp = 2^-8 per element)
+    assert float((xt2.grad - 3.0 * dx).norm() / (3.0 * dx.norm())) <= 6e-3
+    assert float((head.weight.grad - 3.0 * dw).norm() / (3.0 * dw.norm())) <= 6e-3
 
 
 # ----------------------------------------------------------------------------- host-buffer C-ABI step
