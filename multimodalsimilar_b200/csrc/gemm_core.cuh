@@ -6,6 +6,8 @@
 //   warps 4-7: epilogue      (tcgen05.ld 32x32b, thread i owns accumulator row i of the 128-row tile)
 // The accumulator is double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i
 // overlaps the MMAs of tile i+1.  A policy class supplies the tile schedule and the epilogue.
+// Epilogues that write tiles stage them through swizzled shared memory and leave through TMA stores
+// (StoreStager), so every global write is a full 128-byte line.
 //
 // Replaces, in the reference, the cuBLAS/MKL SGEMMs behind F.linear (arcface.py:47) and the two
 // autograd matmuls of loss.backward().
@@ -19,6 +21,7 @@ constexpr int BLOCK_K = 64;  // bf16 elements: one 128-byte swizzle span
 constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 256;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int STAGING_BYTES = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x (32 rows x 128 B)
 
 struct Tile {
     int m0;       // first accumulator row (TMA coordinate of operand A along M)
@@ -27,6 +30,16 @@ struct Tile {
     int kb0;      // first K element for operand B
     int kblocks;  // number of BLOCK_K slices (>= 1)
     int aux;      // policy-defined
+};
+
+// What an epilogue object gets to see.
+struct EpiCtx {
+    uint8_t* extra;          // policy-defined shared memory (filled by P::prologue)
+    uint8_t* staging;        // STAGING_BYTES of 1024-aligned shared memory (only if P::STAGING)
+    const CUtensorMap* tmC;  // output tensor map (only if P::STAGING)
+    int ew;                  // epilogue warp 0..3 == TMEM lane quadrant
+    int lane;
+    int cta;
 };
 
 template <int BLOCK_N>
@@ -38,9 +51,43 @@ struct SmemLayout {
 // Dynamic shared memory needed by gemm_kernel<P> (includes 1 KB of alignment slack).
 template <class P>
 constexpr size_t gemm_smem_bytes(size_t extra_bytes) {
-    return 1024 + static_cast<size_t>(P::STAGES) * SmemLayout<P::BLOCK_N>::STAGE_BYTES + ((extra_bytes + 15) / 16) * 16 +
-           (2 * P::STAGES + 4) * 8 + 16;
+    return 1024 + static_cast<size_t>(P::STAGES) * SmemLayout<P::BLOCK_N>::STAGE_BYTES + (P::STAGING ? STAGING_BYTES : 0) +
+           ((extra_bytes + 15) / 16) * 16 + (2 * P::STAGES + 4) * 8 + 16;
 }
+
+// Per-epilogue-warp output staging: two 4 KB buffers (32 rows x 128 B, TMA SWIZZLE_128B layout).  Thread
+// `lane` owns row `lane`; a block is written as eight 16-byte chunks per row (bank-conflict free thanks to
+// the swizzle) and leaves through one TMA store (or fp32 reduce-add) of a {128 B x 32 rows} box.
+struct StoreStager {
+    uint32_t base;
+    int lane;
+    int it;
+    __device__ StoreStager(const EpiCtx& c) : base(smem_u32(c.staging) + c.ew * 8192), lane(c.lane), it(0) {}
+    // Buffer for the next block; blocks until the store issued two blocks ago has read it out.
+    __device__ __forceinline__ uint32_t acquire() {
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+        return base + (it & 1) * 4096;
+    }
+    __device__ __forceinline__ void put(uint32_t buf, int chunk, uint32_t a, uint32_t b, uint32_t c, uint32_t d) const {
+        st_shared_v4(buf + lane * 128 + ((chunk ^ (lane & 7)) << 4), a, b, c, d);
+    }
+    template <bool REDUCE_ADD>
+    __device__ __forceinline__ void commit(const CUtensorMap* tm, uint32_t buf, int c0, int c1) {
+        fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+            if constexpr (REDUCE_ADD) tma_reduce_add_2d(tm, buf, c0, c1);
+            else tma_store_2d(tm, buf, c0, c1);
+            bulk_commit();
+        }
+        ++it;
+    }
+    __device__ __forceinline__ void drain() {
+        if (lane == 0) bulk_wait<0>();
+        __syncwarp();
+    }
+};
 
 template <bool MN_MAJOR, int TILE_MN>
 __device__ __forceinline__ void load_operand(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int mn0, int k0) {
@@ -67,7 +114,8 @@ __device__ __forceinline__ uint64_t operand_desc(uint32_t stage_base, int kk) {
 template <class P>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ typename P::Params prm, const int extra_bytes) {
+            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ typename P::Params prm,
+            const int extra_bytes) {
     constexpr int BLOCK_N = P::BLOCK_N;
     constexpr int STAGES = P::STAGES;
     constexpr int B_STAGE_BYTES = SmemLayout<BLOCK_N>::B_STAGE_BYTES;
@@ -78,7 +126,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
     uint8_t* sB = sA + STAGES * A_STAGE_BYTES;
-    uint8_t* sExtra = sB + STAGES * B_STAGE_BYTES;
+    uint8_t* sStaging = sB + STAGES * B_STAGE_BYTES;  // 1024-aligned: stage sizes are multiples of 1 KB
+    uint8_t* sExtra = sStaging + (P::STAGING ? STAGING_BYTES : 0);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(sExtra + ((extra_bytes + 15) / 16) * 16);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
@@ -91,6 +140,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (P::STAGING) tma_prefetch_desc(&tmC);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
@@ -124,9 +174,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
                     load_operand<P::A_MN, BLOCK_M>(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], t.m0,
-                                          t.ka0 + kb * BLOCK_K);
+                                                   t.ka0 + kb * BLOCK_K);
                     load_operand<P::B_MN, BLOCK_N>(sB + stage * B_STAGE_BYTES, &tmB, &full_bar[stage], t.n0,
-                                          t.kb0 + kb * BLOCK_K);
+                                                   t.kb0 + kb * BLOCK_K);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -165,16 +215,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
         }
     } else if (warp >= 4) {
-        const int ew = warp - 4;  // == warp % 4: the TMEM lane quadrant this warp may read
+        EpiCtx ctx;
+        ctx.extra = sExtra;
+        ctx.staging = sStaging;
+        ctx.tmC = &tmC;
+        ctx.ew = warp - 4;  // == warp % 4: the TMEM lane quadrant this warp may read
+        ctx.lane = lane;
+        ctx.cta = blockIdx.x;
         typename P::Sched sched(prm, blockIdx.x, gridDim.x);
-        typename P::Epi epi(prm, sExtra, ew, lane, blockIdx.x);
+        typename P::Epi epi(prm, ctx);
         Tile t;
         int acc = 0;
         uint32_t acc_phase = 0;
         while (sched.next(t)) {
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(ew * 32) << 16);
+            const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(ctx.ew * 32) << 16);
             epi.tile(t, taddr);
             // every tcgen05.ld of this tile has completed (tile() waits on its last load)
             tc_fence_before();
@@ -194,8 +250,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // Host-side launcher (needs host_util.h included first for the error macros).
 #ifdef AB_CHECK_CUDA
 template <class P>
-static int32_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const typename P::Params& prm, int grid,
-                           int extra_bytes, cudaStream_t st) {
+static int32_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                           const typename P::Params& prm, int grid, int extra_bytes, cudaStream_t st) {
     const size_t smem = gemm_smem_bytes<P>(extra_bytes);
     AB_REQUIRE(smem <= 227 * 1024, ARCFACE_B200_E_SHAPE, "shared memory request %zu exceeds 227 KB", smem);
     AB_REQUIRE(grid >= 1, ARCFACE_B200_E_SHAPE, "empty grid");
@@ -206,7 +262,7 @@ static int32_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const
         AB_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured[dev] = true;
     }
-    gemm_kernel<P><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, prm, extra_bytes);
+    gemm_kernel<P><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, prm, extra_bytes);
     AB_CHECK_CUDA(cudaGetLastError());
     return ARCFACE_B200_OK;
 }

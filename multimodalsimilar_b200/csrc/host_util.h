@@ -39,6 +39,11 @@ int32_t make_tmap_kmajor(CUtensorMap* out, const void* base, uint64_t inner, uin
 int32_t make_tmap_mnmajor(CUtensorMap* out, const void* base, uint64_t mn, uint64_t k_rows,
                           uint64_t row_stride_elems);
 
+// Output tile map for StoreStager: global [rows][cols] of `elem_bytes`-wide elements (2 = bf16, 4 = fp32),
+// box = {128 bytes of columns, 32 rows}, SWIZZLE_128B.
+int32_t make_tmap_store(CUtensorMap* out, const void* base, int elem_bytes, uint64_t cols, uint64_t rows,
+                        uint64_t row_stride_elems);
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace ab

@@ -20,6 +20,7 @@ constexpr float LOG2E = 1.4426950408889634f;
 struct FwdStats {
     static constexpr int BLOCK_N = 256;
     static constexpr int STAGES = 4;
+    static constexpr bool STAGING = false;
     static constexpr bool A_MN = false;  // xhat [B][D]
     static constexpr bool B_MN = false;  // what [C][D]
 
@@ -68,10 +69,10 @@ struct FwdStats {
         float run_max, sum0, sum1, sum2, sum3;
         int run_arg;
         int lab;
-        __device__ Epi(const Params& prm, uint8_t*, int ew, int lane, int cta) : p(prm) {
-            const int m_tile = cta % p.m_tiles;
-            g = cta / p.m_tiles;
-            row = m_tile * BLOCK_M + ew * 32 + lane;
+        __device__ Epi(const Params& prm, const EpiCtx& c) : p(prm) {
+            const int m_tile = c.cta % p.m_tiles;
+            g = c.cta / p.m_tiles;
+            row = m_tile * BLOCK_M + c.ew * 32 + c.lane;
             active = (g < p.groups) && (row < p.B);
             run_max = -INFINITY;
             sum0 = sum1 = sum2 = sum3 = 0.f;
@@ -141,6 +142,7 @@ struct FwdStats {
 struct FwdLogits {
     static constexpr int BLOCK_N = 256;
     static constexpr int STAGES = 4;
+    static constexpr bool STAGING = false;
     static constexpr bool A_MN = false;
     static constexpr bool B_MN = false;
 
@@ -182,7 +184,7 @@ struct FwdLogits {
     struct Epi {
         const Params& p;
         int ew, lane;
-        __device__ Epi(const Params& prm, uint8_t*, int ew_, int lane_, int) : p(prm), ew(ew_), lane(lane_) {}
+        __device__ Epi(const Params& prm, const EpiCtx& c) : p(prm), ew(c.ew), lane(c.lane) {}
         __device__ void tile(const Tile& t, uint32_t taddr) {
             const int row = t.m0 + ew * 32 + lane;
             const bool rv = row < p.B;
@@ -264,7 +266,7 @@ extern "C" int32_t arcface_b200_forward_stats(const uint16_t* xhat, const uint16
     CUtensorMap tmA, tmB;
     if (int32_t rc = make_tmap_kmajor(&tmA, xhat, D, B, D, BLOCK_M)) return rc;
     if (int32_t rc = make_tmap_kmajor(&tmB, what, D, C_local, D, FwdStats::BLOCK_N)) return rc;
-    return launch_gemm<FwdStats>(tmA, tmB, p, p.groups * p.m_tiles, 0, static_cast<cudaStream_t>(stream));
+    return launch_gemm<FwdStats>(tmA, tmB, tmA, p, p.groups * p.m_tiles, 0, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int32_t arcface_b200_logits(const uint16_t* xhat, const uint16_t* what, const float* z_label,
@@ -286,5 +288,5 @@ extern "C" int32_t arcface_b200_logits(const uint16_t* xhat, const uint16_t* wha
     if (int32_t rc = make_tmap_kmajor(&tmB, what, D, C_local, D, FwdLogits::BLOCK_N)) return rc;
     const int64_t total = static_cast<int64_t>(p.m_tiles) * p.n_tiles;
     const int grid = static_cast<int>(total < sm_count() ? total : sm_count());
-    return launch_gemm<FwdLogits>(tmA, tmB, p, grid, 0, static_cast<cudaStream_t>(stream));
+    return launch_gemm<FwdLogits>(tmA, tmB, tmA, p, grid, 0, static_cast<cudaStream_t>(stream));
 }

@@ -2,14 +2,16 @@
 // arcface.py:45-63 and CrossEntropyLoss), three tcgen05 GEMMs per class chunk on the shared core:
 //
 //   BwdDC  S^T = What . Xhat^T   (classes on accumulator rows) -> epilogue recomputes
-//          p = exp(s cos - lse) from the saved row statistics, forms dC (label column uses the exact
-//          fp32 margin derivative), accumulates q[c] = sum_b dC[b,c] cos[b,c] and writes dC^T (bf16)
-//          into an L2-sized scratch chunk [classes][batch].
+//          p = exp(s cos - lse) from the saved row statistics, forms dC (label column: the exact
+//          fp32 margin derivative times the cancellation-free 1 - p_label), accumulates
+//          q[c] = sum_b dC[b,c] cos[b,c] and writes dC^T (bf16) into an L2-sized scratch chunk
+//          [classes][batch].
 //   DW     dWhat = dC^T . Xhat   (K = batch) -> epilogue applies the normalise backward
 //          dW[c] = (dWhat[c] - q[c] what[c]) * inv_nw[c] and streams fp32 dW.
 //   DX     dXhat += dC . What    (K = classes, split across CTAs; both operands MN-major views of
-//          the buffers already in memory) -> fp32 vector reductions into dXhat [B][D].
+//          the buffers already in memory) -> fp32 TMA reduce-adds into dXhat [B][D].
 //
+// All three epilogues leave through swizzled shared memory + TMA (full 128-byte lines).
 // The B x C probability matrix is never materialised: only a bounded chunk (<= ~64 MB, classes x batch
 // bf16) lives in the workspace at a time.
 #include "host_util.h"
@@ -32,7 +34,8 @@ __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w 
 // ------------------------------------------------------------------ dC^T producer
 struct BwdDC {
     static constexpr int BLOCK_N = 256;  // batch columns per tile
-    static constexpr int STAGES = 4;
+    static constexpr int STAGES = 3;
+    static constexpr bool STAGING = true;
     static constexpr bool A_MN = false;  // what [C][D]
     static constexpr bool B_MN = false;  // xhat [B][D]
 
@@ -44,13 +47,12 @@ struct BwdDC {
         int n_tiles;    // ceil(B / 256)
         float s_log2e;  // s * log2(e)
         float coef;     // s * grad_scale
-        const float* grad_dev;  // nullable device scalar multiplied into coef
+        const float* grad_dev;     // nullable device scalar multiplied into coef
         const float* lse;
         const float* one_minus_p;  // 1 - p_label, cancellation-free (finalize_rows)
         const float* dphi;
         const int* label_local;
-        __nv_bfloat16* dct;  // [c_blocks * 128][Bp]
-        float* q;            // [C]
+        float* q;  // [C]
     };
 
     static int extra_bytes(int n_tiles) { return n_tiles * BLOCK_N * 12; }
@@ -64,9 +66,8 @@ struct BwdDC {
         const float coef = p.coef * (p.grad_dev != nullptr ? *p.grad_dev : 1.f);
         for (int b = tid; b < Bpad; b += GEMM_THREADS) {
             if (b < p.B) {
-                const float l = p.lse[b];
                 const int y = p.label_local[b];
-                lse2[b] = l * LOG2E_B;
+                lse2[b] = p.lse[b] * LOG2E_B;
                 lab[b] = y;
                 dlab[b] = (y >= 0) ? -coef * p.one_minus_p[b] * p.dphi[b] : 0.f;
             } else {
@@ -103,18 +104,40 @@ struct BwdDC {
 
     struct Epi {
         const Params& p;
+        const CUtensorMap* tm_out;  // dC^T scratch [chunk classes][Bp] bf16
+        StoreStager stager;
         const float* lse2;
         const int* lab;
         const float* dlab;
         int ew, lane;
         float qacc, coef_all;
-        __device__ Epi(const Params& prm, uint8_t* extra, int ew_, int lane_, int) : p(prm), ew(ew_), lane(lane_) {
+        __device__ Epi(const Params& prm, const EpiCtx& c) : p(prm), tm_out(c.tmC), stager(c), ew(c.ew), lane(c.lane) {
             coef_all = p.coef * (p.grad_dev != nullptr ? *p.grad_dev : 1.f);
             const int Bpad = p.n_tiles * BLOCK_N;
-            lse2 = reinterpret_cast<const float*>(extra);
-            lab = reinterpret_cast<const int*>(extra + Bpad * 4);
-            dlab = reinterpret_cast<const float*>(extra + Bpad * 8);
+            lse2 = reinterpret_cast<const float*>(c.extra);
+            lab = reinterpret_cast<const int*>(c.extra + Bpad * 4);
+            dlab = reinterpret_cast<const float*>(c.extra + Bpad * 8);
             qacc = 0.f;
+        }
+        // 8 consecutive batch columns -> one 16-byte chunk of bf16
+        __device__ __forceinline__ void eight(const uint32_t* v, int b, float coef, int cmatch, uint32_t (&o)[4]) {
+            const float4 l0 = *reinterpret_cast<const float4*>(lse2 + b);
+            const float4 l1 = *reinterpret_cast<const float4*>(lse2 + b + 4);
+            const int4 y0 = *reinterpret_cast<const int4*>(lab + b);
+            const int4 y1 = *reinterpret_cast<const int4*>(lab + b + 4);
+            const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+            const int ys[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+            float dc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float cosv = __uint_as_float(v[j]);
+                float d = coef * ex2(fmaf(cosv, p.s_log2e, -ls[j]));
+                if (ys[j] == cmatch) d = dlab[b + j];  // rare: this class is row b's label
+                qacc = fmaf(d, cosv, qacc);
+                dc[j] = d;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = pack_bf16x2(dc[2 * j], dc[2 * j + 1]);
         }
         __device__ void tile(const Tile& t, uint32_t taddr) {
             const int c = t.m0 + ew * 32 + lane;  // class owned by this thread
@@ -122,40 +145,33 @@ struct BwdDC {
             const float coef = cvalid ? coef_all : 0.f;
             const int cmatch = cvalid ? c : -2;
             if (t.aux & 1) qacc = 0.f;
-            __nv_bfloat16* orow = p.dct + static_cast<int64_t>(c - p.c_begin) * p.Bp;
+            const int row0 = t.m0 - p.c_begin + ew * 32;  // chunk-relative scratch row of this warp's block
 #pragma unroll 1
-            for (int cc = 0; cc < BLOCK_N / 32; ++cc) {
-                uint32_t v[32];
-                tmem_ld32(taddr + cc * 32, v);
-                tmem_ld_wait();
-                const int b0 = t.n0 + cc * 32;
+            for (int g = 0; g < BLOCK_N / 64; ++g) {
+                const int b0 = t.n0 + g * 64;
                 if (b0 >= p.Bp) break;  // warp-uniform: nothing to store past the padded batch
-                uint32_t packed[16];
+                uint32_t v0[32], v1[32];
+                tmem_ld32(taddr + g * 64, v0);
+                tmem_ld32(taddr + g * 64 + 32, v1);
+                tmem_ld_wait();
+                const uint32_t buf = stager.acquire();
 #pragma unroll
-                for (int j4 = 0; j4 < 32; j4 += 4) {
-                    const float4 l4 = *reinterpret_cast<const float4*>(lse2 + b0 + j4);
-                    const int4 y4 = *reinterpret_cast<const int4*>(lab + b0 + j4);
-                    const float ls[4] = {l4.x, l4.y, l4.z, l4.w};
-                    const int ys[4] = {y4.x, y4.y, y4.z, y4.w};
-                    float dc[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float cosv = __uint_as_float(v[j4 + j]);
-                        float d = coef * ex2(fmaf(cosv, p.s_log2e, -ls[j]));
-                        if (ys[j] == cmatch) d = dlab[b0 + j4 + j];  // rare: this class is row b's label
-                        qacc = fmaf(d, cosv, qacc);
-                        dc[j] = d;
-                    }
-                    packed[j4 / 2] = pack_bf16x2(dc[0], dc[1]);
-                    packed[j4 / 2 + 1] = pack_bf16x2(dc[2], dc[3]);
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t o[4];
+                    eight(v0 + 8 * k, b0 + 8 * k, coef, cmatch, o);
+                    stager.put(buf, k, o[0], o[1], o[2], o[3]);
                 }
-                uint4* o = reinterpret_cast<uint4*>(orow + b0);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) o[k] = make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t o[4];
+                    eight(v1 + 8 * k, b0 + 32 + 8 * k, coef, cmatch, o);
+                    stager.put(buf, 4 + k, o[0], o[1], o[2], o[3]);
+                }
+                stager.commit<false>(tm_out, buf, b0, row0);
             }
             if ((t.aux & 2) && cvalid) p.q[c] = qacc;
         }
-        __device__ void finish() {}
+        __device__ void finish() { stager.drain(); }
     };
 };
 
@@ -163,6 +179,7 @@ struct BwdDC {
 struct BwdDW {
     static constexpr int BLOCK_N = 256;  // embedding columns per tile
     static constexpr int STAGES = 4;
+    static constexpr bool STAGING = true;
     static constexpr bool A_MN = false;  // dC^T chunk [classes][Bp], K = batch contiguous
     static constexpr bool B_MN = false;  // xhat^T [D][ld_t], K = batch contiguous
 
@@ -173,7 +190,6 @@ struct BwdDW {
         const float* q;
         const float* inv_nw;
         const __nv_bfloat16* what;
-        float* dw;
     };
 
     __device__ static void prologue(const Params&, uint8_t*, int) {}
@@ -202,45 +218,56 @@ struct BwdDW {
 
     struct Epi {
         const Params& p;
+        const CUtensorMap* tm_out;  // dW [C][D] fp32
+        StoreStager stager;
         int ew, lane;
-        __device__ Epi(const Params& prm, uint8_t*, int ew_, int lane_, int) : p(prm), ew(ew_), lane(lane_) {}
+        __device__ Epi(const Params& prm, const EpiCtx& c) : p(prm), tm_out(c.tmC), stager(c), ew(c.ew), lane(c.lane) {}
+        // the 32 normalised weights what[c, d0 .. d0+32) as 4 x 16 bytes (zeros past D or for padding rows)
+        __device__ __forceinline__ void load_w(const __nv_bfloat16* wrow, bool cvalid, int d0, uint4 (&w)[4]) const {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int d = d0 + g * 8;
+                w[g] = (cvalid && d < p.D) ? ldg_nc_u4(wrow + d) : make_uint4(0, 0, 0, 0);
+            }
+        }
         __device__ void tile(const Tile& t, uint32_t taddr) {
-            const int c = p.c_begin + t.m0 + ew * 32 + lane;
+            const int crow0 = p.c_begin + t.m0 + ew * 32;
+            const int c = crow0 + lane;
             const bool cvalid = c < p.C;
             const float qc = cvalid ? p.q[c] : 0.f;
             const float inw = cvalid ? p.inv_nw[c] : 0.f;
-            const int64_t roff = static_cast<int64_t>(cvalid ? c : 0) * p.D;
+            const __nv_bfloat16* wrow = p.what + static_cast<int64_t>(cvalid ? c : 0) * p.D;
+            uint4 wcur[4], wnext[4];
+            load_w(wrow, cvalid, t.n0, wcur);
 #pragma unroll 1
             for (int cc = 0; cc < BLOCK_N / 32; ++cc) {
-                uint32_t v[32];
-                tmem_ld32(taddr + cc * 32, v);
-                tmem_ld_wait();
                 const int d0 = t.n0 + cc * 32;
                 if (d0 >= p.D) break;
-                if (cvalid) {
+                uint32_t v[32];
+                tmem_ld32(taddr + cc * 32, v);
+                if (cc + 1 < BLOCK_N / 32) load_w(wrow, cvalid, d0 + 32, wnext);  // prefetch the next chunk's weights
+                tmem_ld_wait();
+                const uint32_t buf = stager.acquire();
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const int d = d0 + g * 8;
-                        if (d < p.D) {  // D % 8 == 0: groups of 8 are all-in or all-out
-                            const uint4 w = ldg_nc_u4(p.what + roff + d);
-                            float4 o0, o1;
-                            o0.x = (__uint_as_float(v[g * 8 + 0]) - qc * bf16_lo(w.x)) * inw;
-                            o0.y = (__uint_as_float(v[g * 8 + 1]) - qc * bf16_hi(w.x)) * inw;
-                            o0.z = (__uint_as_float(v[g * 8 + 2]) - qc * bf16_lo(w.y)) * inw;
-                            o0.w = (__uint_as_float(v[g * 8 + 3]) - qc * bf16_hi(w.y)) * inw;
-                            o1.x = (__uint_as_float(v[g * 8 + 4]) - qc * bf16_lo(w.z)) * inw;
-                            o1.y = (__uint_as_float(v[g * 8 + 5]) - qc * bf16_hi(w.z)) * inw;
-                            o1.z = (__uint_as_float(v[g * 8 + 6]) - qc * bf16_lo(w.w)) * inw;
-                            o1.w = (__uint_as_float(v[g * 8 + 7]) - qc * bf16_hi(w.w)) * inw;
-                            float4* o = reinterpret_cast<float4*>(p.dw + roff + d);
-                            o[0] = o0;
-                            o[1] = o1;
-                        }
-                    }
+                for (int g = 0; g < 4; ++g) {
+                    const uint4 w = wcur[g];
+                    const float o0 = (__uint_as_float(v[g * 8 + 0]) - qc * bf16_lo(w.x)) * inw;
+                    const float o1 = (__uint_as_float(v[g * 8 + 1]) - qc * bf16_hi(w.x)) * inw;
+                    const float o2 = (__uint_as_float(v[g * 8 + 2]) - qc * bf16_lo(w.y)) * inw;
+                    const float o3 = (__uint_as_float(v[g * 8 + 3]) - qc * bf16_hi(w.y)) * inw;
+                    const float o4 = (__uint_as_float(v[g * 8 + 4]) - qc * bf16_lo(w.z)) * inw;
+                    const float o5 = (__uint_as_float(v[g * 8 + 5]) - qc * bf16_hi(w.z)) * inw;
+                    const float o6 = (__uint_as_float(v[g * 8 + 6]) - qc * bf16_lo(w.w)) * inw;
+                    const float o7 = (__uint_as_float(v[g * 8 + 7]) - qc * bf16_hi(w.w)) * inw;
+                    stager.put(buf, 2 * g, __float_as_uint(o0), __float_as_uint(o1), __float_as_uint(o2), __float_as_uint(o3));
+                    stager.put(buf, 2 * g + 1, __float_as_uint(o4), __float_as_uint(o5), __float_as_uint(o6), __float_as_uint(o7));
                 }
+                stager.commit<false>(tm_out, buf, d0, crow0);  // rows >= C / columns >= D are clipped by the TMA
+#pragma unroll
+                for (int g = 0; g < 4; ++g) wcur[g] = wnext[g];
             }
         }
-        __device__ void finish() {}
+        __device__ void finish() { stager.drain(); }
     };
 };
 
@@ -248,6 +275,7 @@ struct BwdDW {
 struct BwdDX {
     static constexpr int BLOCK_N = 256;  // embedding columns per tile
     static constexpr int STAGES = 4;
+    static constexpr bool STAGING = true;
     static constexpr bool A_MN = true;  // dC^T chunk [classes = K][batch = M contiguous]
     static constexpr bool B_MN = true;  // what [classes = K][D = N contiguous]
 
@@ -257,7 +285,6 @@ struct BwdDX {
         int m_tiles, dn_tiles, splits;
         int kb_total;      // 64-class slices in this chunk
         int kb_per_split;  // ceil(kb_total / splits); no split is empty
-        float* dxhat;
     };
 
     __device__ static void prologue(const Params&, uint8_t*, int) {}
@@ -290,31 +317,27 @@ struct BwdDX {
 
     struct Epi {
         const Params& p;
+        const CUtensorMap* tm_out;  // dXhat [B][D] fp32, accumulated with TMA reduce-add
+        StoreStager stager;
         int ew, lane;
-        __device__ Epi(const Params& prm, uint8_t*, int ew_, int lane_, int) : p(prm), ew(ew_), lane(lane_) {}
+        __device__ Epi(const Params& prm, const EpiCtx& c) : p(prm), tm_out(c.tmC), stager(c), ew(c.ew), lane(c.lane) {}
         __device__ void tile(const Tile& t, uint32_t taddr) {
-            const int row = t.m0 + ew * 32 + lane;
-            const bool rv = row < p.B;
-            float* orow = p.dxhat + static_cast<int64_t>(rv ? row : 0) * p.D;
+            const int row0 = t.m0 + ew * 32;
 #pragma unroll 1
             for (int cc = 0; cc < BLOCK_N / 32; ++cc) {
+                const int d0 = t.n0 + cc * 32;
+                if (d0 >= p.D) break;
                 uint32_t v[32];
                 tmem_ld32(taddr + cc * 32, v);
                 tmem_ld_wait();
-                const int d0 = t.n0 + cc * 32;
-                if (d0 >= p.D) break;
-                if (rv) {
+                if (row0 >= p.B) continue;  // warp-uniform: this warp's 32 rows are all padding
+                const uint32_t buf = stager.acquire();
 #pragma unroll
-                    for (int g = 0; g < 8; ++g) {
-                        const int d = d0 + g * 4;
-                        if (d < p.D)
-                            red_add_v4(orow + d, __uint_as_float(v[g * 4 + 0]), __uint_as_float(v[g * 4 + 1]),
-                                       __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3]));
-                    }
-                }
+                for (int g = 0; g < 8; ++g) stager.put(buf, g, v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+                stager.commit<true>(tm_out, buf, d0, row0);  // rows >= B / columns >= D are clipped by the TMA
             }
         }
-        __device__ void finish() {}
+        __device__ void finish() { stager.drain(); }
     };
 };
 
@@ -348,11 +371,19 @@ static BwdPlan plan_backward(int B, int64_t C, int nsm) {
 
 using namespace ab;
 
+static int32_t check_bwd_shape(const char* who, int32_t B, int32_t D, int64_t C_local) {
+    AB_REQUIRE(B >= 1 && B <= ARCFACE_B200_MAX_BATCH, ARCFACE_B200_E_SHAPE, "%s: B=%d outside [1, %d]", who, B,
+               ARCFACE_B200_MAX_BATCH);
+    AB_REQUIRE(D >= 8 && D % 8 == 0, ARCFACE_B200_E_SHAPE, "%s: D=%d must be a positive multiple of 8", who, D);
+    AB_REQUIRE(C_local >= 1 && C_local <= (1ll << 30), ARCFACE_B200_E_SHAPE, "%s: C_local=%lld outside [1, 2^30]", who,
+               (long long)C_local);
+    return ARCFACE_B200_OK;
+}
+
 extern "C" int32_t arcface_b200_backward_workspace_bytes(int32_t B, int32_t D, int64_t C_local, size_t* bytes) {
     if (int32_t rc = check_arch()) return rc;
     AB_REQUIRE(bytes, ARCFACE_B200_E_ARG, "backward_workspace_bytes: null pointer");
-    AB_REQUIRE(B >= 1 && B <= ARCFACE_B200_MAX_BATCH && D >= 8 && D % 8 == 0 && C_local >= 1 && C_local <= (1ll << 30),
-               ARCFACE_B200_E_SHAPE, "backward_workspace_bytes: bad shape B=%d D=%d C=%lld", B, D, (long long)C_local);
+    if (int32_t rc = check_bwd_shape("backward_workspace_bytes", B, D, C_local)) return rc;
     *bytes = plan_backward(B, C_local, sm_count()).total;
     return ARCFACE_B200_OK;
 }
@@ -361,8 +392,7 @@ extern "C" int32_t arcface_b200_backward_plan(int32_t B, int32_t D, int64_t C_lo
                                               int32_t* n_chunks) {
     if (int32_t rc = check_arch()) return rc;
     AB_REQUIRE(chunk_classes && n_chunks, ARCFACE_B200_E_ARG, "backward_plan: null pointer");
-    AB_REQUIRE(B >= 1 && B <= ARCFACE_B200_MAX_BATCH && D >= 8 && D % 8 == 0 && C_local >= 1 && C_local <= (1ll << 30),
-               ARCFACE_B200_E_SHAPE, "backward_plan: bad shape B=%d D=%d C=%lld", B, D, (long long)C_local);
+    if (int32_t rc = check_bwd_shape("backward_plan", B, D, C_local)) return rc;
     const BwdPlan pl = plan_backward(B, C_local, sm_count());
     *chunk_classes = pl.chunk_classes;
     *n_chunks = static_cast<int32_t>((C_local + pl.chunk_classes - 1) / pl.chunk_classes);
@@ -378,10 +408,7 @@ extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* x
     if (int32_t rc = check_arch()) return rc;
     AB_REQUIRE(xhat && xhat_t && what && inv_nw && lse && one_minus_p && dphi && label_local && dxhat && dw && workspace,
                ARCFACE_B200_E_ARG, "backward: null pointer");
-    AB_REQUIRE(B >= 1 && B <= ARCFACE_B200_MAX_BATCH, ARCFACE_B200_E_SHAPE, "backward: B=%d outside [1, %d]", B,
-               ARCFACE_B200_MAX_BATCH);
-    AB_REQUIRE(D >= 8 && D % 8 == 0, ARCFACE_B200_E_SHAPE, "backward: D=%d must be a positive multiple of 8", D);
-    AB_REQUIRE(C_local >= 1 && C_local <= (1ll << 30), ARCFACE_B200_E_SHAPE, "backward: bad C_local");
+    if (int32_t rc = check_bwd_shape("backward", B, D, C_local)) return rc;
     AB_REQUIRE(ld_t >= B && ld_t % 8 == 0, ARCFACE_B200_E_LAYOUT, "backward: ld_t must be >= B and a multiple of 8");
     AB_REQUIRE(aligned16(dxhat) && aligned16(dw) && aligned16(workspace) && aligned16(what), ARCFACE_B200_E_LAYOUT,
                "backward: pointers must be 16-byte aligned");
@@ -398,13 +425,16 @@ extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* x
 
     AB_CHECK_CUDA(cudaMemsetAsync(dxhat, 0, static_cast<size_t>(B) * D * sizeof(float), st));
 
-    CUtensorMap tm_w_k, tm_x_k, tm_dct_k, tm_xt_k, tm_dct_mn, tm_w_mn;
+    CUtensorMap tm_w_k, tm_x_k, tm_dct_k, tm_xt_k, tm_dct_mn, tm_w_mn, tm_dct_out, tm_dw_out, tm_dx_out;
     if (int32_t rc = make_tmap_kmajor(&tm_w_k, what, D, C_local, D, BLOCK_M)) return rc;
     if (int32_t rc = make_tmap_kmajor(&tm_x_k, xhat, D, B, D, BwdDC::BLOCK_N)) return rc;
     if (int32_t rc = make_tmap_kmajor(&tm_dct_k, dct, B, pl.chunk_classes, pl.Bp, BLOCK_M)) return rc;
     if (int32_t rc = make_tmap_kmajor(&tm_xt_k, xhat_t, B, D, ld_t, BwdDW::BLOCK_N)) return rc;
     if (int32_t rc = make_tmap_mnmajor(&tm_dct_mn, dct, B, pl.chunk_classes, pl.Bp)) return rc;
     if (int32_t rc = make_tmap_mnmajor(&tm_w_mn, what, D, C_local, D)) return rc;
+    if (int32_t rc = make_tmap_store(&tm_dct_out, dct, 2, pl.Bp, pl.chunk_classes, pl.Bp)) return rc;
+    if (int32_t rc = make_tmap_store(&tm_dw_out, dw, 4, D, C_local, D)) return rc;
+    if (int32_t rc = make_tmap_store(&tm_dx_out, dxhat, 4, D, B, D)) return rc;
 
     const int n_tiles = (B + BwdDC::BLOCK_N - 1) / BwdDC::BLOCK_N;
     const int m_tiles = (B + BLOCK_M - 1) / BLOCK_M;
@@ -419,18 +449,19 @@ extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* x
             p.c_begin = static_cast<int>(c0); p.c_blocks = c_blocks; p.n_tiles = n_tiles;
             p.s_log2e = s * LOG2E_B; p.coef = s * grad_scale; p.grad_dev = grad_loss_dev;
             p.lse = lse; p.one_minus_p = one_minus_p; p.dphi = dphi; p.label_local = label_local;
-            p.dct = dct; p.q = q;
+            p.q = q;
             const int grid = c_blocks < nsm ? c_blocks : nsm;
-            if (int32_t rc = launch_gemm<BwdDC>(tm_w_k, tm_x_k, p, grid, BwdDC::extra_bytes(n_tiles), st)) return rc;
+            if (int32_t rc = launch_gemm<BwdDC>(tm_w_k, tm_x_k, tm_dct_out, p, grid, BwdDC::extra_bytes(n_tiles), st))
+                return rc;
         }
         {
             BwdDW::Params p;
             p.B = B; p.D = D; p.C = C;
             p.c_begin = static_cast<int>(c0); p.c_blocks = c_blocks; p.dn_tiles = dn_tiles;
-            p.q = q; p.inv_nw = inv_nw; p.what = reinterpret_cast<const __nv_bfloat16*>(what); p.dw = dw;
+            p.q = q; p.inv_nw = inv_nw; p.what = reinterpret_cast<const __nv_bfloat16*>(what);
             const int total = c_blocks * dn_tiles;
             const int grid = total < nsm ? total : nsm;
-            if (int32_t rc = launch_gemm<BwdDW>(tm_dct_k, tm_xt_k, p, grid, 0, st)) return rc;
+            if (int32_t rc = launch_gemm<BwdDW>(tm_dct_k, tm_xt_k, tm_dw_out, p, grid, 0, st)) return rc;
         }
         {
             BwdDX::Params p;
@@ -442,10 +473,9 @@ extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* x
             if (splits > p.kb_total) splits = p.kb_total;
             p.kb_per_split = (p.kb_total + splits - 1) / splits;
             p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
-            p.dxhat = dxhat;
             const int total = m_tiles * dn_tiles * p.splits;
             const int grid = total < nsm ? total : nsm;
-            if (int32_t rc = launch_gemm<BwdDX>(tm_dct_mn, tm_w_mn, p, grid, 0, st)) return rc;
+            if (int32_t rc = launch_gemm<BwdDX>(tm_dct_mn, tm_w_mn, tm_dx_out, p, grid, 0, st)) return rc;
         }
     }
     return ARCFACE_B200_OK;
