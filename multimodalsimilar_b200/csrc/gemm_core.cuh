@@ -20,7 +20,7 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // bf16 elements: one 128-byte swizzle span
 constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 256;
-constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int A_SUB_BYTES = BLOCK_M * BLOCK_K * 2;  // one 128-row sub-tile of operand A
 constexpr int STAGING_BYTES = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x (32 rows x 128 B)
 
 struct Tile {
@@ -42,17 +42,20 @@ struct EpiCtx {
     int cta;
 };
 
-template <int BLOCK_N>
+// A policy may stack M_SUB 128-row sub-tiles that share every B k-block (M_SUB x BLOCK_N accumulator
+// columns each) and chooses how many accumulator sets (ACC_BUFS) live in TMEM.
+template <class P>
 struct SmemLayout {
-    static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int A_STAGE_BYTES = P::M_SUB * A_SUB_BYTES;
+    static constexpr int B_STAGE_BYTES = P::BLOCK_N * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 };
 
 // Dynamic shared memory needed by gemm_kernel<P> (includes 1 KB of alignment slack).
 template <class P>
 constexpr size_t gemm_smem_bytes(size_t extra_bytes) {
-    return 1024 + static_cast<size_t>(P::STAGES) * SmemLayout<P::BLOCK_N>::STAGE_BYTES + (P::STAGING ? STAGING_BYTES : 0) +
-           ((extra_bytes + 15) / 16) * 16 + (2 * P::STAGES + 4) * 8 + 16;
+    return 1024 + static_cast<size_t>(P::STAGES) * SmemLayout<P>::STAGE_BYTES + (P::STAGING ? STAGING_BYTES : 0) +
+           ((extra_bytes + 15) / 16) * 16 + (2 * P::STAGES + 2 * P::ACC_BUFS) * 8 + 16;
 }
 
 // Per-epilogue-warp output staging: two 4 KB buffers (32 rows x 128 B, TMA SWIZZLE_128B layout).  Thread
@@ -118,9 +121,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int extra_bytes) {
     constexpr int BLOCK_N = P::BLOCK_N;
     constexpr int STAGES = P::STAGES;
-    constexpr int B_STAGE_BYTES = SmemLayout<BLOCK_N>::B_STAGE_BYTES;
-    constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;  // 256 or 512: powers of two >= 32
+    constexpr int M_SUB = P::M_SUB;
+    constexpr int ACC_BUFS = P::ACC_BUFS;
+    constexpr int A_STAGE_BYTES = SmemLayout<P>::A_STAGE_BYTES;
+    constexpr int B_STAGE_BYTES = SmemLayout<P>::B_STAGE_BYTES;
+    constexpr int ACC_COLS = M_SUB * BLOCK_N;            // TMEM columns of one accumulator set
+    constexpr uint32_t TMEM_COLS = ACC_BUFS * ACC_COLS;  // 256 or 512: powers of two >= 32
     static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N must be 128 or 256");
+    static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "accumulators must fill 256 or 512 TMEM columns");
+    static_assert(M_SUB == 1 || P::A_MN, "stacked A sub-tiles are only wired for MN-major A");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -131,8 +140,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(sExtra + ((extra_bytes + 15) / 16) * 16);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
-    uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* tempty_bar = tfull_bar + ACC_BUFS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + ACC_BUFS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -147,7 +156,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < ACC_BUFS; ++i) {
             mbar_init(&tfull_bar[i], 1);
             mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
         }
@@ -173,7 +182,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 for (int kb = 0; kb < t.kblocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
-                    load_operand<P::A_MN, BLOCK_M>(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], t.m0,
+                    load_operand<P::A_MN, BLOCK_M * M_SUB>(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], t.m0,
                                                    t.ka0 + kb * BLOCK_K);
                     load_operand<P::B_MN, BLOCK_N>(sB + stage * B_STAGE_BYTES, &tmB, &full_bar[stage], t.n0,
                                                    t.kb0 + kb * BLOCK_K);
@@ -195,7 +204,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             while (sched.next(t)) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+                const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
                 for (int kb = 0; kb < t.kblocks; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
@@ -203,15 +212,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     const uint32_t b_base = sB_u32 + stage * B_STAGE_BYTES;
 #pragma unroll
                     for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
-                        umma_bf16(tmem_d, operand_desc<P::A_MN>(a_base, kk), operand_desc<P::B_MN>(b_base, kk), idesc,
-                                  (kb | kk) != 0 ? 1u : 0u);
+                        const uint64_t bdesc = operand_desc<P::B_MN>(b_base, kk);
+#pragma unroll
+                        for (int ms = 0; ms < M_SUB; ++ms)
+                            umma_bf16(tmem_d + ms * BLOCK_N, operand_desc<P::A_MN>(a_base + ms * A_SUB_BYTES, kk), bdesc,
+                                      idesc, (kb | kk) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);  // frees this smem slot once the MMAs above retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
+                if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else if (warp >= 4) {
@@ -230,14 +241,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         while (sched.next(t)) {
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(ctx.ew * 32) << 16);
+            const uint32_t taddr = tmem_base + acc * ACC_COLS + (static_cast<uint32_t>(ctx.ew * 32) << 16);
             epi.tile(t, taddr);
             // every tcgen05.ld of this tile has completed (tile() waits on its last load)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
+            if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
         }
         epi.finish();
     }

@@ -20,6 +20,8 @@ constexpr float LOG2E = 1.4426950408889634f;
 struct FwdStats {
     static constexpr int BLOCK_N = 256;
     static constexpr int STAGES = 4;
+    static constexpr int M_SUB = 1;
+    static constexpr int ACC_BUFS = 2;
     static constexpr bool STAGING = false;
     static constexpr bool A_MN = false;  // xhat [B][D]
     static constexpr bool B_MN = false;  // what [C][D]
@@ -142,6 +144,8 @@ struct FwdStats {
 struct FwdLogits {
     static constexpr int BLOCK_N = 256;
     static constexpr int STAGES = 4;
+    static constexpr int M_SUB = 1;
+    static constexpr int ACC_BUFS = 2;
     static constexpr bool STAGING = false;
     static constexpr bool A_MN = false;
     static constexpr bool B_MN = false;
