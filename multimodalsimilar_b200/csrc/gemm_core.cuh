@@ -173,43 +173,46 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            typename P::Sched sched(prm, blockIdx.x, gridDim.x);
-            Tile t;
-            int stage = 0;
-            uint32_t phase = 0;
-            while (sched.next(t)) {
-                for (int kb = 0; kb < t.kblocks; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+        // whole warp walks the schedule (uniform control flow); one elected lane issues the TMA loads
+        typename P::Sched sched(prm, blockIdx.x, gridDim.x);
+        Tile t;
+        int stage = 0;
+        uint32_t phase = 0;
+        while (sched.next(t)) {
+            for (int kb = 0; kb < t.kblocks; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
                     mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
                     load_operand<P::A_MN, BLOCK_M * M_SUB>(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], t.m0,
-                                                   t.ka0 + kb * BLOCK_K);
+                                                           t.ka0 + kb * BLOCK_K);
                     load_operand<P::B_MN, BLOCK_N>(sB + stage * B_STAGE_BYTES, &tmB, &full_bar[stage], t.n0,
                                                    t.kb0 + kb * BLOCK_K);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, P::A_MN, P::B_MN);
-            typename P::Sched sched(prm, blockIdx.x, gridDim.x);
-            Tile t;
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            const uint32_t sA_u32 = smem_u32(sA);
-            const uint32_t sB_u32 = smem_u32(sB);
-            while (sched.next(t)) {
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        // whole warp runs the loop, one elected lane issues: see elect_one() in ptx.cuh
+        constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, P::A_MN, P::B_MN);
+        typename P::Sched sched(prm, blockIdx.x, gridDim.x);
+        Tile t;
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const uint32_t sA_u32 = smem_u32(sA);
+        const uint32_t sB_u32 = smem_u32(sB);
+        while (sched.next(t)) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
+            for (int kb = 0; kb < t.kblocks; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
-                for (int kb = 0; kb < t.kblocks; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_base = sA_u32 + stage * A_STAGE_BYTES;
-                    const uint32_t b_base = sB_u32 + stage * B_STAGE_BYTES;
+                const uint32_t a_base = sA_u32 + stage * A_STAGE_BYTES;
+                const uint32_t b_base = sB_u32 + stage * B_STAGE_BYTES;
+                if (elect_one()) {
 #pragma unroll
                     for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
                         const uint64_t bdesc = operand_desc<P::B_MN>(b_base, kk);
@@ -219,11 +222,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                       idesc, (kb | kk) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);  // frees this smem slot once the MMAs above retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (kb == t.kblocks - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
                 }
-                umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-                if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4) {
         EpiCtx ctx;

@@ -1,0 +1,291 @@
+// CTA-pair resident-operand GEMM core ("pair core"): tcgen05 cta_group::2, one 256 x 256 accumulator tile
+// per pair of SMs, one operand parked in shared memory for the whole kernel.
+//
+// Why: a one-CTA 128 x N tile is bound by shared-memory bandwidth, not by the tensor pipe.  Every
+// tcgen05.mma re-reads its A (128 x 16) and B (N x 16) slices from shared memory and every operand byte is
+// first written there by TMA: the streaming forward tile (128 x 256 x 64 per 512 tensor cycles) asks for
+// 96 KB per k-block = 192 B/clk against ~128 B/clk and measures 68 % tensor-busy; the one-CTA
+// resident-operand kernels with N = 128 measure 30-42 % (profiles/r1_v3_*).  With a CTA pair each SM supplies
+// only its 128 rows of A and its 128-row half of B for a 128 x 256 slice of the output (64 B/clk of MMA
+// reads), and with one operand resident only 16 KB per k-block per SM is written by TMA (32 B/clk):
+// 96 B/clk in total, leaving headroom for the epilogue's staging traffic.
+//
+// Per CTA (rank r of the pair), for K <= 512:
+//   resident : 128 rows x K of the reused operand (rows res * 256 + r * 128 ...), loaded once
+//   streamed : 128 rows x 64 per stage of the per-tile operand (rows s_row0 + i * 256 + r * 128 ...)
+//   TMEM     : two accumulator buffers of 256 fp32 columns; the CTA's 128 lanes are its 128 rows of the tile
+// P::RES_A == false: the streamed operand is A (its rows are the accumulator rows), the resident one is B.
+// P::RES_A == true : the resident operand is A, the streamed one is B (accumulator columns).
+// Roles (384 threads): warp 0 TMA producer (both CTAs), warp 1 MMA issuer (leader CTA only), warp 2 TMEM
+// allocator, warps 4-11 epilogue (two per TMEM lane quadrant, 128 accumulator columns each).
+// Barriers: full[] / tempty[] / res live in the LEADER's shared memory (both CTAs' producers and epilogues
+// arrive there through shared::cluster addresses); empty[] / tfull[] exist in both CTAs and are signalled by
+// multicast tcgen05.commit.
+//
+// Reference counterpart: F.linear in arcface.py:47 and the autograd matmuls of loss.backward().
+#pragma once
+#include "ptx.cuh"
+
+namespace ab {
+namespace pr {
+
+constexpr int ROWS = 128;  // rows of either operand held by one CTA
+constexpr int BK = 64;
+constexpr int ACC_COLS = 256;
+constexpr int ACC_BUFS = 2;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = (4 + EPI_WARPS) * 32;
+constexpr int TILE_BYTES = ROWS * BK * 2;  // 16 KB
+constexpr int STAGING_PER_WARP = 4096;
+constexpr int MAX_KBLOCKS = 8;
+
+struct Core {
+    int kblocks;         // ceil(K / 64) <= MAX_KBLOCKS
+    int s_blocks;        // 256-row blocks of the streamed operand handled by this launch
+    int s_row0;          // TMA row coordinate of block 0 in the streamed tensor map
+    int n_res;           // 256-row slices of the resident operand; the number of pairs is a multiple of it
+    int contiguous;      // 1: group g walks blocks [g * per, (g + 1) * per); 0: g, g + groups, ...
+    int prefetch_tiles;  // L2 prefetch distance in tiles (0 = off)
+};
+
+struct EpiCtx {
+    uint8_t* extra;
+    uint32_t staging;  // this warp's 4 KB staging buffer (only if P::STAGING)
+    const CUtensorMap* tmC;
+    int quad;   // TMEM lane quadrant
+    int half;   // which 128 accumulator columns this warp owns
+    int lane;
+    int rank;   // CTA rank in the pair
+    int res;    // resident slice of the pair
+    int grp;    // group of the pair (pairs / n_res groups)
+};
+
+template <class P>
+constexpr size_t smem_bytes(int kblocks, size_t extra_bytes) {
+    return 1024 + static_cast<size_t>(kblocks + P::STAGES) * TILE_BYTES + (P::STAGING ? EPI_WARPS * STAGING_PER_WARP : 0) +
+           ((extra_bytes + 15) / 16) * 16 + (2 * P::STAGES + 2 * ACC_BUFS + 1) * 8 + 16;
+}
+
+// One 4 KB staging buffer per epilogue warp (32 rows x 128 B, TMA SWIZZLE_128B layout); see gemm_rs.cuh.
+struct Stager {
+    uint32_t buf;
+    int lane;
+    __device__ Stager(const EpiCtx& c) : buf(c.staging), lane(c.lane) {}
+    __device__ __forceinline__ void acquire() const {
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
+    }
+    __device__ __forceinline__ void put(int chunk, uint32_t a, uint32_t b, uint32_t c, uint32_t d) const {
+        st_shared_v4(buf + lane * 128 + ((chunk ^ (lane & 7)) << 4), a, b, c, d);
+    }
+    __device__ __forceinline__ void commit(const CUtensorMap* tm, int c0, int c1) const {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_2d(tm, buf, c0, c1);
+            bulk_commit();
+        }
+    }
+    __device__ __forceinline__ void drain() const {
+        if (lane == 0) bulk_wait<0>();
+        __syncwarp();
+    }
+};
+
+template <class P>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+pair_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmR,
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ typename P::Params prm,
+                 const int extra_bytes) {
+    constexpr int STAGES = P::STAGES;
+    const Core& co = prm.core;
+    const int kblocks = co.kblocks;
+
+    extern __shared__ uint8_t smem_raw[];
+    // the two CTAs must carve identically: the dynamic shared-memory window starts at the same offset in both
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sRes = smem;
+    uint8_t* sStage = sRes + kblocks * TILE_BYTES;
+    uint8_t* sStaging = sStage + STAGES * TILE_BYTES;
+    uint8_t* sExtra = sStaging + (P::STAGING ? EPI_WARPS * STAGING_PER_WARP : 0);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sExtra + ((extra_bytes + 15) / 16) * 16);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + ACC_BUFS;
+    uint64_t* res_bar = tempty_bar + ACC_BUFS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int rank = static_cast<int>(cluster_ctarank());
+    const int pair = blockIdx.x >> 1;
+    const int npairs = gridDim.x >> 1;
+    const int res = pair % co.n_res;
+    const int grp = pair / co.n_res;
+    const int ngrp = npairs / co.n_res;
+    // tile walk of this pair
+    int i_begin, i_end, i_step;
+    if (co.contiguous) {
+        const int per = (co.s_blocks + ngrp - 1) / ngrp;
+        i_begin = grp * per;
+        i_end = min(co.s_blocks, i_begin + per);
+        i_step = 1;
+    } else {
+        i_begin = grp;
+        i_end = co.s_blocks;
+        i_step = ngrp;
+    }
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmS);
+        tma_prefetch_desc(&tmR);
+        if (P::STAGING) tma_prefetch_desc(&tmC);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full_bar[i], 2);   // one arrive.expect_tx per CTA of the pair (used in the leader only)
+            mbar_init(&empty_bar[i], 1);  // multicast tcgen05.commit
+        }
+        for (int i = 0; i < ACC_BUFS; ++i) {
+            mbar_init(&tfull_bar[i], 1);                // multicast tcgen05.commit
+            mbar_init(&tempty_bar[i], 2 * EPI_WARPS);   // every epilogue warp of both CTAs (leader only)
+        }
+        mbar_init(res_bar, 2);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc_pair(tmem_slot, ACC_BUFS * ACC_COLS);
+        tmem_relinquish_pair();
+    }
+    P::prologue(prm, sExtra, threadIdx.x, res, rank);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // the peer's barriers are initialised before anyone arrives on them remotely
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---------------- TMA producer (both CTAs): whole warp walks the schedule, one elected lane issues
+        const uint32_t res_bar_leader = mapa_u32(smem_u32(res_bar), 0);
+        if (elect_one()) {
+            mbar_expect_tx_cluster(res_bar_leader, kblocks * TILE_BYTES);
+            for (int kb = 0; kb < kblocks; ++kb)
+                tma_load_2d_pair(sRes + kb * TILE_BYTES, &tmR, res_bar_leader, kb * BK, res * 2 * ROWS + rank * ROWS);
+        }
+        __syncwarp();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int i = i_begin; i < i_end; i += i_step) {
+            const int row = co.s_row0 + i * 2 * ROWS + rank * ROWS;
+            const int ip = i + co.prefetch_tiles * i_step;
+            const bool pf = co.prefetch_tiles > 0 && ip < i_end;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
+                    const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                    mbar_expect_tx_cluster(full_leader, TILE_BYTES);
+                    tma_load_2d_pair(sStage + stage * TILE_BYTES, &tmS, full_leader, kb * BK, row);
+                    // the n_res pairs that stream the same block share the L2 prefetch work
+                    if (pf && (kb % co.n_res) == res)
+                        tma_prefetch_2d(&tmS, kb * BK, co.s_row0 + ip * 2 * ROWS + rank * ROWS);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer: leader CTA only, whole warp runs the loop, one elected lane issues
+        if (rank == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(2 * ROWS, ACC_COLS, false, false);
+            const uint32_t sStage_u32 = smem_u32(sStage);
+            const uint64_t res_desc0 = make_smem_desc(smem_u32(sRes), 16, 1024);
+            mbar_wait_cluster(res_bar, 0);
+            tc_fence_after();
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int i = i_begin; i < i_end; i += i_step) {
+                mbar_wait_cluster(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait_cluster(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t s_desc = make_smem_desc(sStage_u32 + stage * TILE_BYTES, 16, 1024);
+                    const uint64_t r_desc = res_desc0 + static_cast<uint64_t>(kb * (TILE_BYTES >> 4));
+                    const uint64_t a_desc = P::RES_A ? r_desc : s_desc;
+                    const uint64_t b_desc = P::RES_A ? s_desc : r_desc;
+                    if (elect_one()) {
+#pragma unroll
+                        for (int kk = 0; kk < BK / 16; ++kk)
+                            umma_bf16_pair(tmem_d, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (kb | kk) != 0 ? 1u : 0u);
+                        umma_commit_pair(&empty_bar[stage], 3);  // frees the stage in both CTAs
+                        if (kb == kblocks - 1) umma_commit_pair(&tfull_bar[acc], 3);
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ---------------- epilogue (both CTAs)
+        EpiCtx ctx;
+        ctx.extra = sExtra;
+        ctx.staging = smem_u32(sStaging) + (warp - 4) * STAGING_PER_WARP;
+        ctx.tmC = &tmC;
+        ctx.quad = warp & 3;
+        ctx.half = (warp - 4) >> 2;
+        ctx.lane = lane;
+        ctx.rank = rank;
+        ctx.res = res;
+        ctx.grp = grp;
+        typename P::Epi epi(prm, ctx);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        if (i_begin < i_end) epi.prefetch(i_begin);
+        for (int i = i_begin; i < i_end; i += i_step) {
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr =
+                tmem_base + acc * ACC_COLS + ctx.half * 128 + (static_cast<uint32_t>(ctx.quad * 32) << 16);
+            epi.tile(i, i + i_step < i_end ? i + i_step : -1, taddr);  // returns after its last tcgen05.ld completed
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+            if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
+        }
+        epi.finish();
+    }
+
+    // neither CTA may leave (or free TMEM) while the peer can still touch its barriers / shared memory / TMEM
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) tmem_dealloc_pair(tmem_base, ACC_BUFS * ACC_COLS);
+}
+
+#ifdef AB_CHECK_CUDA
+template <class P>
+static int32_t launch_pair(const CUtensorMap& tmS, const CUtensorMap& tmR, const CUtensorMap& tmC,
+                           const typename P::Params& prm, int groups, int extra_bytes, cudaStream_t st) {
+    const size_t smem = smem_bytes<P>(prm.core.kblocks, extra_bytes);
+    AB_REQUIRE(prm.core.kblocks >= 1 && prm.core.kblocks <= MAX_KBLOCKS && smem <= 227 * 1024, ARCFACE_B200_E_SHAPE,
+               "CTA-pair kernel: %d k-blocks / %zu bytes of shared memory do not fit", prm.core.kblocks, smem);
+    AB_REQUIRE(groups >= 1 && prm.core.n_res >= 1, ARCFACE_B200_E_SHAPE, "empty grid");
+    static bool configured[64] = {false};
+    int dev = 0;
+    AB_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        AB_CHECK_CUDA(cudaFuncSetAttribute(pair_gemm_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured[dev] = true;
+    }
+    pair_gemm_kernel<P><<<2 * groups * prm.core.n_res, THREADS, smem, st>>>(tmS, tmR, tmC, prm, extra_bytes);
+    AB_CHECK_CUDA(cudaGetLastError());
+    return ARCFACE_B200_OK;
+}
+#endif
+
+}  // namespace pr
+}  // namespace ab

@@ -147,56 +147,62 @@ rs_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        // whole warp walks the schedule (uniform control flow); one elected lane issues the TMA work
+        if (elect_one()) {
             mbar_expect_tx(res_bar, kblocks * TILE_BYTES);
             for (int kb = 0; kb < kblocks; ++kb) tma_load_2d(sRes + kb * TILE_BYTES, &tmR, res_bar, kb * BK, res * BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int i = grp; i < co.m_blocks; i += ngrp) {
-                const int row = co.s_row0 + i * BM;
-                const int ip = i + co.prefetch_tiles * ngrp;
-                const bool pf = co.prefetch_tiles > 0 && ip < co.m_blocks;
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    // the n_res CTAs that stream the same block share the prefetch work
-                    if (pf && (kb % co.n_res) == res) tma_prefetch_2d(&tmS, kb * BK, co.s_row0 + ip * BM);
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+        }
+        __syncwarp();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int i = grp; i < co.m_blocks; i += ngrp) {
+            const int row = co.s_row0 + i * BM;
+            const int ip = i + co.prefetch_tiles * ngrp;
+            const bool pf = co.prefetch_tiles > 0 && ip < co.m_blocks;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
                     mbar_expect_tx(&full_bar[stage], TILE_BYTES);
                     tma_load_2d(sStage + stage * TILE_BYTES, &tmS, &full_bar[stage], kb * BK, row);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    // the n_res CTAs that stream the same block share the prefetch work
+                    if (pf && (kb % co.n_res) == res) tma_prefetch_2d(&tmS, kb * BK, co.s_row0 + ip * BM);
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BM, BN, false, false);
-            const uint32_t sStage_u32 = smem_u32(sStage);
-            const uint64_t res_desc0 = make_smem_desc(smem_u32(sRes), 16, 1024);
-            mbar_wait(res_bar, 0);
+        constexpr uint32_t idesc = make_idesc_bf16(BM, BN, false, false);
+        const uint32_t sStage_u32 = smem_u32(sStage);
+        const uint64_t res_desc0 = make_smem_desc(smem_u32(sRes), 16, 1024);
+        mbar_wait(res_bar, 0);
+        tc_fence_after();
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int i = grp; i < co.m_blocks; i += ngrp) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             tc_fence_after();
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int i = grp; i < co.m_blocks; i += ngrp) {
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            const uint32_t tmem_d = tmem_base + acc * BN;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * BN;
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint64_t a_desc = make_smem_desc(sStage_u32 + stage * TILE_BYTES, 16, 1024);
-                    const uint64_t b_desc = res_desc0 + static_cast<uint64_t>(kb * (TILE_BYTES >> 4));
+                const uint64_t a_desc = make_smem_desc(sStage_u32 + stage * TILE_BYTES, 16, 1024);
+                const uint64_t b_desc = res_desc0 + static_cast<uint64_t>(kb * (TILE_BYTES >> 4));
+                if (elect_one()) {
 #pragma unroll
                     for (int kk = 0; kk < BK / 16; ++kk) {
                         // +2 in the address field = 32 bytes = 16 bf16 along K inside the swizzle span
                         umma_bf16(tmem_d, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (kb | kk) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (kb == kblocks - 1) umma_commit(&tfull_bar[acc]);
                 }
-                umma_commit(&tfull_bar[acc]);
-                if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4) {
         EpiCtx ctx;
@@ -210,11 +216,13 @@ rs_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ 
         typename P::Epi epi(prm, ctx);
         int acc = 0;
         uint32_t acc_phase = 0;
+        if (grp < co.m_blocks) epi.prefetch(grp);
         for (int i = grp; i < co.m_blocks; i += ngrp) {
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * BN + ctx.half * 64 + (static_cast<uint32_t>(ctx.quad * 32) << 16);
-            epi.tile(i, taddr);  // returns after its last tcgen05.ld has completed
+            // i_next lets the policy issue the NEXT tile's global loads before it works on this one
+            epi.tile(i, i + ngrp < co.m_blocks ? i + ngrp : -1, taddr);  // returns after its last tcgen05.ld completed
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);

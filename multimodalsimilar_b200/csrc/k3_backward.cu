@@ -434,7 +434,8 @@ struct BwdDCr {
 #pragma unroll
             for (int j = 0; j < 4; ++j) o[j] = pack_bf16x2(dc[2 * j], dc[2 * j + 1]);
         }
-        __device__ void tile(int i, uint32_t taddr) {
+        __device__ void prefetch(int) {}
+        __device__ void tile(int i, int, uint32_t taddr) {
             const int c = p.core.s_row0 + i * rs::BM + quad * 32 + lane;  // class owned by this thread
             const bool cvalid = c < p.C;
             if (b0 >= p.Bp) {  // warp-uniform: this warp's columns are all batch padding, nothing to store
@@ -488,34 +489,47 @@ struct BwdDWr {
         const CUtensorMap* tm_out;  // dW [C][D] fp32
         rs::Stager stager;
         int quad, lane, d0;
+        // per-tile operands of the normalise backward, fetched one tile ahead (their HBM / L2 latency would
+        // otherwise sit between every tcgen05.ld and its TMA store)
+        uint4 wn[8];
+        float qn[8];
+        float inwn;
         __device__ Epi(const Params& prm, const rs::EpiCtx& c)
             : p(prm), tm_out(c.tmC), stager(c), quad(c.quad), lane(c.lane), d0(c.res * rs::BN + c.half * 64) {}
-        __device__ void tile(int i, uint32_t taddr) {
-            const int crow0 = p.c_begin + i * rs::BM + quad * 32;
-            const int c = crow0 + lane;
+        __device__ __forceinline__ void prefetch(int i) {
+            const int c = p.c_begin + i * rs::BM + quad * 32 + lane;
             const bool cvalid = c < p.C;
-            if (d0 >= p.D) return;  // warp-uniform: columns past the embedding width
-            uint32_t v0[32], v1[32];
-            tmem_ld32(taddr, v0);
-            tmem_ld32(taddr + 32, v1);
-            // overlap the TMEM read with the global loads of q, 1/||w|| and the normalised weights
-            float qc = 0.f;
-            if (cvalid)
-                for (int sl = 0; sl < p.q_slots; ++sl) qc += p.q[static_cast<int64_t>(sl) * p.C + c];
-            const float inw = cvalid ? p.inv_nw[c] : 0.f;
             const __nv_bfloat16* wrow = p.what + static_cast<int64_t>(cvalid ? c : 0) * p.D;
-            uint4 w[8];
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
                 const int d = d0 + g * 8;
-                w[g] = (cvalid && d < p.D) ? ldg_nc_u4(wrow + d) : make_uint4(0, 0, 0, 0);
+                wn[g] = (cvalid && d < p.D) ? ldg_nc_u4(wrow + d) : make_uint4(0, 0, 0, 0);
             }
-            const float nq = -qc;
+#pragma unroll
+            for (int sl = 0; sl < 8; ++sl)
+                qn[sl] = (cvalid && sl < p.q_slots) ? __ldg(p.q + static_cast<int64_t>(sl) * p.C + c) : 0.f;
+            inwn = cvalid ? __ldg(p.inv_nw + c) : 0.f;
+        }
+        __device__ void tile(int i, int i_next, uint32_t taddr) {
+            const int crow0 = p.c_begin + i * rs::BM + quad * 32;
+            // take over the operands fetched for this tile, then start the next tile's loads
+            uint4 w[8];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) w[g] = wn[g];
+            const float nq = -(((qn[0] + qn[1]) + (qn[2] + qn[3])) + ((qn[4] + qn[5]) + (qn[6] + qn[7])));
+            const float inw = inwn;
+            if (d0 >= p.D) return;  // warp-uniform: columns past the embedding width
+            uint32_t v[32];
+            tmem_ld32(taddr, v);
+            if (i_next >= 0) prefetch(i_next);
             tmem_ld_wait();
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-                const uint32_t* v = hh == 0 ? v0 : v1;
-                if (d0 + hh * 32 >= p.D) break;
+                if (hh == 1) {
+                    if (d0 + 32 >= p.D) break;
+                    tmem_ld32(taddr + 32, v);
+                    tmem_ld_wait();
+                }
                 stager.acquire();
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
