@@ -73,7 +73,7 @@ int32_t arcface_b200_label_margin(const float* x, const float* w, const float* i
                                   float* dphi, int32_t* label_local, int32_t* bad_label_flag, void* stream);
 
 /* Number of per-row partial slots arcface_b200_forward_stats writes for this shape. */
-int32_t arcface_b200_forward_parts(int32_t B, int64_t C_local, int32_t* n_parts);
+int32_t arcface_b200_forward_parts(int32_t B, int32_t D, int64_t C_local, int32_t* n_parts);
 
 /* K2 -- cosine-logit GEMM (tcgen05 / TMEM, TMA-fed) with the margin / scale / online-softmax epilogue.
  * Replaces F.linear (arcface.py:47), the blend + scale (:58-61), CrossEntropyLoss' log-softmax and

@@ -29,7 +29,7 @@ SIGNATURES = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64, c_int64, c_int64,
          c_float, c_float, c_float, c_float, c_float, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     ),
-    "arcface_b200_forward_parts": (c_int32, [c_int32, c_int64, POINTER(c_int32)]),
+    "arcface_b200_forward_parts": (c_int32, [c_int32, c_int32, c_int64, POINTER(c_int32)]),
     "arcface_b200_forward_stats": (
         c_int32,
         [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64, c_float, c_void_p, c_void_p, c_void_p,

@@ -35,7 +35,7 @@ size_t bump(size_t& cur, size_t bytes) {
 }
 
 int32_t plan_step(int32_t B, int32_t D, int64_t C, StepPlan* pl) {
-    if (int32_t rc = arcface_b200_forward_parts(B, C, &pl->n_parts)) return rc;
+    if (int32_t rc = arcface_b200_forward_parts(B, D, C, &pl->n_parts)) return rc;
     if (int32_t rc = arcface_b200_backward_workspace_bytes(B, D, C, &pl->bwd_bytes)) return rc;
     pl->Bp = ((B + 63) / 64) * 64;
     size_t cur = 0;

@@ -9,8 +9,11 @@
 // epilogue thread owns one batch row and the running (max, sum-exp, argmax) is a thread-local scan.
 #include "host_util.h"
 #include "gemm_core.cuh"
+#include "gemm_pair.cuh"
 
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace ab {
 
@@ -140,6 +143,107 @@ struct FwdStats {
     };
 };
 
+// ------------------------------------------------------------------ softmax statistics on a CTA pair
+// (gemm_pair.cuh) resident = 256 batch rows of Xhat (A operand, accumulator lanes: 128 rows per CTA), streamed =
+// What rows (256 classes per tile = accumulator columns, each CTA loads 128 of them), K = D <= 512.  Each pair
+// walks a contiguous class range; the two epilogue warps of a TMEM lane quadrant take 128 columns each and
+// keep separate partial rows (slot = 2 * range + half), merged by combine_partials.
+struct FwdStatsP {
+    static constexpr int STAGES = 4;
+    static constexpr bool STAGING = false;
+    static constexpr bool RES_A = true;
+    static constexpr int NROW = 2 * pr::ROWS;
+
+    struct Params {
+        pr::Core core;
+        int B;
+        int C;
+        float s;
+        const int* label_local;
+        float* part_max;
+        float* part_sum;
+        int* part_arg;
+    };
+
+    __device__ static void prologue(const Params&, uint8_t*, int, int, int) {}
+
+    struct Epi {
+        const Params& p;
+        int row, slot, half;
+        bool active;
+        float run_max, sum0, sum1, sum2, sum3;
+        int run_arg;
+        int lab;
+        __device__ Epi(const Params& prm, const pr::EpiCtx& c) : p(prm) {
+            row = c.res * NROW + c.rank * pr::ROWS + c.quad * 32 + c.lane;
+            slot = c.grp * 2 + c.half;
+            half = c.half;
+            active = row < p.B;
+            run_max = -INFINITY;
+            sum0 = sum1 = sum2 = sum3 = 0.f;
+            run_arg = 0;
+            lab = -1;
+            if (active && p.label_local != nullptr) lab = p.label_local[row];
+        }
+        __device__ void prefetch(int) {}
+        __device__ void tile(int i, int, uint32_t taddr) {
+            const float s = p.s;
+            const int n0 = i * NROW + half * 128;  // first class of this warp's 128 columns
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c * 32, v);
+                tmem_ld_wait();
+                const int col0 = n0 + c * 32;
+                if (col0 >= p.C) break;  // warp-uniform: whole chunk past the last class
+                float z[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) z[j] = __uint_as_float(v[j]) * s;
+                if (col0 + 32 > p.C) {  // warp-uniform tail
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j >= p.C) z[j] = -INFINITY;
+                }
+                const int lr = lab - col0;
+                if (lr >= 0 && lr < 32) {  // the label column is merged exactly (fp32) by finalize_rows
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j == lr) z[j] = -INFINITY;
+                }
+                float cm = z[0];
+#pragma unroll
+                for (int j = 1; j < 32; ++j) cm = fmaxf(cm, z[j]);
+                if (cm == -INFINITY) continue;
+                if (cm > run_max) {  // strict: an equal later maximum never displaces the first one
+                    int first = 31;
+#pragma unroll
+                    for (int j = 30; j >= 0; --j)
+                        if (z[j] == cm) first = j;
+                    run_arg = col0 + first;
+                    const float f = ex2((run_max - cm) * LOG2E);
+                    sum0 *= f; sum1 *= f; sum2 *= f; sum3 *= f;
+                    run_max = cm;
+                }
+                const float mb = run_max * LOG2E;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    sum0 += ex2(fmaf(z[j + 0], LOG2E, -mb));
+                    sum1 += ex2(fmaf(z[j + 1], LOG2E, -mb));
+                    sum2 += ex2(fmaf(z[j + 2], LOG2E, -mb));
+                    sum3 += ex2(fmaf(z[j + 3], LOG2E, -mb));
+                }
+            }
+        }
+        __device__ void finish() {
+            if (!active) return;
+            const int64_t o = static_cast<int64_t>(slot) * p.B + row;
+            p.part_max[o] = run_max;
+            p.part_sum[o] = (sum0 + sum1) + (sum2 + sum3);
+            p.part_arg[o] = run_arg;
+        }
+    };
+};
+
 // ------------------------------------------------------------------ materialising epilogue
 struct FwdLogits {
     static constexpr int BLOCK_N = 256;
@@ -229,6 +333,22 @@ static void fwd_partition(int B, int64_t C, int nsm, int* m_tiles, int* n_tiles,
     *groups = (*n_tiles + *per - 1) / *per;  // no empty class range
 }
 
+// CTA-pair forward: usable when the 256-row Xhat slice fits in shared memory (D <= 512) and the device has
+// at least one pair of SMs.  ARCFACE_B200_FWD_IMPL=generic forces the streaming kernel (A/B measurements).
+static bool fwd_use_pairs(int D, int nsm) {
+    const char* v = getenv("ARCFACE_B200_FWD_IMPL");
+    if (v != nullptr && strcmp(v, "generic") == 0) return false;
+    return (D + pr::BK - 1) / pr::BK <= pr::MAX_KBLOCKS && nsm >= 2;
+}
+static void fwd_pair_partition(int B, int64_t C, int nsm, int* n_res, int* groups, int* s_blocks) {
+    *n_res = (B + FwdStatsP::NROW - 1) / FwdStatsP::NROW;
+    *s_blocks = static_cast<int>((C + FwdStatsP::NROW - 1) / FwdStatsP::NROW);
+    int g = (nsm / 2) / *n_res;
+    if (g < 1) g = 1;
+    if (g > *s_blocks) g = *s_blocks;
+    *groups = g;
+}
+
 }  // namespace ab
 
 using namespace ab;
@@ -242,10 +362,16 @@ static int32_t check_gemm_shape(const char* who, int32_t B, int32_t D, int64_t C
     return ARCFACE_B200_OK;
 }
 
-extern "C" int32_t arcface_b200_forward_parts(int32_t B, int64_t C_local, int32_t* n_parts) {
+extern "C" int32_t arcface_b200_forward_parts(int32_t B, int32_t D, int64_t C_local, int32_t* n_parts) {
     if (int32_t rc = check_arch()) return rc;
     AB_REQUIRE(n_parts, ARCFACE_B200_E_ARG, "forward_parts: null pointer");
-    if (int32_t rc = check_gemm_shape("forward_parts", B, 8, C_local)) return rc;
+    if (int32_t rc = check_gemm_shape("forward_parts", B, D, C_local)) return rc;
+    if (fwd_use_pairs(D, sm_count())) {
+        int n_res, g, sb;
+        fwd_pair_partition(B, C_local, sm_count(), &n_res, &g, &sb);
+        *n_parts = 2 * g;
+        return ARCFACE_B200_OK;
+    }
     int mt, nt, g, per;
     fwd_partition(B, C_local, sm_count(), &mt, &nt, &g, &per);
     *n_parts = g;
@@ -260,6 +386,24 @@ extern "C" int32_t arcface_b200_forward_stats(const uint16_t* xhat, const uint16
     AB_REQUIRE(xhat && what && part_max && part_sum && part_arg, ARCFACE_B200_E_ARG, "forward_stats: null pointer");
     AB_REQUIRE(s > 0.f, ARCFACE_B200_E_ARG, "forward_stats: scale s must be positive");
     if (int32_t rc = check_gemm_shape("forward_stats", B, D, C_local)) return rc;
+    if (fwd_use_pairs(D, sm_count())) {
+        FwdStatsP::Params p;
+        int groups;
+        fwd_pair_partition(B, C_local, sm_count(), &p.core.n_res, &groups, &p.core.s_blocks);
+        AB_REQUIRE(n_parts == 2 * groups, ARCFACE_B200_E_WORKSPACE, "forward_stats: n_parts=%d, expected %d", n_parts,
+                   2 * groups);
+        p.core.kblocks = (D + pr::BK - 1) / pr::BK;
+        p.core.s_row0 = 0;
+        p.core.contiguous = 1;
+        p.core.prefetch_tiles = 2;
+        p.B = B; p.C = static_cast<int>(C_local); p.s = s;
+        p.label_local = label_local;
+        p.part_max = part_max; p.part_sum = part_sum; p.part_arg = part_arg;
+        CUtensorMap tmS, tmR;
+        if (int32_t rc = make_tmap_kmajor(&tmS, what, D, C_local, D, pr::ROWS)) return rc;
+        if (int32_t rc = make_tmap_kmajor(&tmR, xhat, D, B, D, pr::ROWS)) return rc;
+        return pr::launch_pair<FwdStatsP>(tmS, tmR, tmS, p, groups, 0, static_cast<cudaStream_t>(stream));
+    }
     FwdStats::Params p;
     fwd_partition(B, C_local, sm_count(), &p.m_tiles, &p.n_tiles, &p.groups, &p.tiles_per_g);
     AB_REQUIRE(n_parts == p.groups, ARCFACE_B200_E_WORKSPACE, "forward_stats: n_parts=%d, expected %d", n_parts,

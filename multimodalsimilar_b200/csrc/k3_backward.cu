@@ -17,6 +17,7 @@
 #include "host_util.h"
 #include "gemm_core.cuh"
 #include "gemm_rs.cuh"
+#include "gemm_pair.cuh"
 
 #include <math.h>
 #include <stdlib.h>
@@ -552,6 +553,232 @@ struct BwdDWr {
     };
 };
 
+// ================================================================== CTA-pair fast path
+// (gemm_pair.cuh: tcgen05 cta_group::2, 256 x 256 accumulator tile per pair of SMs, reused operand resident)
+
+// ------------------------------------------------------------------ dC^T producer on a CTA pair
+// streamed = What rows (256 classes per tile, 128 per CTA -> accumulator lanes), resident = 256 batch rows of
+// Xhat (accumulator columns), K = D <= 512.
+struct BwdDCp {
+    static constexpr int STAGES = 3;  // 3 x 16 KB: the per-column constants below take the fourth stage's room
+    static constexpr bool STAGING = true;
+    static constexpr bool RES_A = false;
+    static constexpr int NCOL = 2 * pr::ROWS;  // batch columns of one pair
+
+    struct Params {
+        pr::Core core;
+        int B, C, Bp;
+        float s_log2e;
+        float coef;
+        const float* grad_dev;
+        const float* lse;
+        const float* one_minus_p;
+        const float* dphi;
+        const int* label_local;
+        float* q;  // [2 * n_res][C]: one slot per (batch slice, column half)
+    };
+    static constexpr int EXTRA_BYTES = NCOL * 12;
+
+    // constants of this pair's 256 batch columns: lse * log2e (+inf on padding -> p = 0), label, label-column dC
+    __device__ static void prologue(const Params& p, uint8_t* extra, int tid, int res, int) {
+        float* lse2 = reinterpret_cast<float*>(extra);
+        int* lab = reinterpret_cast<int*>(extra + NCOL * 4);
+        float* dlab = reinterpret_cast<float*>(extra + NCOL * 8);
+        const float coef = p.coef * (p.grad_dev != nullptr ? *p.grad_dev : 1.f);
+        for (int j = tid; j < NCOL; j += pr::THREADS) {
+            const int b = res * NCOL + j;
+            if (b < p.B) {
+                const int y = p.label_local[b];
+                lse2[j] = p.lse[b] * LOG2E_B;
+                lab[j] = y;
+                dlab[j] = (y >= 0) ? -coef * p.one_minus_p[b] * p.dphi[b] : 0.f;
+            } else {
+                lse2[j] = INFINITY;
+                lab[j] = -1;
+                dlab[j] = 0.f;
+            }
+        }
+    }
+
+    struct Epi {
+        const Params& p;
+        const CUtensorMap* tm_out;  // dC^T scratch [chunk classes][Bp] bf16
+        pr::Stager stager;
+        const float* lse2;
+        const int* lab;
+        const float* dlab;
+        int quad, lane, rank, jl0, b0;
+        float coef_all;
+        float* qslot;
+        __device__ Epi(const Params& prm, const pr::EpiCtx& c)
+            : p(prm), tm_out(c.tmC), stager(c), quad(c.quad), lane(c.lane), rank(c.rank) {
+            coef_all = p.coef * (p.grad_dev != nullptr ? *p.grad_dev : 1.f);
+            jl0 = c.half * 128;          // first of this warp's 128 columns inside the pair's 256
+            b0 = c.res * NCOL + jl0;     // the same as a batch index
+            lse2 = reinterpret_cast<const float*>(c.extra) + jl0;
+            lab = reinterpret_cast<const int*>(c.extra + NCOL * 4) + jl0;
+            dlab = reinterpret_cast<const float*>(c.extra + NCOL * 8) + jl0;
+            qslot = p.q + static_cast<int64_t>(c.res * 2 + c.half) * p.C;
+        }
+        // 8 consecutive batch columns -> one 16-byte chunk of bf16
+        __device__ __forceinline__ void eight(const uint32_t* v, int j0, float coef, int cmatch, float& qacc,
+                                              uint32_t (&o)[4]) const {
+            const float4 l0 = *reinterpret_cast<const float4*>(lse2 + j0);
+            const float4 l1 = *reinterpret_cast<const float4*>(lse2 + j0 + 4);
+            const int4 y0 = *reinterpret_cast<const int4*>(lab + j0);
+            const int4 y1 = *reinterpret_cast<const int4*>(lab + j0 + 4);
+            const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+            const int ys[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+            float dc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float cosv = __uint_as_float(v[j]);
+                float d = coef * ex2(fmaf(cosv, p.s_log2e, -ls[j]));
+                if (ys[j] == cmatch) d = dlab[j0 + j];  // rare: this class is row b's label
+                qacc = fmaf(d, cosv, qacc);
+                dc[j] = d;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = pack_bf16x2(dc[2 * j], dc[2 * j + 1]);
+        }
+        __device__ void prefetch(int) {}
+        __device__ void tile(int i, int, uint32_t taddr) {
+            const int row0 = i * NCOL + rank * pr::ROWS + quad * 32;  // chunk-relative class row of lane 0
+            const int c = p.core.s_row0 + row0 + lane;                // class owned by this thread
+            const bool cvalid = c < p.C;
+            const float coef = cvalid ? coef_all : 0.f;
+            const int cmatch = cvalid ? c : -2;
+            float q0 = 0.f, q1 = 0.f;
+#pragma unroll 1
+            for (int g = 0; g < 2; ++g) {
+                if (b0 + g * 64 >= p.Bp) break;  // warp-uniform: these columns are all batch padding
+                uint32_t v0[32], v1[32];
+                tmem_ld32(taddr + g * 64, v0);
+                tmem_ld32(taddr + g * 64 + 32, v1);
+                tmem_ld_wait();
+                stager.acquire();
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t o[4];
+                    eight(v0 + 8 * k, g * 64 + 8 * k, coef, cmatch, q0, o);
+                    stager.put(k, o[0], o[1], o[2], o[3]);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t o[4];
+                    eight(v1 + 8 * k, g * 64 + 32 + 8 * k, coef, cmatch, q1, o);
+                    stager.put(4 + k, o[0], o[1], o[2], o[3]);
+                }
+                stager.commit(tm_out, b0 + g * 64, row0);  // rows past the chunk are clipped by the TMA
+            }
+            if (cvalid) qslot[c] = q0 + q1;
+        }
+        __device__ void finish() { stager.drain(); }
+    };
+};
+
+// ------------------------------------------------------------------ dW on a CTA pair
+// streamed = dC^T scratch rows (256 classes per tile), resident = 256 rows of Xhat^T (embedding columns of the
+// accumulator), K = batch <= 512.
+struct BwdDWp {
+    static constexpr int STAGES = 4;
+    static constexpr bool STAGING = true;
+    static constexpr bool RES_A = false;
+    static constexpr int NCOL = 2 * pr::ROWS;
+
+    struct Params {
+        pr::Core core;
+        int C, D;
+        int c_begin;  // first class of this chunk (the scratch is chunk-relative)
+        const float* q;
+        int q_slots;  // <= 8
+        const float* inv_nw;
+        const __nv_bfloat16* what;
+    };
+    static constexpr int EXTRA_BYTES = 0;
+
+    __device__ static void prologue(const Params&, uint8_t*, int, int, int) {}
+
+    struct Epi {
+        const Params& p;
+        const CUtensorMap* tm_out;  // dW [C][D] fp32
+        pr::Stager stager;
+        int quad, lane, rank, d0;
+        // operands of the normalise backward, fetched one 32-column box ahead (their L2 latency would otherwise
+        // sit between every tcgen05.ld and its TMA store)
+        uint4 wn[4];
+        float nqn, inwn;
+        __device__ Epi(const Params& prm, const pr::EpiCtx& c)
+            : p(prm), tm_out(c.tmC), stager(c), quad(c.quad), lane(c.lane), rank(c.rank),
+              d0(c.res * NCOL + c.half * 128) {}
+        __device__ __forceinline__ int class_of(int i) const {
+            return p.c_begin + i * NCOL + rank * pr::ROWS + quad * 32 + lane;
+        }
+        __device__ __forceinline__ void fetch_w(int i, int box) {
+            const int c = class_of(i);
+            const bool cvalid = c < p.C;
+            const __nv_bfloat16* wrow = p.what + static_cast<int64_t>(cvalid ? c : 0) * p.D;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int d = d0 + box * 32 + g * 8;
+                wn[g] = (cvalid && d < p.D) ? ldg_nc_u4(wrow + d) : make_uint4(0, 0, 0, 0);
+            }
+        }
+        __device__ __forceinline__ void fetch_scalars(int i) {
+            const int c = class_of(i);
+            const bool cvalid = c < p.C;
+            float qs[8];
+#pragma unroll
+            for (int sl = 0; sl < 8; ++sl)
+                qs[sl] = (cvalid && sl < p.q_slots) ? __ldg(p.q + static_cast<int64_t>(sl) * p.C + c) : 0.f;
+            nqn = -(((qs[0] + qs[1]) + (qs[2] + qs[3])) + ((qs[4] + qs[5]) + (qs[6] + qs[7])));
+            inwn = cvalid ? __ldg(p.inv_nw + c) : 0.f;
+        }
+        __device__ void prefetch(int i) {
+            fetch_scalars(i);
+            fetch_w(i, 0);
+        }
+        __device__ void tile(int i, int i_next, uint32_t taddr) {
+            const int crow0 = p.c_begin + i * NCOL + rank * pr::ROWS + quad * 32;
+            const float nq = nqn, inw = inwn;
+#pragma unroll 1
+            for (int box = 0; box < 4; ++box) {
+                const int dbox = d0 + box * 32;
+                if (dbox >= p.D) {  // warp-uniform: columns past the embedding width
+                    if (i_next >= 0) prefetch(i_next);
+                    break;
+                }
+                uint4 w[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) w[g] = wn[g];
+                uint32_t v[32];
+                tmem_ld32(taddr + box * 32, v);
+                // start the next box's operand loads before waiting on this one
+                if (box < 3) fetch_w(i, box + 1);
+                else if (i_next >= 0) prefetch(i_next);
+                tmem_ld_wait();
+                stager.acquire();
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const uint4 ww = w[g];
+                    const float o0 = fmaf(nq, bf16_lo(ww.x), __uint_as_float(v[g * 8 + 0])) * inw;
+                    const float o1 = fmaf(nq, bf16_hi(ww.x), __uint_as_float(v[g * 8 + 1])) * inw;
+                    const float o2 = fmaf(nq, bf16_lo(ww.y), __uint_as_float(v[g * 8 + 2])) * inw;
+                    const float o3 = fmaf(nq, bf16_hi(ww.y), __uint_as_float(v[g * 8 + 3])) * inw;
+                    const float o4 = fmaf(nq, bf16_lo(ww.z), __uint_as_float(v[g * 8 + 4])) * inw;
+                    const float o5 = fmaf(nq, bf16_hi(ww.z), __uint_as_float(v[g * 8 + 5])) * inw;
+                    const float o6 = fmaf(nq, bf16_lo(ww.w), __uint_as_float(v[g * 8 + 6])) * inw;
+                    const float o7 = fmaf(nq, bf16_hi(ww.w), __uint_as_float(v[g * 8 + 7])) * inw;
+                    stager.put(2 * g, __float_as_uint(o0), __float_as_uint(o1), __float_as_uint(o2), __float_as_uint(o3));
+                    stager.put(2 * g + 1, __float_as_uint(o4), __float_as_uint(o5), __float_as_uint(o6), __float_as_uint(o7));
+                }
+                stager.commit(tm_out, dbox, crow0);  // rows >= C / columns >= D are clipped by the TMA
+            }
+        }
+        __device__ void finish() { stager.drain(); }
+    };
+};
+
 // ------------------------------------------------------------------ dXhat, 256 x 256 output tile per CTA
 // Two stacked 128-row batch sub-tiles share every What k-block (64 KB per 1024 tensor cycles instead of
 // 48 KB per 512), the class range is split across CTAs and each CTA keeps its partial product in all 512
@@ -635,6 +862,7 @@ struct BwdPlan {
     int chunk_classes;  // classes per scratch chunk (multiple of 128)
     int n_chunks;
     bool dc_rs, dw_rs, dx2;  // which kernels take the resident-operand / stacked-tile fast path
+    bool dc_pair, dw_pair;   // ... on CTA pairs (cta_group::2) instead of single CTAs
     int q_slots;             // partial-sum slots of q per class
     size_t scratch_off, scratch_bytes, q_off, q_bytes, total;
 };
@@ -646,6 +874,7 @@ static bool env_is(const char* name, const char* value) {
 
 // Kernel selection and scratch chunking.  Environment knobs (diagnostics / A-B measurements only):
 //   ARCFACE_B200_BWD_IMPL=generic   use the streaming kernels of gemm_core.cuh for every shape
+//   ARCFACE_B200_BWD_IMPL=rs        resident-operand kernels on single CTAs (gemm_rs.cuh) instead of CTA pairs
 //   ARCFACE_B200_BWD_CHUNK_MB=<n>   cap of the dC^T scratch in MiB
 static BwdPlan plan_backward(int B, int D, int64_t C, int nsm) {
     BwdPlan pl;
@@ -655,7 +884,10 @@ static BwdPlan plan_backward(int B, int D, int64_t C, int nsm) {
     pl.dc_rs = !generic && (D + 63) / 64 <= rs::MAX_KBLOCKS;
     pl.dw_rs = !generic && pl.Bp / 64 <= rs::MAX_KBLOCKS;
     pl.dx2 = !generic;
-    pl.q_slots = pl.dc_rs ? 2 * ((B + rs::BN - 1) / rs::BN) : 1;
+    const bool pairs = !env_is("ARCFACE_B200_BWD_IMPL", "rs") && nsm >= 2;
+    pl.dc_pair = pl.dc_rs && pairs;
+    pl.dw_pair = pl.dw_rs && pairs;
+    pl.q_slots = pl.dc_pair ? 2 * ((B + BwdDCp::NCOL - 1) / BwdDCp::NCOL) : pl.dc_rs ? 2 * ((B + rs::BN - 1) / rs::BN) : 1;
     const int64_t c_round = ((C + 127) / 128) * 128;
     int64_t chunk;
     size_t cap = generic ? (size_t(64) << 20) : (size_t(2048) << 20);
@@ -763,7 +995,24 @@ extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* x
         const int cn = static_cast<int>(C_local - c0 < pl.chunk_classes ? C_local - c0 : pl.chunk_classes);
         const int c_blocks = (cn + BLOCK_M - 1) / BLOCK_M;
         // ---- dC^T (and q) for this chunk
-        if (pl.dc_rs) {
+        if (pl.dc_pair) {
+            BwdDCp::Params p;
+            p.core.kblocks = (D + pr::BK - 1) / pr::BK;
+            p.core.s_blocks = (cn + BwdDCp::NCOL - 1) / BwdDCp::NCOL;
+            p.core.s_row0 = static_cast<int>(c0);
+            p.core.n_res = (B + BwdDCp::NCOL - 1) / BwdDCp::NCOL;
+            p.core.contiguous = 0;
+            p.core.prefetch_tiles = 2;
+            p.B = B; p.C = C; p.Bp = pl.Bp;
+            p.s_log2e = s * LOG2E_B; p.coef = s * grad_scale; p.grad_dev = grad_loss_dev;
+            p.lse = lse; p.one_minus_p = one_minus_p; p.dphi = dphi; p.label_local = label_local;
+            p.q = q;
+            int groups = (nsm / 2) / p.core.n_res;
+            if (groups < 1) groups = 1;
+            if (groups > p.core.s_blocks) groups = p.core.s_blocks;
+            if (int32_t rc = pr::launch_pair<BwdDCp>(tm_w_k, tm_x_k, tm_dct_out, p, groups, BwdDCp::EXTRA_BYTES, st))
+                return rc;
+        } else if (pl.dc_rs) {
             BwdDCr::Params p;
             p.core.kblocks = (D + rs::BK - 1) / rs::BK;
             p.core.m_blocks = c_blocks;
@@ -791,7 +1040,23 @@ extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* x
                 return rc;
         }
         // ---- dW rows of this chunk
-        if (pl.dw_rs) {
+        if (pl.dw_pair) {
+            BwdDWp::Params p;
+            p.core.kblocks = pl.Bp / pr::BK;
+            p.core.s_blocks = (cn + BwdDWp::NCOL - 1) / BwdDWp::NCOL;
+            p.core.s_row0 = 0;  // the scratch is chunk-relative
+            p.core.n_res = (D + BwdDWp::NCOL - 1) / BwdDWp::NCOL;
+            p.core.contiguous = 0;
+            p.core.prefetch_tiles = 2;
+            p.C = C; p.D = D; p.c_begin = static_cast<int>(c0);
+            p.q = q; p.q_slots = pl.q_slots; p.inv_nw = inv_nw;
+            p.what = reinterpret_cast<const __nv_bfloat16*>(what);
+            int groups = (nsm / 2) / p.core.n_res;
+            if (groups < 1) groups = 1;
+            if (groups > p.core.s_blocks) groups = p.core.s_blocks;
+            if (int32_t rc = pr::launch_pair<BwdDWp>(tm_dct_k, tm_xt_k, tm_dw_out, p, groups, BwdDWp::EXTRA_BYTES, st))
+                return rc;
+        } else if (pl.dw_rs) {
             BwdDWr::Params p;
             p.core.kblocks = pl.Bp / rs::BK;
             p.core.m_blocks = c_blocks;

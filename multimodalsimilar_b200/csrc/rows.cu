@@ -151,35 +151,51 @@ label_margin_kernel(const float* __restrict__ x, const float* __restrict__ w, co
     }
 }
 
-__global__ void combine_partials_kernel(const float* __restrict__ pm, const float* __restrict__ ps,
-                                        const int* __restrict__ pa, int n_parts, int B, int64_t class_offset,
-                                        float* __restrict__ row_max, float* __restrict__ row_sum,
-                                        int64_t* __restrict__ row_arg) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per batch row: lane l merges parts l, l + 32, ... (independent loads), then the 32 partial
+// (max, sum-exp, argmax) triples are merged by shuffles.  Ties on the maximum keep the LOWEST class index
+// (torch.argmax), whatever order the parts cover the classes in.
+__global__ void __launch_bounds__(256)
+combine_partials_kernel(const float* __restrict__ pm, const float* __restrict__ ps, const int* __restrict__ pa,
+                        int n_parts, int B, int64_t class_offset, float* __restrict__ row_max,
+                        float* __restrict__ row_sum, int64_t* __restrict__ row_arg) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (b >= B) return;
-    // two passes with independent loads (the one-pass online merge serialises ~3 L2 round trips per part)
     float M = -INFINITY, S = 0.f;
-    int P = 0;
-#pragma unroll 8
-    for (int p = 0; p < n_parts; ++p) {
+    int A = 0x7fffffff;
+    for (int p = lane; p < n_parts; p += 32) {
         const float m = pm[static_cast<int64_t>(p) * B + b];
-        if (m > M) {  // strict: on ties the earlier part (lower class range) wins
+        const float s = ps[static_cast<int64_t>(p) * B + b];
+        const int a = pa[static_cast<int64_t>(p) * B + b];
+        if (m == -INFINITY) continue;  // empty part
+        if (m > M) {
+            S = S * expf(M - m) + s;  // expf(-inf) = 0 on the first part
             M = m;
-            P = p;
+            A = a;
+        } else {
+            S += s * expf(m - M);
+            if (m == M && a < A) A = a;
         }
     }
-    const int A = pa[static_cast<int64_t>(P) * B + b];
-    if (M > -INFINITY) {
-#pragma unroll 8
-        for (int p = 0; p < n_parts; ++p) {
-            const float m = pm[static_cast<int64_t>(p) * B + b];
-            const float s = ps[static_cast<int64_t>(p) * B + b];
-            S += (m > -INFINITY) ? s * expf(m - M) : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, M, o);
+        const float s2 = __shfl_xor_sync(0xffffffffu, S, o);
+        const int a2 = __shfl_xor_sync(0xffffffffu, A, o);
+        if (m2 > M) {
+            S = (M > -INFINITY ? S * expf(M - m2) : 0.f) + s2;
+            M = m2;
+            A = a2;
+        } else if (m2 > -INFINITY) {
+            S += s2 * expf(m2 - M);
+            if (m2 == M && a2 < A) A = a2;
         }
     }
-    row_max[b] = M;
-    row_sum[b] = S;
-    row_arg[b] = static_cast<int64_t>(A) + class_offset;
+    if (lane == 0) {
+        row_max[b] = M;
+        row_sum[b] = S;
+        row_arg[b] = static_cast<int64_t>(M > -INFINITY ? A : 0) + class_offset;
+    }
 }
 
 // Merges the per-rank statistics of the NON-label columns with the fp32 label logit.  Keeping the label
@@ -323,7 +339,7 @@ extern "C" int32_t arcface_b200_combine_partials(const float* part_max, const fl
                "combine_partials: null pointer");
     AB_REQUIRE(n_parts >= 1 && B >= 0, ARCFACE_B200_E_SHAPE, "combine_partials: bad shape");
     if (B == 0) return ARCFACE_B200_OK;
-    combine_partials_kernel<<<(B + 31) / 32, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+    combine_partials_kernel<<<(B + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         part_max, part_sum, part_arg, n_parts, B, class_offset, row_max, row_sum, row_arg);
     AB_CHECK_CUDA(cudaGetLastError());
     return ARCFACE_B200_OK;

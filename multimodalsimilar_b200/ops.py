@@ -93,9 +93,9 @@ def label_margin(x, w, inv_nx, inv_nw, label, class_offset, c_total, s, m, easy_
     return out
 
 
-def forward_parts(B: int, c_local: int) -> int:
+def forward_parts(B: int, D: int, c_local: int) -> int:
     n = ctypes.c_int32(0)
-    _lib.call("arcface_b200_forward_parts", B, c_local, ctypes.byref(n))
+    _lib.call("arcface_b200_forward_parts", B, D, c_local, ctypes.byref(n))
     return n.value
 
 
@@ -107,7 +107,7 @@ def forward_rows(xhat, what, label_local, s: float, class_offset: int = 0):
     B, D = xhat.shape
     C = what.shape[0]
     dev = xhat.device
-    n_parts = forward_parts(B, C)
+    n_parts = forward_parts(B, D, C)
     pmax = torch.empty((n_parts, B), dtype=torch.float32, device=dev)
     psum = torch.empty((n_parts, B), dtype=torch.float32, device=dev)
     parg = torch.empty((n_parts, B), dtype=torch.int32, device=dev)

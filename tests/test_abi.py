@@ -58,7 +58,7 @@ def test_no_device_is_an_error_not_a_fallback():
     with pytest.raises(_lib.ArcfaceB200Error):
         _lib.call("arcface_b200_device_ok")
     n = ctypes.c_int32(0)
-    assert lib.arcface_b200_forward_parts(512, 1000000, ctypes.byref(n)) < 0  # needs the device's SM count
+    assert lib.arcface_b200_forward_parts(512, 512, 1000000, ctypes.byref(n)) < 0  # needs the device's SM count
 
 
 def test_missing_library_raises(monkeypatch):
