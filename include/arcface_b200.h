@@ -64,6 +64,8 @@ int32_t arcface_b200_normalize_cast(const float* src, int64_t rows, int32_t D, u
  *   u = easy ? (t > 0 ? phi : t) : (t - th > 0 ? phi : t - mm);   z_label = s * u
  *   dphi = d u / d t   (cos_m + t sin_m / sine on the phi branch, 1 otherwise)
  *   label_local = label - class_offset
+ * inv_nw may be NULL: 1 / max(||w_y||, 1e-12) is then computed here from the label's weight row (so the call
+ * does not have to wait for the weight normalisation).
  * Rows whose label lives on another rank get z_label = 0, dphi = 0, label_local = -1.
  * A label outside [0, C_total) sets *bad_label_flag (device int32) to 1. */
 int32_t arcface_b200_label_margin(const float* x, const float* w, const float* inv_nx, const float* inv_nw,
@@ -87,6 +89,18 @@ int32_t arcface_b200_forward_stats(const uint16_t* xhat, const uint16_t* what,
                                    const int32_t* label_local, int32_t B, int32_t D, int64_t C_local, float s,
                                    float* part_max, float* part_sum, int32_t* part_arg, int32_t n_parts,
                                    void* stream);
+
+/* K1 (class weights) + K2 in ONE launch: helper warps of the forward kernel normalise and cast the fp32 class
+ * weights (outputs what / inv_nw, bit-identical to arcface_b200_normalize_cast) while the tcgen05 pipeline of the
+ * same kernel consumes the rows already published, reading them back from L2; the fp32 weights cross HBM once.
+ * Same partial-row outputs as arcface_b200_forward_stats (n_parts from arcface_b200_forward_parts).  Shapes the
+ * fused kernel does not cover (D > 512) run the two steps as separate launches behind the same call.
+ * workspace: arcface_b200_forward_fused_workspace_bytes() bytes of device memory (per-block ready counters). */
+int32_t arcface_b200_forward_fused_workspace_bytes(int32_t B, int32_t D, int64_t C_local, size_t* bytes);
+int32_t arcface_b200_forward_stats_fused(const uint16_t* xhat, const float* w, const int32_t* label_local, int32_t B,
+                                         int32_t D, int64_t C_local, float s, uint16_t* what, float* inv_nw,
+                                         float* part_max, float* part_sum, int32_t* part_arg, int32_t n_parts,
+                                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* Merge partial rows of one shard (ascending class order, first max wins) into row_max / row_sum /
  * row_arg (global class id = local + class_offset). */

@@ -35,6 +35,12 @@ SIGNATURES = {
         [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64, c_float, c_void_p, c_void_p, c_void_p,
          c_int32, c_void_p],
     ),
+    "arcface_b200_forward_fused_workspace_bytes": (c_int32, [c_int32, c_int32, c_int64, POINTER(c_size_t)]),
+    "arcface_b200_forward_stats_fused": (
+        c_int32,
+        [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+         c_void_p, c_int32, c_void_p, c_size_t, c_void_p],
+    ),
     "arcface_b200_combine_partials": (
         c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "arcface_b200_finalize_rows": (

@@ -1,5 +1,5 @@
 // C-ABI odds and ends of libarcface_b200: version / error string / device check, and the one-call
-// host-buffer step (H2D copies -> K1 -> label margin -> K2 -> combine -> K3 -> normalise backward ->
+// host-buffer step (H2D copies -> K1(x) -> label margin -> K1(w)+K2 -> combine -> K3 -> normalise backward ->
 // D2H copies) that a host without torch binds.  See include/arcface_b200.h.
 #include "host_util.h"
 
@@ -22,10 +22,10 @@ namespace {
 struct StepPlan {
     int Bp;
     int n_parts;
-    size_t bwd_bytes;
+    size_t bwd_bytes, fwd_bytes;
     size_t off_x, off_label, off_xhat, off_xhat_t, off_inv_nx, off_what, off_inv_nw, off_t, off_z, off_dphi,
         off_lab_local, off_flag, off_pmax, off_psum, off_parg, off_rmax, off_rsum, off_rarg, off_lse, off_argmax,
-        off_zout, off_omp, off_loss, off_dxhat, off_dx, off_bwd, total;
+        off_zout, off_omp, off_loss, off_dxhat, off_dx, off_fwd, off_bwd, total;
 };
 
 size_t bump(size_t& cur, size_t bytes) {
@@ -37,6 +37,7 @@ size_t bump(size_t& cur, size_t bytes) {
 int32_t plan_step(int32_t B, int32_t D, int64_t C, StepPlan* pl) {
     if (int32_t rc = arcface_b200_forward_parts(B, D, C, &pl->n_parts)) return rc;
     if (int32_t rc = arcface_b200_backward_workspace_bytes(B, D, C, &pl->bwd_bytes)) return rc;
+    if (int32_t rc = arcface_b200_forward_fused_workspace_bytes(B, D, C, &pl->fwd_bytes)) return rc;
     pl->Bp = ((B + 63) / 64) * 64;
     size_t cur = 0;
     const size_t b = static_cast<size_t>(B), d = static_cast<size_t>(D), c = static_cast<size_t>(C);
@@ -65,6 +66,7 @@ int32_t plan_step(int32_t B, int32_t D, int64_t C, StepPlan* pl) {
     pl->off_loss = bump(cur, 4);
     pl->off_dxhat = bump(cur, b * d * 4);
     pl->off_dx = bump(cur, b * d * 4);
+    pl->off_fwd = bump(cur, pl->fwd_bytes);
     pl->off_bwd = bump(cur, pl->bwd_bytes);
     pl->total = cur;
     return ARCFACE_B200_OK;
@@ -129,12 +131,12 @@ extern "C" int32_t arcface_b200_step_host(const float* x_host, const int64_t* la
     AB_CHECK_CUDA(cudaMemsetAsync(flag, 0, 4, st));
     // the xhat^T padding columns [B, Bp) are never read (TMA extent = B), no need to clear them
     if (int32_t rc = arcface_b200_normalize_cast(x, B, D, xhat, inv_nx, xhat_t, pl.Bp, st)) return rc;
-    if (int32_t rc = arcface_b200_normalize_cast(w_dev, C, D, what, inv_nw, nullptr, 0, st)) return rc;
-    if (int32_t rc = arcface_b200_label_margin(x, w_dev, inv_nx, inv_nw, label, B, D, C, 0, C, s, cos_m, sin_m, th, mm,
+    if (int32_t rc = arcface_b200_label_margin(x, w_dev, inv_nx, nullptr, label, B, D, C, 0, C, s, cos_m, sin_m, th, mm,
                                                easy_margin, t_label, z_label, dphi, lab_local, flag, st))
         return rc;
-    if (int32_t rc = arcface_b200_forward_stats(xhat, what, lab_local, B, D, C, s, pmax, psum, parg,
-                                                pl.n_parts, st))
+    // K1 of the class weights runs inside the forward kernel (what / inv_nw are its outputs)
+    if (int32_t rc = arcface_b200_forward_stats_fused(xhat, w_dev, lab_local, B, D, C, s, what, inv_nw, pmax, psum, parg,
+                                                      pl.n_parts, ws + pl.off_fwd, pl.fwd_bytes, st))
         return rc;
     if (int32_t rc = arcface_b200_combine_partials(pmax, psum, parg, pl.n_parts, B, 0, rmax, rsum, rarg, st)) return rc;
     if (int32_t rc = arcface_b200_finalize_rows(rmax, rsum, rarg, z_label, label, 1, B, lse, argmax, zout, omp, loss, st)) return rc;

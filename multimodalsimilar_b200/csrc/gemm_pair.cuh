@@ -17,7 +17,9 @@
 // P::RES_A == false: the streamed operand is A (its rows are the accumulator rows), the resident one is B.
 // P::RES_A == true : the resident operand is A, the streamed one is B (accumulator columns).
 // Roles (384 threads): warp 0 TMA producer (both CTAs), warp 1 MMA issuer (leader CTA only), warp 2 TMEM
-// allocator, warps 4-11 epilogue (two per TMEM lane quadrant, 128 accumulator columns each).
+// allocator, warps 4-11 epilogue (two per TMEM lane quadrant, 128 accumulator columns each).  A policy may add
+// P::AUX_WARPS helper warps (12 ...) that run P::aux() beside the GEMM -- the forward uses them to normalise
+// and cast the class weights it is about to stream -- and gates each streamed tile on P::acquire_tile().
 // Barriers: full[] / tempty[] / res live in the LEADER's shared memory (both CTAs' producers and epilogues
 // arrive there through shared::cluster addresses); empty[] / tfull[] exist in both CTAs and are signalled by
 // multicast tcgen05.commit.
@@ -93,7 +95,7 @@ struct Stager {
 };
 
 template <class P>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS + P::AUX_WARPS * 32, 1)
 pair_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmR,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ typename P::Params prm,
                  const int extra_bytes) {
@@ -164,6 +166,12 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // A policy with helper warps may let the light roles hand registers to the helper warpgroups (P::AUX_REGS > 0;
+    // setmaxnreg is executed by whole warpgroups -- warps 0-3, 4-11, 12-... -- at the top of the branch that holds
+    // the role's code, so that ptxas allocates each role against its own limit; the pool is what the CTA was
+    // launched with, threads x registers, not the whole register file).
+    if (warp < 4) {
+    if constexpr (P::AUX_REGS > 0) setmaxnreg_dec<P::LOW_REGS>();
     if (warp == 0) {
         // ---------------- TMA producer (both CTAs): whole warp walks the schedule, one elected lane issues
         const uint32_t res_bar_leader = mapa_u32(smem_u32(res_bar), 0);
@@ -177,6 +185,7 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
         uint32_t phase = 0;
         for (int i = i_begin; i < i_end; i += i_step) {
             const int row = co.s_row0 + i * 2 * ROWS + rank * ROWS;
+            P::acquire_tile(prm, i, rank, lane);  // whole warp; returns once this CTA's 128 rows may be fetched
             const int ip = i + co.prefetch_tiles * i_step;
             const bool pf = co.prefetch_tiles > 0 && ip < i_end;
             for (int kb = 0; kb < kblocks; ++kb) {
@@ -229,8 +238,10 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
                 if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else if (warp >= 4) {
+    }
+    } else if (warp < 4 + EPI_WARPS) {
         // ---------------- epilogue (both CTAs)
+        if constexpr (P::AUX_REGS > 0) setmaxnreg_dec<P::EPI_REGS>();
         EpiCtx ctx;
         ctx.extra = sExtra;
         ctx.staging = smem_u32(sStaging) + (warp - 4) * STAGING_PER_WARP;
@@ -257,6 +268,10 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
             if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
         }
         epi.finish();
+    } else if constexpr (P::AUX_WARPS > 0) {
+        if constexpr (P::AUX_REGS > 0) setmaxnreg_inc<P::AUX_REGS>();
+        P::aux(prm, static_cast<int>(blockIdx.x) * P::AUX_WARPS + (warp - 4 - EPI_WARPS),
+               static_cast<int>(gridDim.x) * P::AUX_WARPS, lane);
     }
 
     // neither CTA may leave (or free TMEM) while the peer can still touch its barriers / shared memory / TMEM
@@ -281,7 +296,8 @@ static int32_t launch_pair(const CUtensorMap& tmS, const CUtensorMap& tmR, const
         AB_CHECK_CUDA(cudaFuncSetAttribute(pair_gemm_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured[dev] = true;
     }
-    pair_gemm_kernel<P><<<2 * groups * prm.core.n_res, THREADS, smem, st>>>(tmS, tmR, tmC, prm, extra_bytes);
+    pair_gemm_kernel<P><<<2 * groups * prm.core.n_res, THREADS + P::AUX_WARPS * 32, smem, st>>>(tmS, tmR, tmC, prm,
+                                                                                                  extra_bytes);
     AB_CHECK_CUDA(cudaGetLastError());
     return ARCFACE_B200_OK;
 }

@@ -148,11 +148,29 @@ struct FwdStats {
 // What rows (256 classes per tile = accumulator columns, each CTA loads 128 of them), K = D <= 512.  Each pair
 // walks a contiguous class range; the two epilogue warps of a TMEM lane quadrant take 128 columns each and
 // keep separate partial rows (slot = 2 * range + half), merged by combine_partials.
-struct FwdStatsP {
+//
+// NORM = true additionally runs K1 for the class weights INSIDE this kernel (arcface.py:47, F.normalize of the
+// weight): eight helper warps per CTA read the fp32 rows, write bf16 what + 1/||w|| and publish one counter
+// per 128-row block; the TMA producer of a CTA waits for the counter of the block it is about to fetch, so the
+// bf16 rows are read back from L2 and the fp32 weights cross HBM exactly once per step for the forward.
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+template <bool NORM>
+struct FwdStatsPairT {
     static constexpr int STAGES = 4;
     static constexpr bool STAGING = false;
     static constexpr bool RES_A = true;
     static constexpr int NROW = 2 * pr::ROWS;
+    static constexpr int AUX_WARPS = NORM ? 8 : 0;
+    // setmaxnreg register reallocation between the roles (gemm_pair.cuh): off (0) -- see aux() below
+    static constexpr int LOW_REGS = 0, EPI_REGS = 0, AUX_REGS = 0;
+    static constexpr int RUN = 32;  // consecutive rows a helper warp normalises between two counter updates
 
     struct Params {
         pr::Core core;
@@ -163,9 +181,130 @@ struct FwdStatsP {
         float* part_max;
         float* part_sum;
         int* part_arg;
+        // NORM only
+        int D;
+        const float* w;          // fp32 class weights [C][D]
+        __nv_bfloat16* what;     // out: bf16 normalised weights [C][D]
+        float* inv_nw;           // out: 1 / max(||w||, 1e-12)
+        int* ready;              // [ceil(C / 128)] rows published per 128-row block (zeroed before the launch)
+        int debug;               // measurements only: 1 = the GEMM does not wait for the helper warps
     };
 
     __device__ static void prologue(const Params&, uint8_t*, int, int, int) {}
+
+    __device__ static void acquire_tile(const Params& p, int i, int rank, int lane) {
+        if constexpr (NORM) {
+            const int blk = i * 2 + rank;
+            const int need = min(pr::ROWS, p.C - blk * pr::ROWS);
+            if (need > 0 && p.debug != 1) {
+                if (lane == 0) wait_counter_ge(p.ready + blk, need);
+                __syncwarp();
+                fence_proxy_async_all();  // the rows were written with ordinary stores, TMA reads them
+            }
+        }
+    }
+
+    // two rows of up to 512 floats per lane pair of chunks: lane l owns the 8-float chunks l and l + 32
+    struct RowPair {
+        float4 v[2][2][2];  // [row][chunk][half]
+    };
+    __device__ static __forceinline__ void load_pair(const Params& p, int64_t r0, int lane, RowPair& rp) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int64_t row = min(r0 + r, static_cast<int64_t>(p.C) - 1);  // clamp: the tail re-reads the last row
+            const float* src = p.w + row * p.D;
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const int d = (lane + 32 * ch) * 8;
+                if (d < p.D) {
+                    rp.v[r][ch][0] = ldg_stream4(src + d);
+                    rp.v[r][ch][1] = ldg_stream4(src + d + 4);
+                } else {
+                    rp.v[r][ch][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    rp.v[r][ch][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+    }
+    __device__ static __forceinline__ void store_pair(const Params& p, int64_t r0, int lane, const RowPair& rp) {
+        float ss[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            float a = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {  // same order as normalize_cast_kernel: bit-identical norms
+                const float4 x = rp.v[r][ch][0], y = rp.v[r][ch][1];
+                a += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+                a += y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w;
+            }
+            ss[r] = a;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ss[0] += __shfl_xor_sync(0xffffffffu, ss[0], o);
+            ss[1] += __shfl_xor_sync(0xffffffffu, ss[1], o);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int64_t row = r0 + r;
+            if (row >= p.C) break;
+            const float inv = 1.0f / fmaxf(sqrtf(ss[r]), 1e-12f);
+            if (lane == 0) p.inv_nw[row] = inv;
+            __nv_bfloat16* dst = p.what + row * p.D;
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const int d = (lane + 32 * ch) * 8;
+                if (d < p.D) {
+                    const float4 x = rp.v[r][ch][0], y = rp.v[r][ch][1];
+                    uint4 o;
+                    o.x = pack_bf16x2(x.x * inv, x.y * inv);
+                    o.y = pack_bf16x2(x.z * inv, x.w * inv);
+                    o.z = pack_bf16x2(y.x * inv, y.y * inv);
+                    o.w = pack_bf16x2(y.z * inv, y.w * inv);
+                    *reinterpret_cast<uint4*>(dst + d) = o;
+                }
+            }
+        }
+    }
+
+    // helper warp u of nu: runs u, u + nu, ... of RUN consecutive rows, in the order the GEMM consumes them.
+    // The warp's rows form one sequence of row pairs j = 0, 1, ...; pair j + 1 is loading into registers while
+    // pair j is reduced and stored.  (Measured: a 4-deep register pipeline fed by setmaxnreg, and bulk L2
+    // prefetches ahead of the loads, were both slower than this -- the stage is bound by the fence + counter
+    // update that ends every run, not by the loads in flight.)
+    static constexpr int PPR = RUN / 2;  // pairs per run
+    __device__ static void aux(const Params& p, int u, int nu, int lane) {
+        if constexpr (NORM) {
+            const int64_t n_runs = (static_cast<int64_t>(p.C) + RUN - 1) / RUN;
+            if (u >= n_runs) return;
+            const int64_t n_pairs = ((n_runs - u + nu - 1) / nu) * PPR;  // of this warp (even)
+            auto row_of = [&](int64_t j) { return (u + (j / PPR) * nu) * RUN + (j % PPR) * 2; };
+            auto fetch = [&](int64_t j, RowPair& rp) {
+                if (j < n_pairs) load_pair(p, row_of(j), lane, rp);
+            };
+            auto retire = [&](int64_t j, const RowPair& rp) {
+                const int64_t r = row_of(j);
+                store_pair(p, r, lane, rp);
+                if (j % PPR == PPR - 1) {  // last pair of a run: publish its rows
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int64_t r0 = r - (RUN - 2);
+                        const int rows = static_cast<int>(min(static_cast<int64_t>(RUN), p.C - r0));
+                        if (rows > 0) red_relaxed_gpu_add(p.ready + (r0 / pr::ROWS), rows);
+                    }
+                }
+            };
+            RowPair a, b;
+            fetch(0, a);
+            for (int64_t j = 0; j < n_pairs; j += 2) {
+                fetch(j + 1, b);
+                retire(j, a);
+                fetch(j + 2, a);
+                retire(j + 1, b);
+            }
+        }
+    }
 
     struct Epi {
         const Params& p;
@@ -243,6 +382,9 @@ struct FwdStatsP {
         }
     };
 };
+
+using FwdStatsP = FwdStatsPairT<false>;
+using FwdStatsPN = FwdStatsPairT<true>;
 
 // ------------------------------------------------------------------ materialising epilogue
 struct FwdLogits {
@@ -362,6 +504,36 @@ static int32_t check_gemm_shape(const char* who, int32_t B, int32_t D, int64_t C
     return ARCFACE_B200_OK;
 }
 
+template <bool NORM>
+static int32_t launch_fwd_pairs(const uint16_t* xhat, const uint16_t* what, const float* w, float* inv_nw, int* ready,
+                                const int32_t* label_local, int32_t B, int32_t D, int64_t C_local, float s,
+                                float* part_max, float* part_sum, int32_t* part_arg, int32_t n_parts, cudaStream_t st) {
+    using P = FwdStatsPairT<NORM>;
+    typename P::Params p;
+    int groups;
+    fwd_pair_partition(B, C_local, sm_count(), &p.core.n_res, &groups, &p.core.s_blocks);
+    AB_REQUIRE(n_parts == 2 * groups, ARCFACE_B200_E_WORKSPACE, "forward_stats: n_parts=%d, expected %d", n_parts,
+               2 * groups);
+    p.core.kblocks = (D + pr::BK - 1) / pr::BK;
+    p.core.s_row0 = 0;
+    // NORM: the helper warps publish rows in ascending order, so the pairs walk the tiles interleaved
+    // (tile t at step t / groups); otherwise every pair takes a contiguous class range
+    p.core.contiguous = NORM ? 0 : 1;
+    p.core.prefetch_tiles = NORM ? 0 : 2;  // NORM: the rows come out of L2 anyway (just written there)
+    p.B = B; p.C = static_cast<int>(C_local); p.s = s;
+    p.label_local = label_local;
+    p.part_max = part_max; p.part_sum = part_sum; p.part_arg = part_arg;
+    p.D = D; p.w = w; p.what = reinterpret_cast<__nv_bfloat16*>(const_cast<uint16_t*>(what));
+    p.inv_nw = inv_nw; p.ready = ready;
+    p.debug = 0;
+    if (const char* dbg = getenv("ARCFACE_B200_FWD_DEBUG")) p.debug = atoi(dbg);
+    if (p.debug == 2) p.core.s_blocks = 0;  // measurements only: helper warps alone
+    CUtensorMap tmS, tmR;
+    if (int32_t rc = make_tmap_kmajor(&tmS, what, D, C_local, D, pr::ROWS)) return rc;
+    if (int32_t rc = make_tmap_kmajor(&tmR, xhat, D, B, D, pr::ROWS)) return rc;
+    return pr::launch_pair<P>(tmS, tmR, tmS, p, groups, 0, st);
+}
+
 extern "C" int32_t arcface_b200_forward_parts(int32_t B, int32_t D, int64_t C_local, int32_t* n_parts) {
     if (int32_t rc = check_arch()) return rc;
     AB_REQUIRE(n_parts, ARCFACE_B200_E_ARG, "forward_parts: null pointer");
@@ -386,24 +558,9 @@ extern "C" int32_t arcface_b200_forward_stats(const uint16_t* xhat, const uint16
     AB_REQUIRE(xhat && what && part_max && part_sum && part_arg, ARCFACE_B200_E_ARG, "forward_stats: null pointer");
     AB_REQUIRE(s > 0.f, ARCFACE_B200_E_ARG, "forward_stats: scale s must be positive");
     if (int32_t rc = check_gemm_shape("forward_stats", B, D, C_local)) return rc;
-    if (fwd_use_pairs(D, sm_count())) {
-        FwdStatsP::Params p;
-        int groups;
-        fwd_pair_partition(B, C_local, sm_count(), &p.core.n_res, &groups, &p.core.s_blocks);
-        AB_REQUIRE(n_parts == 2 * groups, ARCFACE_B200_E_WORKSPACE, "forward_stats: n_parts=%d, expected %d", n_parts,
-                   2 * groups);
-        p.core.kblocks = (D + pr::BK - 1) / pr::BK;
-        p.core.s_row0 = 0;
-        p.core.contiguous = 1;
-        p.core.prefetch_tiles = 2;
-        p.B = B; p.C = static_cast<int>(C_local); p.s = s;
-        p.label_local = label_local;
-        p.part_max = part_max; p.part_sum = part_sum; p.part_arg = part_arg;
-        CUtensorMap tmS, tmR;
-        if (int32_t rc = make_tmap_kmajor(&tmS, what, D, C_local, D, pr::ROWS)) return rc;
-        if (int32_t rc = make_tmap_kmajor(&tmR, xhat, D, B, D, pr::ROWS)) return rc;
-        return pr::launch_pair<FwdStatsP>(tmS, tmR, tmS, p, groups, 0, static_cast<cudaStream_t>(stream));
-    }
+    if (fwd_use_pairs(D, sm_count()))
+        return launch_fwd_pairs<false>(xhat, what, nullptr, nullptr, nullptr, label_local, B, D, C_local, s, part_max,
+                                       part_sum, part_arg, n_parts, static_cast<cudaStream_t>(stream));
     FwdStats::Params p;
     fwd_partition(B, C_local, sm_count(), &p.m_tiles, &p.n_tiles, &p.groups, &p.tiles_per_g);
     AB_REQUIRE(n_parts == p.groups, ARCFACE_B200_E_WORKSPACE, "forward_stats: n_parts=%d, expected %d", n_parts,
@@ -415,6 +572,43 @@ extern "C" int32_t arcface_b200_forward_stats(const uint16_t* xhat, const uint16
     if (int32_t rc = make_tmap_kmajor(&tmA, xhat, D, B, D, BLOCK_M)) return rc;
     if (int32_t rc = make_tmap_kmajor(&tmB, what, D, C_local, D, FwdStats::BLOCK_N)) return rc;
     return launch_gemm<FwdStats>(tmA, tmB, tmA, p, p.groups * p.m_tiles, 0, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int32_t arcface_b200_forward_fused_workspace_bytes(int32_t B, int32_t D, int64_t C_local, size_t* bytes) {
+    if (int32_t rc = check_arch()) return rc;
+    AB_REQUIRE(bytes, ARCFACE_B200_E_ARG, "forward_fused_workspace_bytes: null pointer");
+    if (int32_t rc = check_gemm_shape("forward_fused_workspace_bytes", B, D, C_local)) return rc;
+    *bytes = static_cast<size_t>((C_local + pr::ROWS - 1) / pr::ROWS) * sizeof(int) + 256;
+    return ARCFACE_B200_OK;
+}
+
+extern "C" int32_t arcface_b200_forward_stats_fused(const uint16_t* xhat, const float* w, const int32_t* label_local,
+                                                    int32_t B, int32_t D, int64_t C_local, float s, uint16_t* what,
+                                                    float* inv_nw, float* part_max, float* part_sum,
+                                                    int32_t* part_arg, int32_t n_parts, void* workspace,
+                                                    size_t workspace_bytes, void* stream) {
+    if (int32_t rc = check_arch()) return rc;
+    AB_REQUIRE(xhat && w && what && inv_nw && part_max && part_sum && part_arg && workspace, ARCFACE_B200_E_ARG,
+               "forward_stats_fused: null pointer");
+    AB_REQUIRE(s > 0.f, ARCFACE_B200_E_ARG, "forward_stats_fused: scale s must be positive");
+    if (int32_t rc = check_gemm_shape("forward_stats_fused", B, D, C_local)) return rc;
+    AB_REQUIRE(aligned16(w) && aligned16(what) && aligned16(workspace), ARCFACE_B200_E_LAYOUT,
+               "forward_stats_fused: pointers must be 16-byte aligned");
+    const char* impl = getenv("ARCFACE_B200_FWD_IMPL");
+    const bool split = impl != nullptr && strcmp(impl, "split") == 0;  // A/B: K1 and K2 as two launches
+    if (!fwd_use_pairs(D, sm_count()) || split) {
+        // shapes the in-kernel normaliser does not cover: the same two steps as separate launches
+        if (int32_t rc = arcface_b200_normalize_cast(w, C_local, D, what, inv_nw, nullptr, 0, stream)) return rc;
+        return arcface_b200_forward_stats(xhat, what, label_local, B, D, C_local, s, part_max, part_sum, part_arg,
+                                          n_parts, stream);
+    }
+    const size_t flag_bytes = static_cast<size_t>((C_local + pr::ROWS - 1) / pr::ROWS) * sizeof(int);
+    AB_REQUIRE(workspace_bytes >= flag_bytes, ARCFACE_B200_E_WORKSPACE, "forward_stats_fused: workspace %zu < required %zu",
+               workspace_bytes, flag_bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    AB_CHECK_CUDA(cudaMemsetAsync(workspace, 0, flag_bytes, st));
+    return launch_fwd_pairs<true>(xhat, what, w, inv_nw, static_cast<int*>(workspace), label_local, B, D, C_local, s,
+                                  part_max, part_sum, part_arg, n_parts, st);
 }
 
 extern "C" int32_t arcface_b200_logits(const uint16_t* xhat, const uint16_t* what, const float* z_label,

@@ -561,6 +561,8 @@ struct BwdDWr {
 // Xhat (accumulator columns), K = D <= 512.
 struct BwdDCp {
     static constexpr int STAGES = 3;  // 3 x 16 KB: the per-column constants below take the fourth stage's room
+    static constexpr int AUX_WARPS = 0;
+    static constexpr int LOW_REGS = 0, EPI_REGS = 0, AUX_REGS = 0;  // no helper warps, no register reallocation
     static constexpr bool STAGING = true;
     static constexpr bool RES_A = false;
     static constexpr int NCOL = 2 * pr::ROWS;  // batch columns of one pair
@@ -599,6 +601,9 @@ struct BwdDCp {
             }
         }
     }
+
+    __device__ static void acquire_tile(const Params&, int, int, int) {}
+    __device__ static void aux(const Params&, int, int, int) {}
 
     struct Epi {
         const Params& p;
@@ -682,6 +687,8 @@ struct BwdDCp {
 // accumulator), K = batch <= 512.
 struct BwdDWp {
     static constexpr int STAGES = 4;
+    static constexpr int AUX_WARPS = 0;
+    static constexpr int LOW_REGS = 0, EPI_REGS = 0, AUX_REGS = 0;  // no helper warps, no register reallocation
     static constexpr bool STAGING = true;
     static constexpr bool RES_A = false;
     static constexpr int NCOL = 2 * pr::ROWS;
@@ -698,6 +705,8 @@ struct BwdDWp {
     static constexpr int EXTRA_BYTES = 0;
 
     __device__ static void prologue(const Params&, uint8_t*, int, int, int) {}
+    __device__ static void acquire_tile(const Params&, int, int, int) {}
+    __device__ static void aux(const Params&, int, int, int) {}
 
     struct Epi {
         const Params& p;

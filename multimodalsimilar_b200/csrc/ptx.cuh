@@ -74,6 +74,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// ---------------------------------------------------------------- cross-SM flags in global memory
+// Producer side: every writing thread runs __threadfence(), the warp syncs, one lane bumps the counter.
+// Consumer side: poll with an acquire load, then (if the data is fetched by TMA) fence_proxy_async_all().
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_relaxed_gpu_add(int* p, int v) {  // after __threadfence()
+    asm volatile("red.relaxed.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// orders generic-proxy accesses (the acquire above, ordinary stores) against async-proxy accesses (TMA) in
+// every state space
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void wait_counter_ge(const int* p, int target) {
+    uint32_t spins = 0;
+    while (ld_acquire_gpu(p) < target) {
+        __nanosleep(40);
+        if (++spins > (AB_SPIN_LIMIT >> 4)) __trap();
+    }
+}
+
 // ---------------------------------------------------------------- TMA loads
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -99,6 +121,11 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int32_t c0
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
                  ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
                  : "memory");
+}
+
+// warm L2 with `bytes` (multiple of 16) of contiguous global memory: no registers, no shared memory, no barrier
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
 
 // ---------------------------------------------------------------- TMA stores (shared -> global, bulk async-group)
@@ -273,6 +300,16 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn, bool b_mn) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
            (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- register reallocation between warpgroups
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 
 // ---------------------------------------------------------------- misc

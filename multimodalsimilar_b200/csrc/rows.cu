@@ -130,15 +130,18 @@ label_margin_kernel(const float* __restrict__ x, const float* __restrict__ w, co
     }
     const float* xp = x + static_cast<int64_t>(b) * D;
     const float* wp = w + loc * D;
-    float dot = 0.f;
+    float dot = 0.f, ww = 0.f;
     for (int d = lane * 4; d < D; d += 128) {
         const float4 a = *reinterpret_cast<const float4*>(xp + d);
         const float4 c = *reinterpret_cast<const float4*>(wp + d);
         dot += a.x * c.x + a.y * c.y + a.z * c.z + a.w * c.w;
+        ww += c.x * c.x + c.y * c.y + c.z * c.z + c.w * c.w;
     }
     dot = warp_sum(dot);
+    ww = warp_sum(ww);
     if (lane == 0) {
-        const float t = dot * inv_nx[b] * inv_nw[loc];
+        const float inw = (inv_nw != nullptr) ? inv_nw[loc] : 1.0f / fmaxf(sqrtf(ww), 1e-12f);
+        const float t = dot * inv_nx[b] * inw;
         // reference: sqrt(1 - cos^2) unclamped (arcface.py:49); clamped here so |t| = 1 + ulp cannot NaN
         const float sine = sqrtf(fmaxf(0.f, 1.f - t * t));
         const float phi = t * cos_m - sine * sin_m;
@@ -318,7 +321,7 @@ extern "C" int32_t arcface_b200_label_margin(const float* x, const float* w, con
                                              float th, float mm, int32_t easy_margin, float* t_label, float* z_label,
                                              float* dphi, int32_t* label_local, int32_t* bad_label_flag, void* stream) {
     if (int32_t rc = check_arch()) return rc;
-    AB_REQUIRE(x && w && inv_nx && inv_nw && label && t_label && z_label && dphi && label_local, ARCFACE_B200_E_ARG,
+    AB_REQUIRE(x && w && inv_nx && label && t_label && z_label && dphi && label_local, ARCFACE_B200_E_ARG,
                "label_margin: null pointer");
     AB_REQUIRE(B >= 0 && D >= 8 && D % 8 == 0 && C_local >= 1, ARCFACE_B200_E_SHAPE, "label_margin: bad shape");
     AB_REQUIRE(aligned16(x) && aligned16(w), ARCFACE_B200_E_LAYOUT, "label_margin: x / w must be 16-byte aligned");

@@ -26,7 +26,7 @@ from . import ops
 class ArcFaceCEFunction(torch.autograd.Function):
     """loss, argmax = ArcFaceCE(x, weight, label; s, m, easy_margin).
 
-    forward : K1 (x), K1 (weight), label margin, K2 (+combine, finalize)
+    forward : K1 (x), label margin, K1 (weight) fused into K2 (+combine, finalize)
     backward: K3 (dC^T producer, dW GEMM, dX GEMM) + normalise backward for x
     Saved for backward: xhat / xhat^T / what (bf16), the inverse norms, lse, z_label, dphi, labels --
     no B x C tensor.
@@ -37,9 +37,8 @@ class ArcFaceCEFunction(torch.autograd.Function):
         B, D = x.shape
         C = weight.shape[0]
         xhat, inv_nx, xhat_t = ops.normalize_cast(x, want_transpose=True)
-        what, inv_nw, _ = ops.normalize_cast(weight)
-        lm = ops.label_margin(x, weight, inv_nx, inv_nw, label, 0, C, s, m, easy_margin)
-        rmax, rsum, rarg = ops.forward_rows(xhat, what, lm.label_local, s, 0)
+        lm = ops.label_margin(x, weight, inv_nx, None, label, 0, C, s, m, easy_margin)
+        what, inv_nw, rmax, rsum, rarg = ops.forward_rows_fused(xhat, weight, lm.label_local, s, 0)
         lse, argmax, _z, omp, loss = ops.finalize_rows(rmax.view(1, B), rsum.view(1, B), rarg.view(1, B),
                                                        lm.z_label.view(1, B), label)
         if validate_labels and int(lm.bad_flag.item()) != 0:

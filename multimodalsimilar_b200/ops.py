@@ -121,6 +121,35 @@ def forward_rows(xhat, what, label_local, s: float, class_offset: int = 0):
     return rmax, rsum, rarg
 
 
+def forward_rows_fused(xhat, weight, label_local, s: float, class_offset: int = 0):
+    """K1 (class weights) + K2 + per-shard combine in one GEMM launch: the forward kernel's helper warps
+    normalise and cast `weight` (fp32 [C, D]) while its tcgen05 pipeline consumes the rows already
+    published.  Returns (what bf16 [C, D], inv_nw fp32 [C], row_max, row_sum, row_arg) -- the first two are
+    bit-identical to `normalize_cast(weight)`."""
+    _req(xhat, torch.bfloat16, "xhat")
+    _req(weight, torch.float32, "weight")
+    B, D = xhat.shape
+    C = weight.shape[0]
+    dev = xhat.device
+    what = torch.empty((C, D), dtype=torch.bfloat16, device=dev)
+    inv_nw = torch.empty((C,), dtype=torch.float32, device=dev)
+    n_parts = forward_parts(B, D, C)
+    pmax = torch.empty((n_parts, B), dtype=torch.float32, device=dev)
+    psum = torch.empty((n_parts, B), dtype=torch.float32, device=dev)
+    parg = torch.empty((n_parts, B), dtype=torch.int32, device=dev)
+    nws = ctypes.c_size_t(0)
+    _lib.call("arcface_b200_forward_fused_workspace_bytes", B, D, C, ctypes.byref(nws))
+    ws = torch.empty(max(16, nws.value), dtype=torch.uint8, device=dev)
+    _lib.call("arcface_b200_forward_stats_fused", _ptr(xhat), _ptr(weight), _ptr(label_local), B, D, C, s,
+              _ptr(what), _ptr(inv_nw), _ptr(pmax), _ptr(psum), _ptr(parg), n_parts, _ptr(ws), ws.numel(), _stream())
+    rmax = torch.empty(B, dtype=torch.float32, device=dev)
+    rsum = torch.empty(B, dtype=torch.float32, device=dev)
+    rarg = torch.empty(B, dtype=torch.int64, device=dev)
+    _lib.call("arcface_b200_combine_partials", _ptr(pmax), _ptr(psum), _ptr(parg), n_parts, B, class_offset,
+              _ptr(rmax), _ptr(rsum), _ptr(rarg), _stream())
+    return what, inv_nw, rmax, rsum, rarg
+
+
 def finalize_rows(rows_max, rows_sum, rows_arg, rows_z, label):
     """Merge [R, B] per-rank rows of the non-label columns with the label logits ->
     (lse [B], argmax int64 [B], z_label [B], one_minus_p [B], loss [])."""

@@ -78,10 +78,10 @@ class ShardedArcFaceCE(torch.autograd.Function):
         x_all = _all_gather_rows(x_local, group)
         y_all = _all_gather_rows(label_local, group)
         xhat, inv_nx, xhat_t = K.normalize_cast(x_all, want_transpose=True)
-        what, inv_nw, _ = K.normalize_cast(w_shard)
-        lm = K.label_margin(x_all, w_shard, inv_nx, inv_nw, y_all, head.class_lo, head.out_feature, float(head.s),
+        lm = K.label_margin(x_all, w_shard, inv_nx, None, y_all, head.class_lo, head.out_feature, float(head.s),
                             float(head.m), bool(head.easy_margin))
-        rmax, rsum, rarg = K.forward_rows(xhat, what, lm.label_local, float(head.s), head.class_lo)
+        what, inv_nw, rmax, rsum, rarg = K.forward_rows_fused(xhat, w_shard, lm.label_local, float(head.s),
+                                                              head.class_lo)
         packed = _all_gather_rows(_pack_rows(rmax, rsum, lm.z_label, rarg), group)
         rows_max, rows_sum, rows_z, rows_arg = _unpack_rows(packed, B)
         lse, argmax, _z, omp, loss = K.finalize_rows(rows_max, rows_sum, rows_arg, rows_z, y_all)

@@ -21,6 +21,8 @@ def label_margin(x, w, inv_nx, inv_nw, label, class_offset, c_total, s, m, easy_
     loc = label - class_offset
     own = (loc >= 0) & (loc < C)
     lc = loc.clamp(0, C - 1)
+    if inv_nw is None:
+        inv_nw = 1.0 / w.double().norm(dim=1).clamp_min(1e-12)
     t = (x.double() * w.double()[lc]).sum(1) * inv_nx * inv_nw[lc]
     sine = (1.0 - t * t).clamp_min(0).sqrt()
     phi = t * math.cos(m) - sine * math.sin(m)
@@ -47,6 +49,11 @@ def forward_rows(xhat, what, label_local, s, class_offset=0):
     rarg = (z == rmax[:, None]).int().argmax(dim=1)  # first maximum
     rsum = torch.where(torch.isinf(rmax), torch.zeros_like(rmax), (z - rmax[:, None]).exp().sum(1))
     return rmax.float(), rsum.float(), (rarg + class_offset).long()
+
+
+def forward_rows_fused(xhat, weight, label_local, s, class_offset=0):
+    what, inv_nw, _ = normalize_cast(weight)
+    return (what, inv_nw) + forward_rows(xhat, what, label_local, s, class_offset)
 
 
 def finalize_rows(rows_max, rows_sum, rows_arg, rows_z, label):

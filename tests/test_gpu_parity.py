@@ -201,6 +201,35 @@ def test_fused_statistics_match_materialised_logits(B, D, C, s):
     assert torch.equal(lm.label_local.long(), yt)
 
 
+# ----------------------------------------------------------------------------- K1(w) fused into K2
+@pytest.mark.parametrize("B,D,C,s", [(64, 512, 1000, 30.0), (512, 512, 40000, 64.0), (200, 64, 30000, 64.0),
+                                     (300, 256, 70001, 64.0), (512, 128, 129, 64.0), (3, 8, 2, 10.0),
+                                     (256, 1792, 3000, 64.0)])
+def test_fused_forward_equals_split_forward(B, D, C, s):
+    """arcface_b200_forward_stats_fused (weight normalise + cast inside the GEMM kernel, rows handed to the TMA
+    producer through per-block counters) must produce bit-identical what / inv_nw / statistics to the two
+    separate launches; the label margin computed without inv_nw must equal the one computed with it."""
+    from multimodalsimilar_b200 import ops
+
+    x, w, y = onp.synthetic_inputs(B, D, C, seed=7 * B + C)
+    xt, wt, yt = _t(x), _t(w), _t(y)
+    xhat, inv_nx, _ = ops.normalize_cast(xt)
+    what, inv_nw, _ = ops.normalize_cast(wt)
+    lm = ops.label_margin(xt, wt, inv_nx, inv_nw, yt, 0, C, s, 0.4, False)
+    lm2 = ops.label_margin(xt, wt, inv_nx, None, yt, 0, C, s, 0.4, False)
+    assert float((lm.t_label - lm2.t_label).abs().max()) <= 1e-6
+    assert float((lm.z_label - lm2.z_label).abs().max()) <= 1e-4
+    assert torch.equal(lm.label_local, lm2.label_local)
+    rmax, rsum, rarg = ops.forward_rows(xhat, what, lm.label_local, s, 0)
+    for _ in range(3):  # the counters are re-armed on every call
+        what2, inv_nw2, rmax2, rsum2, rarg2 = ops.forward_rows_fused(xhat, wt, lm.label_local, s, 0)
+        assert torch.equal(what2.view(torch.int16), what.view(torch.int16))
+        assert torch.equal(inv_nw2, inv_nw)
+        assert torch.equal(rmax2, rmax)
+        assert torch.equal(rarg2, rarg)
+        assert float(((rsum2 - rsum).abs() / rsum.abs().clamp_min(1e-30)).max()) <= 1e-5
+
+
 # ----------------------------------------------------------------------------- backward vs oracle (medium)
 @pytest.mark.parametrize("B,D,C,s,m,easy,trained", [
     (64, 64, 1000, 30.0, 0.5, False, False),
