@@ -250,7 +250,8 @@ def main():
 
     # ---- kernel launches per step (our kernels only; memset / NCCL not counted)
     _, n_chunks = ops.backward_plan(B, D, c_hi - c_lo)
-    launches_per_step = 1 + 1 + 1 + 1 + 1 + 3 * n_chunks + 1  # K1(x), label, K1(w)+K2, combine, finalize, K3, bwd-x
+    k3_launches = ops.backward_launches(B, D, c_hi - c_lo)
+    launches_per_step = 1 + 1 + 1 + 1 + 1 + k3_launches + 1  # K1(x), label, K1(w)+K2, combine, finalize, K3, bwd-x
     gpu_launches = launches_per_step * args.steps
 
     # ---- end-to-end with host buffers
@@ -321,7 +322,8 @@ def main():
     cand = {
         "fwd": fwd_cand + ("K1(w)+K2 forward: in-kernel weight normalise/cast + cosine GEMM + softmax epilogue",),
         "k3": ("tensor", 4.0 * B * D * c_loc / 1e12, "TFLOP/s", p_tensor,
-               "K3 backward (dC^T producer + dW GEMM + dX GEMM, %d chunks)" % n_chunks),
+               "K3 backward (dC^T producer + dW GEMM + dX GEMM, %s)"
+               % ("one persistent launch, dC^T through an L2 ring" if k3_launches == 1 else "%d chunks" % n_chunks)),
     }
     top = max(cand, key=lambda k: stages[k])
     bnd, work, unit, peak, name = cand[top]

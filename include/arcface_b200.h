@@ -130,9 +130,14 @@ int32_t arcface_b200_backward_workspace_bytes(int32_t B, int32_t D, int64_t C_lo
 /* How arcface_b200_backward walks the classes: classes per scratch chunk and number of chunks
  * (each chunk is three kernel launches: dC^T producer, dW GEMM, dX GEMM). */
 int32_t arcface_b200_backward_plan(int32_t B, int32_t D, int64_t C_local, int64_t* chunk_classes, int32_t* n_chunks);
+/* Kernels arcface_b200_backward launches for this shape: 1 when the single-launch backward applies (B, D <= 512:
+ * the dC^T / dW / dX contractions run as roles of one persistent kernel and exchange dC^T through an L2-resident
+ * ring), otherwise 3 per scratch chunk. */
+int32_t arcface_b200_backward_launches(int32_t B, int32_t D, int64_t C_local, int32_t* n_kernels);
 
 /* K3 -- backward of the head + cross-entropy (loss.backward() through arcface.py:45-63).
- * Recomputes p = exp(z - lse) tile by tile from the saved row statistics, forms
+ * Recomputes p = exp(z - lse) tile by tile from the saved row statistics (the B x C matrix is never stored;
+ * with B, D <= 512 not even a full dC^T scratch: see arcface_b200_backward_launches), forms
  *   dC[b, c] = s * grad_scale * p            (c != label)
  *   dC[b, y] = -s * grad_scale * one_minus_p[b] * dphi[b]      (one_minus_p from arcface_b200_finalize_rows)
  * and runs dXhat = dC . What (accumulated into the zeroed dxhat) and dWhat = dC^T . Xhat; the epilogue of

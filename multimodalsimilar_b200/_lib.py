@@ -50,6 +50,7 @@ SIGNATURES = {
         c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64, c_float, c_void_p, c_int64, c_void_p]),
     "arcface_b200_backward_workspace_bytes": (c_int32, [c_int32, c_int32, c_int64, POINTER(c_size_t)]),
     "arcface_b200_backward_plan": (c_int32, [c_int32, c_int32, c_int64, POINTER(c_int64), POINTER(c_int32)]),
+    "arcface_b200_backward_launches": (c_int32, [c_int32, c_int32, c_int64, POINTER(c_int32)]),
     "arcface_b200_backward": (
         c_int32,
         [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,

@@ -48,6 +48,22 @@ struct Core {
     int n_res;           // 256-row slices of the resident operand; the number of pairs is a multiple of it
     int contiguous;      // 1: group g walks blocks [g * per, (g + 1) * per); 0: g, g + groups, ...
     int prefetch_tiles;  // L2 prefetch distance in tiles (0 = off)
+    // measurements only (nullable): 16 counters per CTA, see WaitProf
+    unsigned long long* prof = nullptr;
+    int prof_cta = 0;    // index of this launch's / role's first CTA in `prof`
+};
+
+// Where a CTA's warps spent their time (cycles), written once at the end of the body when Core::prof is set:
+//   [0] producer waiting in acquire_tile   [1] producer waiting for a free stage
+//   [2] MMA warp waiting for operands      [3] MMA warp waiting for a free accumulator
+//   [4] epilogue warp 4 waiting for an accumulator   [5] epilogue warp 4 inside Epi::tile
+//   [6] whole body   [7] tiles
+struct WaitProf {
+    unsigned long long t0, acc;
+    bool on;
+    __device__ __forceinline__ explicit WaitProf(bool enabled) : t0(0), acc(0), on(enabled) {}
+    __device__ __forceinline__ void begin() { if (on) t0 = clock64(); }
+    __device__ __forceinline__ void end() { if (on) acc += clock64() - t0; }
 };
 
 struct EpiCtx {
@@ -60,11 +76,13 @@ struct EpiCtx {
     int rank;   // CTA rank in the pair
     int res;    // resident slice of the pair
     int grp;    // group of the pair (pairs / n_res groups)
+    unsigned long long* prof;  // measurements only: this CTA's counters [8..15] for warp 4, else null
 };
 
 template <class P>
 constexpr size_t smem_bytes(int kblocks, size_t extra_bytes) {
-    return 1024 + static_cast<size_t>(kblocks + P::STAGES) * TILE_BYTES + (P::STAGING ? EPI_WARPS * STAGING_PER_WARP : 0) +
+    // no alignment slack: the kernels declare their dynamic shared memory __align__(1024) and trap if it is not
+    return static_cast<size_t>(kblocks + P::STAGES) * TILE_BYTES + (P::STAGING ? EPI_WARPS * STAGING_PER_WARP : 0) +
            ((extra_bytes + 15) / 16) * 16 + (2 * P::STAGES + 2 * ACC_BUFS + 1) * 8 + 16;
 }
 
@@ -94,18 +112,67 @@ struct Stager {
     }
 };
 
+// Two 2 KB staging buffers per epilogue warp (32 rows x 64 B, TMA SWIZZLE_64B layout: the 16-byte chunk index
+// is XORed with bits 7-8 of the row offset): the next box is written while the TMA still reads the previous one.
+struct Stager2 {
+    uint32_t base;
+    int lane;
+    int it;
+    __device__ Stager2(const EpiCtx& c) : base(c.staging), lane(c.lane), it(0) {}
+    // buffer for the next box; blocks until the store issued two boxes ago has read it out
+    __device__ __forceinline__ uint32_t acquire() const {
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+        return base + (it & 1) * 2048;
+    }
+    __device__ __forceinline__ void put(uint32_t buf, int chunk, uint32_t a, uint32_t b, uint32_t c, uint32_t d) const {
+        st_shared_v4(buf + lane * 64 + ((chunk ^ ((lane >> 1) & 3)) << 4), a, b, c, d);
+    }
+    __device__ __forceinline__ void commit(const CUtensorMap* tm, uint32_t buf, int c0, int c1) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_2d(tm, buf, c0, c1);
+            bulk_commit();
+        }
+        ++it;
+    }
+    __device__ __forceinline__ void drain() const {
+        if (lane == 0) bulk_wait<0>();
+        __syncwarp();
+    }
+};
+
+// Optional hooks of a pair policy (a policy derives from this and hides what it needs).
+struct PairDefaults {
+    static constexpr int AUX_WARPS = 0;                             // helper warps running aux()
+    static constexpr int LOW_REGS = 0, EPI_REGS = 0, AUX_REGS = 0;  // setmaxnreg targets (0 = no reallocation)
+    // producer warp (all lanes), before the first k-block of tile i of this CTA is fetched
+    // (`extra` = the policy's shared memory, the same pointer Epi sees as EpiCtx::extra)
+    template <class Prm>
+    __device__ static void acquire_tile(const Prm&, uint8_t*, int, int, int) {}
+    // one lane of the leader's MMA warp, after every operand byte of tile i has landed in both CTAs
+    template <class Prm>
+    __device__ static void release_tile(const Prm&, int) {}
+    template <class Prm>
+    __device__ static void aux(const Prm&, int, int, int) {}
+    // warp 3 (otherwise idle), all lanes: (prm, extra, i_begin, i_end, i_step, rank, lane) = this pair's tile walk
+    template <class Prm>
+    __device__ static void side_warp(const Prm&, uint8_t*, int, int, int, int, int) {}
+    // TMA row coordinate of tile i of the streamed operand (the CTA adds rank * ROWS)
+    template <class Prm>
+    __device__ static int stream_row(const Prm& p, int i) { return p.core.s_row0 + i * 2 * ROWS; }
+};
+
+// The body of a pair kernel: `pair` of `npairs` (consecutive CTA pairs of one launch that share the policy),
+// `smem` 1024-aligned dynamic shared memory carved identically in both CTAs.
 template <class P>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS + P::AUX_WARPS * 32, 1)
-pair_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmR,
-                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ typename P::Params prm,
-                 const int extra_bytes) {
+__device__ __forceinline__ void pair_gemm_body(const CUtensorMap& tmS, const CUtensorMap& tmR, const CUtensorMap& tmC,
+                                               const typename P::Params& prm, const int extra_bytes, uint8_t* smem,
+                                               const int pair, const int npairs) {
     constexpr int STAGES = P::STAGES;
     const Core& co = prm.core;
     const int kblocks = co.kblocks;
-
-    extern __shared__ uint8_t smem_raw[];
-    // the two CTAs must carve identically: the dynamic shared-memory window starts at the same offset in both
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sRes = smem;
     uint8_t* sStage = sRes + kblocks * TILE_BYTES;
     uint8_t* sStaging = sStage + STAGES * TILE_BYTES;
@@ -120,8 +187,6 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int rank = static_cast<int>(cluster_ctarank());
-    const int pair = blockIdx.x >> 1;
-    const int npairs = gridDim.x >> 1;
     const int res = pair % co.n_res;
     const int grp = pair / co.n_res;
     const int ngrp = npairs / co.n_res;
@@ -165,6 +230,9 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
     cluster_sync_all();  // the peer's barriers are initialised before anyone arrives on them remotely
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const bool prof_on = co.prof != nullptr;
+    unsigned long long* prof = prof_on ? co.prof + static_cast<size_t>(co.prof_cta + pair * 2 + rank) * 16 : nullptr;
+    const unsigned long long body_t0 = prof_on ? clock64() : 0;
 
     // A policy with helper warps may let the light roles hand registers to the helper warpgroups (P::AUX_REGS > 0;
     // setmaxnreg is executed by whole warpgroups -- warps 0-3, 4-11, 12-... -- at the top of the branch that holds
@@ -183,25 +251,31 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
         __syncwarp();
         int stage = 0;
         uint32_t phase = 0;
+        WaitProf wp_a(prof_on), wp_b(prof_on);
         for (int i = i_begin; i < i_end; i += i_step) {
-            const int row = co.s_row0 + i * 2 * ROWS + rank * ROWS;
-            P::acquire_tile(prm, i, rank, lane);  // whole warp; returns once this CTA's 128 rows may be fetched
+            const int row = P::stream_row(prm, i) + rank * ROWS;
+            wp_a.begin();
+            P::acquire_tile(prm, sExtra, i, rank, lane);  // whole warp; returns once this CTA's 128 rows may be fetched
+            wp_a.end();
             const int ip = i + co.prefetch_tiles * i_step;
             const bool pf = co.prefetch_tiles > 0 && ip < i_end;
             for (int kb = 0; kb < kblocks; ++kb) {
+                wp_b.begin();
                 mbar_wait(&empty_bar[stage], phase ^ 1);
+                wp_b.end();
                 if (elect_one()) {
                     const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
                     mbar_expect_tx_cluster(full_leader, TILE_BYTES);
                     tma_load_2d_pair(sStage + stage * TILE_BYTES, &tmS, full_leader, kb * BK, row);
                     // the n_res pairs that stream the same block share the L2 prefetch work
                     if (pf && (kb % co.n_res) == res)
-                        tma_prefetch_2d(&tmS, kb * BK, co.s_row0 + ip * 2 * ROWS + rank * ROWS);
+                        tma_prefetch_2d(&tmS, kb * BK, P::stream_row(prm, ip) + rank * ROWS);
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
+        if (prof_on && lane == 0) { prof[0] = wp_a.acc; prof[1] = wp_b.acc; }
     } else if (warp == 1) {
         // ---------------- MMA issuer: leader CTA only, whole warp runs the loop, one elected lane issues
         if (rank == 0) {
@@ -214,12 +288,17 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            WaitProf wp_f(prof_on), wp_e(prof_on);
             for (int i = i_begin; i < i_end; i += i_step) {
+                wp_e.begin();
                 mbar_wait_cluster(&tempty_bar[acc], acc_phase ^ 1);
+                wp_e.end();
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
                 for (int kb = 0; kb < kblocks; ++kb) {
+                    wp_f.begin();
                     mbar_wait_cluster(&full_bar[stage], phase);
+                    wp_f.end();
                     tc_fence_after();
                     const uint64_t s_desc = make_smem_desc(sStage_u32 + stage * TILE_BYTES, 16, 1024);
                     const uint64_t r_desc = res_desc0 + static_cast<uint64_t>(kb * (TILE_BYTES >> 4));
@@ -230,14 +309,20 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
                         for (int kk = 0; kk < BK / 16; ++kk)
                             umma_bf16_pair(tmem_d, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (kb | kk) != 0 ? 1u : 0u);
                         umma_commit_pair(&empty_bar[stage], 3);  // frees the stage in both CTAs
-                        if (kb == kblocks - 1) umma_commit_pair(&tfull_bar[acc], 3);
+                        if (kb == kblocks - 1) {
+                            umma_commit_pair(&tfull_bar[acc], 3);
+                            P::release_tile(prm, i);
+                        }
                     }
                     __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
             }
+            if (prof_on && lane == 0) { prof[2] = wp_f.acc; prof[3] = wp_e.acc; }
         }
+    } else if (warp == 3) {
+        P::side_warp(prm, sExtra, i_begin, i_end, i_step, rank, lane);
     }
     } else if (warp < 4 + EPI_WARPS) {
         // ---------------- epilogue (both CTAs)
@@ -252,12 +337,19 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
         ctx.rank = rank;
         ctx.res = res;
         ctx.grp = grp;
+        ctx.prof = (prof_on && warp == 4) ? prof + 8 : nullptr;
         typename P::Epi epi(prm, ctx);
         int acc = 0;
         uint32_t acc_phase = 0;
         if (i_begin < i_end) epi.prefetch(i_begin);
+        WaitProf wp_t(prof_on && warp == 4), wp_w(prof_on && warp == 4);
+        unsigned long long n_tiles = 0;
         for (int i = i_begin; i < i_end; i += i_step) {
+            wp_t.begin();
             mbar_wait(&tfull_bar[acc], acc_phase);
+            wp_t.end();
+            ++n_tiles;
+            wp_w.begin();
             tc_fence_after();
             const uint32_t taddr =
                 tmem_base + acc * ACC_COLS + ctx.half * 128 + (static_cast<uint32_t>(ctx.quad * 32) << 16);
@@ -265,13 +357,19 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+            wp_w.end();
             if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
         }
         epi.finish();
+        if (prof_on && warp == 4 && lane == 0) {
+            prof[4] = wp_t.acc;
+            prof[5] = wp_w.acc;
+            prof[6] = clock64() - body_t0;
+            prof[7] = n_tiles;
+        }
     } else if constexpr (P::AUX_WARPS > 0) {
         if constexpr (P::AUX_REGS > 0) setmaxnreg_inc<P::AUX_REGS>();
-        P::aux(prm, static_cast<int>(blockIdx.x) * P::AUX_WARPS + (warp - 4 - EPI_WARPS),
-               static_cast<int>(gridDim.x) * P::AUX_WARPS, lane);
+        P::aux(prm, (pair * 2 + rank) * P::AUX_WARPS + (warp - 4 - EPI_WARPS), npairs * 2 * P::AUX_WARPS, lane);
     }
 
     // neither CTA may leave (or free TMEM) while the peer can still touch its barriers / shared memory / TMEM
@@ -279,6 +377,18 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
     __syncthreads();
     cluster_sync_all();
     if (warp == 2) tmem_dealloc_pair(tmem_base, ACC_BUFS * ACC_COLS);
+}
+
+template <class P>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS + P::AUX_WARPS * 32, 1)
+pair_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmR,
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ typename P::Params prm,
+                 const int extra_bytes) {
+    // 1024-byte alignment (SWIZZLE_128B operand tiles); the two CTAs carve identically
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+    uint8_t* smem = smem_raw;
+    pair_gemm_body<P>(tmS, tmR, tmC, prm, extra_bytes, smem, blockIdx.x >> 1, gridDim.x >> 1);
 }
 
 #ifdef AB_CHECK_CUDA

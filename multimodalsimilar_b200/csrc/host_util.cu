@@ -105,17 +105,25 @@ int32_t make_tmap_mnmajor(CUtensorMap* out, const void* base, uint64_t mn, uint6
 
 int32_t make_tmap_store(CUtensorMap* out, const void* base, int elem_bytes, uint64_t cols, uint64_t rows,
                         uint64_t row_stride_elems) {
+    return make_tmap_store_box(out, base, elem_bytes, cols, rows, row_stride_elems, 128);
+}
+
+int32_t make_tmap_store_box(CUtensorMap* out, const void* base, int elem_bytes, uint64_t cols, uint64_t rows,
+                            uint64_t row_stride_elems, int box_bytes) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return set_error(ARCFACE_B200_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
     if (!aligned16(base) || (row_stride_elems * elem_bytes) % 16 != 0 || (elem_bytes != 2 && elem_bytes != 4))
         return set_error(ARCFACE_B200_E_LAYOUT, "TMA store target must be 16-byte aligned with a 16-byte multiple row stride");
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {row_stride_elems * elem_bytes};
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elem_bytes), 32};
+    if (box_bytes != 128 && box_bytes != 64)
+        return set_error(ARCFACE_B200_E_ARG, "TMA store box must be 64 or 128 bytes wide");
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(box_bytes / elem_bytes), 32};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    box_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return set_error(ARCFACE_B200_E_CUDA, "cuTensorMapEncodeTiled (store %llu x %llu) failed: CUresult %d",
                          (unsigned long long)rows, (unsigned long long)cols, (int)r);

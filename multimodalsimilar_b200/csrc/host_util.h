@@ -44,6 +44,11 @@ int32_t make_tmap_mnmajor(CUtensorMap* out, const void* base, uint64_t mn, uint6
 int32_t make_tmap_store(CUtensorMap* out, const void* base, int elem_bytes, uint64_t cols, uint64_t rows,
                         uint64_t row_stride_elems);
 
+// Same with a box of {box_bytes of columns, 32 rows}: 128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B (half-size staging
+// buffers that can be double-buffered).
+int32_t make_tmap_store_box(CUtensorMap* out, const void* base, int elem_bytes, uint64_t cols, uint64_t rows,
+                            uint64_t row_stride_elems, int box_bytes);
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace ab

@@ -162,7 +162,7 @@ __device__ __forceinline__ float4 ldg_stream4(const float* p) {
 }
 
 template <bool NORM>
-struct FwdStatsPairT {
+struct FwdStatsPairT : pr::PairDefaults {
     static constexpr int STAGES = 4;
     static constexpr bool STAGING = false;
     static constexpr bool RES_A = true;
@@ -192,7 +192,7 @@ struct FwdStatsPairT {
 
     __device__ static void prologue(const Params&, uint8_t*, int, int, int) {}
 
-    __device__ static void acquire_tile(const Params& p, int i, int rank, int lane) {
+    __device__ static void acquire_tile(const Params& p, uint8_t*, int i, int rank, int lane) {
         if constexpr (NORM) {
             const int blk = i * 2 + rank;
             const int need = min(pr::ROWS, p.C - blk * pr::ROWS);

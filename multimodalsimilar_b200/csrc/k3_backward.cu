@@ -20,6 +20,7 @@
 #include "gemm_pair.cuh"
 
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -559,10 +560,21 @@ struct BwdDWr {
 // ------------------------------------------------------------------ dC^T producer on a CTA pair
 // streamed = What rows (256 classes per tile, 128 per CTA -> accumulator lanes), resident = 256 batch rows of
 // Xhat (accumulator columns), K = D <= 512.
-struct BwdDCp {
+//
+// FUSED = true is the producer role of the single-launch backward (k3_fused.cuh): tile i is the global
+// 256-class block i, its dC^T goes to slot i % ring of an L2-resident ring instead of a full-size scratch, and
+// the epilogue warps gate on / publish per-block counters (struct Ring).
+struct Ring {
+    int slots;         // ring slots (each 256 classes x Bp bf16)
+    int* ready;        // [blocks] epilogue-warp arrivals of the dC^T producers
+    int* done;         // [blocks] consumer arrivals (dW pairs + dX CTAs)
+    int ready_target;  // arrivals that complete a block
+    int done_target;   // arrivals that free its slot
+};
+
+template <bool FUSED>
+struct BwdDCpT : pr::PairDefaults {
     static constexpr int STAGES = 3;  // 3 x 16 KB: the per-column constants below take the fourth stage's room
-    static constexpr int AUX_WARPS = 0;
-    static constexpr int LOW_REGS = 0, EPI_REGS = 0, AUX_REGS = 0;  // no helper warps, no register reallocation
     static constexpr bool STAGING = true;
     static constexpr bool RES_A = false;
     static constexpr int NCOL = 2 * pr::ROWS;  // batch columns of one pair
@@ -578,15 +590,34 @@ struct BwdDCp {
         const float* dphi;
         const int* label_local;
         float* q;  // [2 * n_res][C]: one slot per (batch slice, column half)
+        Ring ring;  // FUSED only
     };
-    static constexpr int EXTRA_BYTES = NCOL * 12;
+    static constexpr int BLOOM_WORDS = 128;  // 4096 bits, one per 128-class block (mod 4096)
+    static constexpr int PUB_BAR_OFF = NCOL * 12 + BLOOM_WORDS * 4;  // FUSED: mbarrier epilogue warps -> publisher warp
+    static constexpr int EXTRA_BYTES = PUB_BAR_OFF + 16;
 
-    // constants of this pair's 256 batch columns: lse * log2e (+inf on padding -> p = 0), label, label-column dC
+    // constants of this pair's 256 batch columns: lse * log2e (+inf on padding -> p = 0), label, label-column dC;
+    // plus a bloom filter of the 128-class blocks that hold one of these labels: the epilogue only runs the
+    // per-element label test on tiles the filter flags (256 labels among C classes: a few percent of the tiles)
     __device__ static void prologue(const Params& p, uint8_t* extra, int tid, int res, int) {
         float* lse2 = reinterpret_cast<float*>(extra);
         int* lab = reinterpret_cast<int*>(extra + NCOL * 4);
         float* dlab = reinterpret_cast<float*>(extra + NCOL * 8);
+        unsigned* bloom = reinterpret_cast<unsigned*>(extra + NCOL * 12);
         const float coef = p.coef * (p.grad_dev != nullptr ? *p.grad_dev : 1.f);
+        if (FUSED && tid == 0) {
+            mbar_init(reinterpret_cast<uint64_t*>(extra + PUB_BAR_OFF), pr::EPI_WARPS);
+            fence_barrier_init();
+        }
+        for (int j = tid; j < BLOOM_WORDS; j += pr::THREADS) bloom[j] = 0u;
+        __syncthreads();  // every thread of the CTA runs the prologue
+        for (int j = tid; j < NCOL; j += pr::THREADS) {
+            const int bb = res * NCOL + j;
+            if (bb < p.B) {
+                const int yy = p.label_local[bb];
+                if (yy >= 0) atomicOr(&bloom[((yy >> 7) & 4095) >> 5], 1u << ((yy >> 7) & 31));
+            }
+        }
         for (int j = tid; j < NCOL; j += pr::THREADS) {
             const int b = res * NCOL + j;
             if (b < p.B) {
@@ -602,8 +633,22 @@ struct BwdDCp {
         }
     }
 
-    __device__ static void acquire_tile(const Params&, int, int, int) {}
-    __device__ static void aux(const Params&, int, int, int) {}
+    // FUSED: the publisher.  For every tile of the pair's walk: wait until the CTA's eight epilogue warps have
+    // handed the block over, fence at gpu scope (cumulative over what the mbarrier made visible) and bump the
+    // block's ready counter -- one arrival per CTA.
+    __device__ static void side_warp(const Params& p, uint8_t* extra, int i_begin, int i_end, int i_step, int, int lane) {
+        if constexpr (FUSED) {
+            uint64_t* bar = reinterpret_cast<uint64_t*>(extra + PUB_BAR_OFF);
+            uint32_t phase = 0;
+            for (int i = i_begin; i < i_end; i += i_step) {
+                mbar_wait(bar, phase);
+                phase ^= 1;
+                __threadfence();
+                if (lane == 0) red_relaxed_gpu_add(p.ring.ready + i, 1);
+                __syncwarp();
+            }
+        }
+    }
 
     struct Epi {
         const Params& p;
@@ -612,83 +657,146 @@ struct BwdDCp {
         const float* lse2;
         const int* lab;
         const float* dlab;
+        const unsigned* bloom;
+        uint64_t* pub_bar;
         int quad, lane, rank, jl0, b0;
+        int prev;  // FUSED: block whose stores are committed but not yet published
         float coef_all;
         float* qslot;
+        unsigned long long* prof;  // measurements only: [0] publish [1] slot wait [2] tmem load [3] math [4] staging wait
+        unsigned long long pacc[5];
+        __device__ __forceinline__ unsigned long long tick() const { return prof != nullptr ? clock64() : 0ull; }
         __device__ Epi(const Params& prm, const pr::EpiCtx& c)
-            : p(prm), tm_out(c.tmC), stager(c), quad(c.quad), lane(c.lane), rank(c.rank) {
+            : p(prm), tm_out(c.tmC), stager(c), quad(c.quad), lane(c.lane), rank(c.rank), prev(-1), prof(c.prof) {
+            for (int k = 0; k < 5; ++k) pacc[k] = 0;
             coef_all = p.coef * (p.grad_dev != nullptr ? *p.grad_dev : 1.f);
             jl0 = c.half * 128;          // first of this warp's 128 columns inside the pair's 256
             b0 = c.res * NCOL + jl0;     // the same as a batch index
             lse2 = reinterpret_cast<const float*>(c.extra) + jl0;
             lab = reinterpret_cast<const int*>(c.extra + NCOL * 4) + jl0;
             dlab = reinterpret_cast<const float*>(c.extra + NCOL * 8) + jl0;
+            bloom = reinterpret_cast<const unsigned*>(c.extra + NCOL * 12);
+            pub_bar = reinterpret_cast<uint64_t*>(c.extra + PUB_BAR_OFF);
             qslot = p.q + static_cast<int64_t>(c.res * 2 + c.half) * p.C;
         }
-        // 8 consecutive batch columns -> one 16-byte chunk of bf16
-        __device__ __forceinline__ void eight(const uint32_t* v, int j0, float coef, int cmatch, float& qacc,
-                                              uint32_t (&o)[4]) const {
+        // 8 consecutive batch columns -> one 16-byte chunk of bf16.  LABELS = false skips the label test (the
+        // caller knows none of the CTA's 128 classes is a label of these batch columns).
+        template <bool LABELS>
+        __device__ __forceinline__ void eight(const uint32_t* v, int j0, float coef, int cmatch, float& qa, float& qb,
+                                              uint32_t* o) const {
             const float4 l0 = *reinterpret_cast<const float4*>(lse2 + j0);
             const float4 l1 = *reinterpret_cast<const float4*>(lse2 + j0 + 4);
-            const int4 y0 = *reinterpret_cast<const int4*>(lab + j0);
-            const int4 y1 = *reinterpret_cast<const int4*>(lab + j0 + 4);
             const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-            const int ys[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
             float dc[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float cosv = __uint_as_float(v[j]);
                 float d = coef * ex2(fmaf(cosv, p.s_log2e, -ls[j]));
-                if (ys[j] == cmatch) d = dlab[j0 + j];  // rare: this class is row b's label
-                qacc = fmaf(d, cosv, qacc);
+                if constexpr (LABELS) {
+                    if (lab[j0 + j] == cmatch) d = dlab[j0 + j];  // rare: this class is row b's label
+                }
+                if (j & 1) qb = fmaf(d, cosv, qb);
+                else qa = fmaf(d, cosv, qa);
                 dc[j] = d;
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) o[j] = pack_bf16x2(dc[2 * j], dc[2 * j + 1]);
         }
+        template <bool LABELS>
+        __device__ __forceinline__ void group(uint32_t taddr, int g, int row0, float coef, int cmatch, float (&q)[4]) {
+            uint32_t v0[32], v1[32];
+            const unsigned long long t0 = tick();
+            tmem_ld32(taddr + g * 64, v0);
+            tmem_ld32(taddr + g * 64 + 32, v1);
+            tmem_ld_wait();
+            const unsigned long long t1 = tick();
+            uint32_t o[32];  // 64 columns of bf16
+#pragma unroll
+            for (int k = 0; k < 4; ++k) eight<LABELS>(v0 + 8 * k, g * 64 + 8 * k, coef, cmatch, q[0], q[1], o + 4 * k);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                eight<LABELS>(v1 + 8 * k, g * 64 + 32 + 8 * k, coef, cmatch, q[2], q[3], o + 16 + 4 * k);
+            const unsigned long long t2 = tick();
+            stager.acquire();  // only now: the previous box has had the whole computation above to leave
+            const unsigned long long t3 = tick();
+#pragma unroll
+            for (int k = 0; k < 8; ++k) stager.put(k, o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+            stager.commit(tm_out, b0 + g * 64, row0);  // rows past the chunk are clipped by the TMA
+            if (prof != nullptr) { pacc[2] += t1 - t0; pacc[3] += t2 - t1; pacc[4] += t3 - t2; }
+        }
         __device__ void prefetch(int) {}
+        // FUSED: hand the previous block over to the CTA's publisher warp (side_warp below).  Its TMA stores were
+        // committed by lane 0 a whole tile ago, its q values written by every lane; the gpu-scope fence and the
+        // counter update -- ~2700 cycles when the epilogue warps did them themselves -- happen off this path.
+        __device__ __forceinline__ void hand_over() {
+            // the dC^T boxes have been written (completion of the bulk group makes them visible to this thread;
+            // the release chain below -- mbarrier arrive, publisher's gpu fence, counter -- carries them on)
+            if (lane == 0) bulk_wait<0>();
+            __syncwarp();  // every lane's q stores are ordered before lane 0's arrive
+            if (lane == 0) mbar_arrive(pub_bar);
+        }
         __device__ void tile(int i, int, uint32_t taddr) {
-            const int row0 = i * NCOL + rank * pr::ROWS + quad * 32;  // chunk-relative class row of lane 0
-            const int c = p.core.s_row0 + row0 + lane;                // class owned by this thread
+            const int row0 = (FUSED ? (i % p.ring.slots) : i) * NCOL + rank * pr::ROWS + quad * 32;  // scratch row
+            const int c0 = p.core.s_row0 + i * NCOL + rank * pr::ROWS;  // first class of this CTA's 128
+            const int c = c0 + quad * 32 + lane;                        // class owned by this thread
             const bool cvalid = c < p.C;
             const float coef = cvalid ? coef_all : 0.f;
             const int cmatch = cvalid ? c : -2;
-            float q0 = 0.f, q1 = 0.f;
+            float q[4] = {0.f, 0.f, 0.f, 0.f};
+            if constexpr (FUSED) {
+                const unsigned long long t0 = tick();
+                if (prev >= 0) hand_over();
+                prev = i;
+                const unsigned long long t1 = tick();
+                if (i >= p.ring.slots) {  // the slot's previous tenant must have been consumed
+                    if (lane == 0) wait_counter_ge(p.ring.done + (i - p.ring.slots), p.ring.done_target);
+                    __syncwarp();
+                }
+                if (prof != nullptr) { pacc[0] += t1 - t0; pacc[1] += tick() - t1; }
+            }
+            // does one of the two 128-class blocks this CTA's classes touch hold a label of our batch columns?
+            const int k0 = (c0 >> 7) & 4095, k1 = ((c0 + pr::ROWS - 1) >> 7) & 4095;
+            const bool labels = ((bloom[k0 >> 5] >> (k0 & 31)) | (bloom[k1 >> 5] >> (k1 & 31))) & 1u;
 #pragma unroll 1
             for (int g = 0; g < 2; ++g) {
                 if (b0 + g * 64 >= p.Bp) break;  // warp-uniform: these columns are all batch padding
-                uint32_t v0[32], v1[32];
-                tmem_ld32(taddr + g * 64, v0);
-                tmem_ld32(taddr + g * 64 + 32, v1);
-                tmem_ld_wait();
-                stager.acquire();
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    uint32_t o[4];
-                    eight(v0 + 8 * k, g * 64 + 8 * k, coef, cmatch, q0, o);
-                    stager.put(k, o[0], o[1], o[2], o[3]);
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    uint32_t o[4];
-                    eight(v1 + 8 * k, g * 64 + 32 + 8 * k, coef, cmatch, q1, o);
-                    stager.put(4 + k, o[0], o[1], o[2], o[3]);
-                }
-                stager.commit(tm_out, b0 + g * 64, row0);  // rows past the chunk are clipped by the TMA
+                if (labels) group<true>(taddr, g, row0, coef, cmatch, q);
+                else group<false>(taddr, g, row0, coef, cmatch, q);
             }
-            if (cvalid) qslot[c] = q0 + q1;
+            if (cvalid) qslot[c] = (q[0] + q[1]) + (q[2] + q[3]);
         }
-        __device__ void finish() { stager.drain(); }
+        __device__ void finish() {
+            if constexpr (FUSED) {
+                if (prev >= 0) hand_over();
+            }
+            if (prof != nullptr && lane == 0)
+                for (int k = 0; k < 5; ++k) prof[k] = pacc[k];
+            stager.drain();
+        }
     };
 };
+using BwdDCp = BwdDCpT<false>;
 
 // ------------------------------------------------------------------ dW on a CTA pair
 // streamed = dC^T scratch rows (256 classes per tile), resident = 256 rows of Xhat^T (embedding columns of the
 // accumulator), K = batch <= 512.
-struct BwdDWp {
+// FUSED = true: consumer role of the single-launch backward: the streamed rows come out of the ring once the
+// block's counter says every dC^T producer warp has published it; the slot is released when the last operand
+// byte of the block has landed in shared memory.
+__device__ __forceinline__ float ld_cg_f32(const float* p) {  // data written earlier in this kernel by another SM
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+template <bool FUSED>
+struct BwdDWpT : pr::PairDefaults {
     static constexpr int STAGES = 4;
-    static constexpr int AUX_WARPS = 0;
-    static constexpr int LOW_REGS = 0, EPI_REGS = 0, AUX_REGS = 0;  // no helper warps, no register reallocation
+    // The dW rows leave through one 4 KB staging buffer per warp and TMA stores of {32 columns x 32 rows}.
+    // Measured alternatives (ARCFACE_B200_BWD_PROF): two 2 KB buffers with 16-column boxes double the number of
+    // proxy fences (~640 cycles per box: the fence waits for st.shared traffic that competes with the tensor
+    // pipe's operand reads for shared-memory bandwidth); 128-bit global stores straight from registers (thread =
+    // class row) are 4x slower still (32 half-sectors per warp instruction).
     static constexpr bool STAGING = true;
     static constexpr bool RES_A = false;
     static constexpr int NCOL = 2 * pr::ROWS;
@@ -701,92 +809,165 @@ struct BwdDWp {
         int q_slots;  // <= 8
         const float* inv_nw;
         const __nv_bfloat16* what;
+        float* dw;  // out [C][D] fp32
+        Ring ring;  // FUSED only
     };
-    static constexpr int EXTRA_BYTES = 0;
+    static constexpr int EXTRA_BYTES = 16;  // FUSED: [0] = 1 + the last block this CTA's producer has acquired
 
-    __device__ static void prologue(const Params&, uint8_t*, int, int, int) {}
-    __device__ static void acquire_tile(const Params&, int, int, int) {}
-    __device__ static void aux(const Params&, int, int, int) {}
+    __device__ static void prologue(const Params&, uint8_t* extra, int tid, int, int) {
+        if (tid == 0) *reinterpret_cast<volatile int*>(extra) = 0;
+    }
+    __device__ static int stream_row(const Params& p, int i) {
+        return FUSED ? (i % p.ring.slots) * NCOL : p.core.s_row0 + i * NCOL;
+    }
+    __device__ static void acquire_tile(const Params& p, uint8_t* extra, int i, int, int lane) {
+        if constexpr (FUSED) {
+            if (lane == 0) {
+                wait_counter_ge(p.ring.ready + i, p.ring.ready_target);
+                __threadfence_block();
+                *reinterpret_cast<volatile int*>(extra) = i + 1;  // lets the epilogue fetch q[i] ahead of its tile
+            }
+            __syncwarp();
+            fence_proxy_async_all();  // the acquire above -> ordered before the TMA reads of the block
+        }
+    }
+    __device__ static void release_tile(const Params& p, int i) {
+        if constexpr (FUSED) red_relaxed_gpu_add(p.ring.done + i, 1);
+    }
 
     struct Epi {
         const Params& p;
-        const CUtensorMap* tm_out;  // dW [C][D] fp32
+        const CUtensorMap* tm_out;  // dW [C][D] fp32, boxes of 32 columns x 32 rows
         pr::Stager stager;
         int quad, lane, rank, d0;
-        // operands of the normalise backward, fetched one 32-column box ahead (their L2 latency would otherwise
-        // sit between every tcgen05.ld and its TMA store)
-        uint4 wn[4];
-        float nqn, inwn;
+        // operands of the normalise backward, fetched ahead of their use (their L2 latency would otherwise sit
+        // between every tcgen05.ld and its TMA store): the normalised weights TWO 32-column groups ahead (across
+        // the tile boundary), the per-class scalars one tile ahead (FUSED: at the start of the tile -- q of a later
+        // block may not have been produced yet).  The scalars stay raw in registers until they are needed, so
+        // that nothing in program order waits on their loads.
+        uint4 wa[4], wb[4];  // groups g and g + 1 in flight / ready
+        float qn[8];
+        float inwn;
+        const volatile int* acquired;  // FUSED: see EXTRA_BYTES
+        bool have_scalars;
+        unsigned long long* prof;  // measurements only: [0] scalars [1] tmem load [2] math [3] staging wait [4] store issue
+        unsigned long long pacc[5];
+        __device__ __forceinline__ unsigned long long tick() const { return prof != nullptr ? clock64() : 0ull; }
         __device__ Epi(const Params& prm, const pr::EpiCtx& c)
             : p(prm), tm_out(c.tmC), stager(c), quad(c.quad), lane(c.lane), rank(c.rank),
-              d0(c.res * NCOL + c.half * 128) {}
+              d0(c.res * NCOL + c.half * 128), acquired(reinterpret_cast<const volatile int*>(c.extra)),
+              have_scalars(false), prof(c.prof) {
+            for (int k = 0; k < 5; ++k) pacc[k] = 0;
+        }
         __device__ __forceinline__ int class_of(int i) const {
             return p.c_begin + i * NCOL + rank * pr::ROWS + quad * 32 + lane;
         }
-        __device__ __forceinline__ void fetch_w(int i, int box) {
+        // the 32 normalised weights of group `grp` (0..3) of tile i
+        __device__ __forceinline__ void fetch_w(int i, int grp, uint4 (&w)[4]) const {
             const int c = class_of(i);
             const bool cvalid = c < p.C;
             const __nv_bfloat16* wrow = p.what + static_cast<int64_t>(cvalid ? c : 0) * p.D;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-                const int d = d0 + box * 32 + g * 8;
-                wn[g] = (cvalid && d < p.D) ? ldg_nc_u4(wrow + d) : make_uint4(0, 0, 0, 0);
+                const int d = d0 + grp * 32 + g * 8;
+                w[g] = (cvalid && d < p.D) ? ldg_nc_u4(wrow + d) : make_uint4(0, 0, 0, 0);
             }
         }
         __device__ __forceinline__ void fetch_scalars(int i) {
             const int c = class_of(i);
             const bool cvalid = c < p.C;
-            float qs[8];
 #pragma unroll
             for (int sl = 0; sl < 8; ++sl)
-                qs[sl] = (cvalid && sl < p.q_slots) ? __ldg(p.q + static_cast<int64_t>(sl) * p.C + c) : 0.f;
-            nqn = -(((qs[0] + qs[1]) + (qs[2] + qs[3])) + ((qs[4] + qs[5]) + (qs[6] + qs[7])));
+                qn[sl] = (cvalid && sl < p.q_slots) ? ld_cg_f32(p.q + static_cast<int64_t>(sl) * p.C + c) : 0.f;
             inwn = cvalid ? __ldg(p.inv_nw + c) : 0.f;
         }
-        __device__ void prefetch(int i) {
-            fetch_scalars(i);
-            fetch_w(i, 0);
+        __device__ void prefetch(int i) {  // before the first tile
+            if constexpr (!FUSED) fetch_scalars(i);
+            fetch_w(i, 0, wa);
+            fetch_w(i, 1, wb);
+        }
+        // one 32-column group: w = its weights (consumed), refilled with the group two ahead
+        __device__ __forceinline__ void group(int i, int i_next, int grp, uint32_t taddr, int crow0, float nq, float inw,
+                                              uint4 (&w)[4]) {
+            const int dg = d0 + grp * 32;
+            uint4 wc[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) wc[g] = w[g];
+            if (dg >= p.D) {  // warp-uniform: columns past the embedding width; only keep the prefetch chain going
+                if (grp < 2) fetch_w(i, grp + 2, w);
+                else if (i_next >= 0) fetch_w(i_next, grp - 2, w);
+                return;
+            }
+            uint32_t v[32];
+            const unsigned long long t0 = tick();
+            tmem_ld32(taddr + grp * 32, v);
+            // refill: group grp + 2 of this tile, or group grp - 2 of the next one
+            if (grp < 2) fetch_w(i, grp + 2, w);
+            else if (i_next >= 0) fetch_w(i_next, grp - 2, w);
+            tmem_ld_wait();
+            const unsigned long long t1 = tick();
+            float o[32];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const uint4 ww = wc[g];
+                o[g * 8 + 0] = fmaf(nq, bf16_lo(ww.x), __uint_as_float(v[g * 8 + 0])) * inw;
+                o[g * 8 + 1] = fmaf(nq, bf16_hi(ww.x), __uint_as_float(v[g * 8 + 1])) * inw;
+                o[g * 8 + 2] = fmaf(nq, bf16_lo(ww.y), __uint_as_float(v[g * 8 + 2])) * inw;
+                o[g * 8 + 3] = fmaf(nq, bf16_hi(ww.y), __uint_as_float(v[g * 8 + 3])) * inw;
+                o[g * 8 + 4] = fmaf(nq, bf16_lo(ww.z), __uint_as_float(v[g * 8 + 4])) * inw;
+                o[g * 8 + 5] = fmaf(nq, bf16_hi(ww.z), __uint_as_float(v[g * 8 + 5])) * inw;
+                o[g * 8 + 6] = fmaf(nq, bf16_lo(ww.w), __uint_as_float(v[g * 8 + 6])) * inw;
+                o[g * 8 + 7] = fmaf(nq, bf16_hi(ww.w), __uint_as_float(v[g * 8 + 7])) * inw;
+            }
+            const unsigned long long t2 = tick();
+            stager.acquire();  // only now: the previous box has had the tcgen05.ld and the math above to leave
+            const unsigned long long t3 = tick();
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                stager.put(k, __float_as_uint(o[4 * k]), __float_as_uint(o[4 * k + 1]), __float_as_uint(o[4 * k + 2]),
+                           __float_as_uint(o[4 * k + 3]));
+            stager.commit(tm_out, dg, crow0);  // rows >= C / columns >= D are clipped by the TMA
+            if (prof != nullptr) { pacc[1] += t1 - t0; pacc[2] += t2 - t1; pacc[3] += t3 - t2; pacc[4] += tick() - t3; }
         }
         __device__ void tile(int i, int i_next, uint32_t taddr) {
             const int crow0 = p.c_begin + i * NCOL + rank * pr::ROWS + quad * 32;
-            const float nq = nqn, inw = inwn;
-#pragma unroll 1
-            for (int box = 0; box < 4; ++box) {
-                const int dbox = d0 + box * 32;
-                if (dbox >= p.D) {  // warp-uniform: columns past the embedding width
-                    if (i_next >= 0) prefetch(i_next);
-                    break;
-                }
-                uint4 w[4];
-#pragma unroll
-                for (int g = 0; g < 4; ++g) w[g] = wn[g];
-                uint32_t v[32];
-                tmem_ld32(taddr + box * 32, v);
-                // start the next box's operand loads before waiting on this one
-                if (box < 3) fetch_w(i, box + 1);
-                else if (i_next >= 0) prefetch(i_next);
-                tmem_ld_wait();
-                stager.acquire();
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const uint4 ww = w[g];
-                    const float o0 = fmaf(nq, bf16_lo(ww.x), __uint_as_float(v[g * 8 + 0])) * inw;
-                    const float o1 = fmaf(nq, bf16_hi(ww.x), __uint_as_float(v[g * 8 + 1])) * inw;
-                    const float o2 = fmaf(nq, bf16_lo(ww.y), __uint_as_float(v[g * 8 + 2])) * inw;
-                    const float o3 = fmaf(nq, bf16_hi(ww.y), __uint_as_float(v[g * 8 + 3])) * inw;
-                    const float o4 = fmaf(nq, bf16_lo(ww.z), __uint_as_float(v[g * 8 + 4])) * inw;
-                    const float o5 = fmaf(nq, bf16_hi(ww.z), __uint_as_float(v[g * 8 + 5])) * inw;
-                    const float o6 = fmaf(nq, bf16_lo(ww.w), __uint_as_float(v[g * 8 + 6])) * inw;
-                    const float o7 = fmaf(nq, bf16_hi(ww.w), __uint_as_float(v[g * 8 + 7])) * inw;
-                    stager.put(2 * g, __float_as_uint(o0), __float_as_uint(o1), __float_as_uint(o2), __float_as_uint(o3));
-                    stager.put(2 * g + 1, __float_as_uint(o4), __float_as_uint(o5), __float_as_uint(o6), __float_as_uint(o7));
-                }
-                stager.commit(tm_out, dbox, crow0);  // rows >= C / columns >= D are clipped by the TMA
+            const unsigned long long ts = tick();
+            if constexpr (FUSED) {
+                // q[i] is published (the block's accumulator is complete); normally it was fetched a tile ago
+                if (!have_scalars) fetch_scalars(i);
             }
+            const float nq = -(((qn[0] + qn[1]) + (qn[2] + qn[3])) + ((qn[4] + qn[5]) + (qn[6] + qn[7])));
+            const float inw = inwn;
+            if (prof != nullptr) pacc[0] += (nq == 123.456f ? 1 : 0) + tick() - ts;  // (uses nq: the loads must have landed)
+            if constexpr (!FUSED) {
+                if (i_next >= 0) fetch_scalars(i_next);
+            } else {
+                // the next block's q may be fetched now if this CTA's producer has already seen it published
+                have_scalars = false;
+                if (i_next >= 0) {
+                    int a = 0;
+                    if (lane == 0) a = *acquired;
+                    a = __shfl_sync(0xffffffffu, a, 0);
+                    if (a > i_next) {
+                        __threadfence_block();
+                        fetch_scalars(i_next);
+                        have_scalars = true;
+                    }
+                }
+            }
+            group(i, i_next, 0, taddr, crow0, nq, inw, wa);
+            group(i, i_next, 1, taddr, crow0, nq, inw, wb);
+            group(i, i_next, 2, taddr, crow0, nq, inw, wa);
+            group(i, i_next, 3, taddr, crow0, nq, inw, wb);
         }
-        __device__ void finish() { stager.drain(); }
+        __device__ void finish() {
+            if (prof != nullptr && lane == 0)
+                for (int k = 0; k < 5; ++k) prof[k] = pacc[k];
+            stager.drain();
+        }
     };
 };
+using BwdDWp = BwdDWpT<false>;
 
 // ------------------------------------------------------------------ dXhat, 256 x 256 output tile per CTA
 // Two stacked 128-row batch sub-tiles share every What k-block (64 KB per 1024 tensor cycles instead of
@@ -866,15 +1047,66 @@ struct BwdDX2 {
     };
 };
 
+}  // namespace ab
+#include "k3_fused.cuh"
+namespace ab {
+
 struct BwdPlan {
     int Bp;             // scratch leading dimension (batch rounded up to 64)
     int chunk_classes;  // classes per scratch chunk (multiple of 128)
     int n_chunks;
     bool dc_rs, dw_rs, dx2;  // which kernels take the resident-operand / stacked-tile fast path
     bool dc_pair, dw_pair;   // ... on CTA pairs (cta_group::2) instead of single CTAs
+    // single-launch backward (k3_fused.cuh): role split in CTA pairs, ring slots, counters
+    bool fused;
+    int n_dc, n_dw, n_dx, ring_slots, n_blocks;
+    size_t cnt_off, cnt_bytes;
     int q_slots;             // partial-sum slots of q per class
     size_t scratch_off, scratch_bytes, q_off, q_bytes, total;
 };
+
+// CTA pairs of bwd_fused_kernel that can be resident at once on the current device (the roles spin on each
+// other's counters, so the whole launch has to be).  0 on failure.
+static size_t fused_smem_bytes() {
+    size_t a = pr::smem_bytes<BwdDCpT<true>>(pr::MAX_KBLOCKS, BwdDCpT<true>::EXTRA_BYTES);
+    size_t b = pr::smem_bytes<BwdDWpT<true>>(pr::MAX_KBLOCKS, BwdDWpT<true>::EXTRA_BYTES);
+    size_t c = fz::dx_smem_bytes();
+    size_t m = a > b ? a : b;
+    return m > c ? m : c;
+}
+static int fused_max_pairs(int nsm) {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+    if (cached[dev] == 0) {
+        const size_t smem = fused_smem_bytes();
+        if (smem > 227 * 1024) return 0;
+        if (cudaFuncSetAttribute(fz::bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+            cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(static_cast<unsigned>(nsm / 2 * 2));
+        cfg.blockDim = dim3(pr::THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, fz::bwd_fused_kernel, &cfg) != cudaSuccess) {
+            cudaGetLastError();
+            n = 0;
+        }
+        if (n > nsm / 2) n = nsm / 2;
+        cached[dev] = n > 0 ? n : -1;
+    }
+    return cached[dev] > 0 ? cached[dev] : 0;
+}
 
 static bool env_is(const char* name, const char* value) {
     const char* v = getenv(name);
@@ -884,6 +1116,9 @@ static bool env_is(const char* name, const char* value) {
 // Kernel selection and scratch chunking.  Environment knobs (diagnostics / A-B measurements only):
 //   ARCFACE_B200_BWD_IMPL=generic   use the streaming kernels of gemm_core.cuh for every shape
 //   ARCFACE_B200_BWD_IMPL=rs        resident-operand kernels on single CTAs (gemm_rs.cuh) instead of CTA pairs
+//   ARCFACE_B200_BWD_IMPL=split     CTA-pair kernels as three launches through a full-size scratch
+//   ARCFACE_B200_BWD_SPLIT=a,b,c    CTA pairs given to the dC^T / dW / dX roles of the single-launch backward
+//   ARCFACE_B200_BWD_RING=<n>       ring slots of the single-launch backward
 //   ARCFACE_B200_BWD_CHUNK_MB=<n>   cap of the dC^T scratch in MiB
 static BwdPlan plan_backward(int B, int D, int64_t C, int nsm) {
     BwdPlan pl;
@@ -897,6 +1132,53 @@ static BwdPlan plan_backward(int B, int D, int64_t C, int nsm) {
     pl.dc_pair = pl.dc_rs && pairs;
     pl.dw_pair = pl.dw_rs && pairs;
     pl.q_slots = pl.dc_pair ? 2 * ((B + BwdDCp::NCOL - 1) / BwdDCp::NCOL) : pl.dc_rs ? 2 * ((B + rs::BN - 1) / rs::BN) : 1;
+    // ---- single-launch backward: every role needs its resident operand to fit (D, B <= 512) and the launch
+    // needs enough co-resident CTA pairs to give each role a few
+    pl.fused = false;
+    pl.n_dc = pl.n_dw = pl.n_dx = pl.ring_slots = 0;
+    pl.n_blocks = static_cast<int>((C + 255) / 256);
+    if (pl.dc_pair && pl.dw_pair && !env_is("ARCFACE_B200_BWD_IMPL", "split")) {
+        const int n_res_dc = (B + 255) / 256, n_res_dw = (D + 255) / 256;
+        const int tiles = n_res_dc * n_res_dw;         // dX output tiles (256 x 256)
+        const int dx_unit = (tiles + 1) / 2;           // CTA pairs per dX split
+        const int pairs = fused_max_pairs(nsm);
+        int a = 0, b = 0, c = 0;
+        if (const char* v = getenv("ARCFACE_B200_BWD_SPLIT")) sscanf(v, "%d,%d,%d", &a, &b, &c);
+        if (a <= 0 || b <= 0 || c <= 0 || a + b + c > pairs) {
+            // default shares, from the per-tile cycle counts of the roles (ARCFACE_B200_BWD_PROF): the dW role is
+            // the slowest per tile (fp32 output staged through shared memory), the dX role the fastest
+            c = static_cast<int>(pairs * 0.25) / dx_unit * dx_unit;
+            a = static_cast<int>(pairs * 0.33) / n_res_dc * n_res_dc;
+            b = (pairs - a - c) / n_res_dw * n_res_dw;
+        }
+        a = a / n_res_dc * n_res_dc;
+        b = b / n_res_dw * n_res_dw;
+        c = c / dx_unit * dx_unit;
+        if (a >= n_res_dc && b >= n_res_dw && c >= dx_unit && a + b + c <= pairs && pl.n_blocks >= 1) {
+            pl.fused = true;
+            pl.n_dc = a; pl.n_dw = b; pl.n_dx = c;
+            int slots = 64;
+            if (const char* v = getenv("ARCFACE_B200_BWD_RING")) slots = atoi(v);
+            const int min_slots = 2 * (a / n_res_dc) + 2;  // producers may run a tile or two ahead of the consumers
+            if (slots < min_slots) slots = min_slots;
+            if (slots > pl.n_blocks) slots = pl.n_blocks;
+            pl.ring_slots = slots;
+        }
+    }
+    if (pl.fused) {
+        pl.q_slots = 2 * ((B + BwdDCp::NCOL - 1) / BwdDCp::NCOL);
+        pl.chunk_classes = static_cast<int>(((C + 255) / 256) * 256);
+        pl.n_chunks = 1;
+        pl.scratch_off = 0;
+        pl.scratch_bytes = static_cast<size_t>(pl.ring_slots) * 256 * pl.Bp * 2;
+        pl.q_off = (pl.scratch_bytes + 255) / 256 * 256;
+        pl.q_bytes = static_cast<size_t>(C) * 4 * pl.q_slots;
+        pl.cnt_off = pl.q_off + (pl.q_bytes + 255) / 256 * 256;
+        pl.cnt_bytes = static_cast<size_t>(pl.n_blocks) * 2 * sizeof(int);
+        pl.total = pl.cnt_off + (pl.cnt_bytes + 255) / 256 * 256;
+        return pl;
+    }
+    pl.cnt_off = pl.cnt_bytes = 0;
     const int64_t c_round = ((C + 127) / 128) * 128;
     int64_t chunk;
     size_t cap = generic ? (size_t(64) << 20) : (size_t(2048) << 20);
@@ -960,6 +1242,15 @@ extern "C" int32_t arcface_b200_backward_plan(int32_t B, int32_t D, int64_t C_lo
     return ARCFACE_B200_OK;
 }
 
+extern "C" int32_t arcface_b200_backward_launches(int32_t B, int32_t D, int64_t C_local, int32_t* n_kernels) {
+    if (int32_t rc = check_arch()) return rc;
+    AB_REQUIRE(n_kernels, ARCFACE_B200_E_ARG, "backward_launches: null pointer");
+    if (int32_t rc = check_bwd_shape("backward_launches", B, D, C_local)) return rc;
+    const BwdPlan pl = plan_backward(B, D, C_local, sm_count());
+    *n_kernels = pl.fused ? 1 : 3 * pl.n_chunks;
+    return ARCFACE_B200_OK;
+}
+
 extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* xhat_t, int64_t ld_t,
                                          const uint16_t* what, const float* inv_nw, const float* lse,
                                          const float* one_minus_p, const float* dphi, const int32_t* label_local,
@@ -999,6 +1290,139 @@ extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* x
 
     const int n_tiles = (B + BwdDC::BLOCK_N - 1) / BwdDC::BLOCK_N;
     const int dn_tiles = (D + 255) / 256;
+
+    if (pl.fused) {
+        int* counters = reinterpret_cast<int*>(ws + pl.cnt_off);
+        AB_CHECK_CUDA(cudaMemsetAsync(counters, 0, pl.cnt_bytes, st));
+        Ring ring;
+        ring.slots = pl.ring_slots;
+        ring.ready = counters;
+        ring.done = counters + pl.n_blocks;
+        const int n_res_dc = (B + 255) / 256, n_res_dw = (D + 255) / 256;
+        ring.ready_target = n_res_dc * 2;  // one arrival per producer CTA (its publisher warp)
+        ring.done_target = n_res_dw + n_res_dc * n_res_dw;
+        fz::FusedParams fp;
+        fp.n_dc = pl.n_dc;
+        fp.n_dw = pl.n_dw;
+        fp.n_dx = pl.n_dx;
+        {
+            // interleave the roles over the launch order (largest deficit first)
+            const int total = pl.n_dc + pl.n_dw + pl.n_dx;
+            AB_REQUIRE(total <= fz::MAX_PAIRS, ARCFACE_B200_E_SHAPE, "backward: %d CTA pairs exceed the role table", total);
+            const int want[3] = {pl.n_dc, pl.n_dw, pl.n_dx};
+            int got[3] = {0, 0, 0};
+            const bool blocked = env_is("ARCFACE_B200_BWD_ORDER", "blocked");  // A/B: roles in contiguous ranges
+            for (int pi = 0; pi < total; ++pi) {
+                int best = -1;
+                double best_def = -1e30;
+                for (int k = 0; k < 3; ++k) {
+                    if (got[k] >= want[k]) continue;
+                    const double def = blocked ? -k : static_cast<double>(want[k]) * (pi + 1) / total - got[k];
+                    if (def > best_def) { best_def = def; best = k; }
+                }
+                fp.role[pi] = static_cast<uint8_t>(best);
+                fp.index[pi] = static_cast<uint8_t>(got[best]++);
+            }
+        }
+        {
+            BwdDCpT<true>::Params& p = fp.dc;
+            p.core.kblocks = (D + pr::BK - 1) / pr::BK;
+            p.core.s_blocks = pl.n_blocks;
+            p.core.s_row0 = 0;
+            p.core.n_res = n_res_dc;
+            p.core.contiguous = 0;
+            p.core.prefetch_tiles = 2;
+            p.B = B; p.C = C; p.Bp = pl.Bp;
+            p.s_log2e = s * LOG2E_B; p.coef = s * grad_scale; p.grad_dev = grad_loss_dev;
+            p.lse = lse; p.one_minus_p = one_minus_p; p.dphi = dphi; p.label_local = label_local;
+            p.q = q;
+            p.ring = ring;
+        }
+        {
+            BwdDWpT<true>::Params& p = fp.dw;
+            p.core.kblocks = pl.Bp / pr::BK;
+            p.core.s_blocks = pl.n_blocks;
+            p.core.s_row0 = 0;
+            p.core.n_res = n_res_dw;
+            p.core.contiguous = 0;
+            p.core.prefetch_tiles = 0;  // the ring lives in L2
+            p.C = C; p.D = D; p.c_begin = 0;
+            p.q = q; p.q_slots = pl.q_slots; p.inv_nw = inv_nw;
+            p.what = reinterpret_cast<const __nv_bfloat16*>(what);
+            p.dw = dw;
+            p.ring = ring;
+        }
+        {
+            fz::DXParams& p = fp.dx;
+            p.B = B; p.D = D;
+            p.n_blocks = pl.n_blocks;
+            p.m_tiles = n_res_dc; p.dn_tiles = n_res_dw;
+            p.splits = (2 * pl.n_dx) / (n_res_dc * n_res_dw);
+            p.ring = ring;
+        }
+        // the ring replaces the full-size scratch: [slots * 256][Bp] bf16
+        CUtensorMap tm_ring_out, tm_ring_k, tm_ring_mn;
+        const int64_t ring_rows = static_cast<int64_t>(pl.ring_slots) * 256;
+        if (int32_t rc = make_tmap_store(&tm_ring_out, dct, 2, pl.Bp, ring_rows, pl.Bp)) return rc;
+        if (int32_t rc = make_tmap_kmajor(&tm_ring_k, dct, B, ring_rows, pl.Bp, pr::ROWS)) return rc;
+        if (int32_t rc = make_tmap_mnmajor(&tm_ring_mn, dct, B, ring_rows, pl.Bp)) return rc;
+        const size_t smem = fused_smem_bytes();
+        const int grid = 2 * (pl.n_dc + pl.n_dw + pl.n_dx);
+        // measurements only: ARCFACE_B200_BWD_PROF=1 prints where each role's warps waited (synchronises!)
+        static unsigned long long* prof_dev = nullptr;
+        const bool prof = env_is("ARCFACE_B200_BWD_PROF", "1");
+        if (prof) {
+            if (prof_dev == nullptr) AB_CHECK_CUDA(cudaMalloc(&prof_dev, 2 * fz::MAX_PAIRS * 16 * sizeof(unsigned long long)));
+            AB_CHECK_CUDA(cudaMemsetAsync(prof_dev, 0, 2 * fz::MAX_PAIRS * 16 * sizeof(unsigned long long), st));
+            fp.dc.core.prof = prof_dev; fp.dc.core.prof_cta = 0;
+            fp.dw.core.prof = prof_dev; fp.dw.core.prof_cta = 2 * pl.n_dc;
+            fp.dx.prof = prof_dev; fp.dx.prof_cta = 2 * (pl.n_dc + pl.n_dw);
+        }
+        fz::bwd_fused_kernel<<<grid, pr::THREADS, smem, st>>>(tm_w_k, tm_x_k, tm_ring_out, tm_ring_k, tm_xt_k, tm_dw_out,
+                                                             tm_ring_mn, tm_w_mn, tm_dx_out, fp);
+        AB_CHECK_CUDA(cudaGetLastError());
+        if (prof) {
+            static unsigned long long host[2 * fz::MAX_PAIRS * 16];
+            AB_CHECK_CUDA(cudaStreamSynchronize(st));
+            AB_CHECK_CUDA(cudaMemcpy(host, prof_dev, sizeof(host), cudaMemcpyDeviceToHost));
+            const char* names[3] = {"dC^T", "dW", "dX"};
+            const int first[4] = {0, 2 * pl.n_dc, 2 * (pl.n_dc + pl.n_dw), grid};
+            for (int r = 0; r < 3; ++r) {
+                double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                int n = 0;
+                for (int c = first[r]; c < first[r + 1]; ++c) {
+                    if (r < 2 && ((c - first[r]) & 1)) continue;  // pair roles: the leader CTA carries the MMA counters
+                    for (int k = 0; k < 8; ++k) a[k] += static_cast<double>(host[c * 16 + k]);
+                    ++n;
+                }
+                if (n == 0) continue;
+                for (int k = 0; k < 8; ++k) a[k] /= n;
+                fprintf(stderr,
+                        "[bwd prof] %-5s ctas=%d tiles/cta=%.1f body=%.0f cyc | producer: flags %.0f, free stage %.0f | "
+                        "mma: operands %.0f, free acc %.0f | epi warp: acc wait %.0f, in tile %.0f | per tile: body %.0f, "
+                        "epi %.0f\n",
+                        names[r], first[r + 1] - first[r], a[7], a[6], a[0], a[1], a[2], a[3], a[4], a[5],
+                        a[7] > 0 ? a[6] / a[7] : 0.0, a[7] > 0 ? a[5] / a[7] : 0.0);
+                if (r == 1 && a[7] > 0) {
+                    double e[5] = {0, 0, 0, 0, 0};
+                    for (int c = first[1]; c < first[2]; c += 2)
+                        for (int k = 0; k < 5; ++k) e[k] += static_cast<double>(host[c * 16 + 8 + k]);
+                    fprintf(stderr, "[bwd prof] dW epilogue per tile: scalars %.0f, tmem load %.0f, math %.0f, staging wait %.0f, "
+                                    "store issue %.0f\n",
+                            e[0] / n / a[7], e[1] / n / a[7], e[2] / n / a[7], e[3] / n / a[7], e[4] / n / a[7]);
+                }
+                if (r == 0 && a[7] > 0) {
+                    double e[5] = {0, 0, 0, 0, 0};
+                    for (int c = first[0]; c < first[1]; c += 2)
+                        for (int k = 0; k < 5; ++k) e[k] += static_cast<double>(host[c * 16 + 8 + k]);
+                    fprintf(stderr, "[bwd prof] dC^T epilogue per tile: publish %.0f, slot wait %.0f, tmem load %.0f, math %.0f, "
+                                    "staging wait %.0f\n",
+                            e[0] / n / a[7], e[1] / n / a[7], e[2] / n / a[7], e[3] / n / a[7], e[4] / n / a[7]);
+                }
+            }
+        }
+        return ARCFACE_B200_OK;
+    }
 
     for (int64_t c0 = 0; c0 < C_local; c0 += pl.chunk_classes) {
         const int cn = static_cast<int>(C_local - c0 < pl.chunk_classes ? C_local - c0 : pl.chunk_classes);
@@ -1060,6 +1484,7 @@ extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* x
             p.C = C; p.D = D; p.c_begin = static_cast<int>(c0);
             p.q = q; p.q_slots = pl.q_slots; p.inv_nw = inv_nw;
             p.what = reinterpret_cast<const __nv_bfloat16*>(what);
+            p.dw = dw;
             int groups = (nsm / 2) / p.core.n_res;
             if (groups < 1) groups = 1;
             if (groups > p.core.s_blocks) groups = p.core.s_blocks;

@@ -151,8 +151,18 @@ template <int N>
 __device__ __forceinline__ void bulk_wait() {
     asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
+// No "memory" clobber: the staging buffers are only ever touched through these volatile asm statements (which
+// keep their order among themselves and against the fence / TMA asm that follows), and a clobber here would
+// stop the compiler from overlapping the loads of the next chunk's constants with this chunk's stores.
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
+}
+
+__device__ __forceinline__ void st_global_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void st_global_v4_b32(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
 // ---------------------------------------------------------------- tcgen05 / TMEM

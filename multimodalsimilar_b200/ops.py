@@ -193,6 +193,13 @@ def backward_plan(B: int, D: int, c_local: int):
     return cc.value, n.value
 
 
+def backward_launches(B: int, D: int, c_local: int) -> int:
+    """Kernels one `backward` call launches (1 = single-launch backward, else 3 per scratch chunk)."""
+    n = ctypes.c_int32(0)
+    _lib.call("arcface_b200_backward_launches", B, D, c_local, ctypes.byref(n))
+    return n.value
+
+
 def backward(xhat, xhat_t, what, inv_nw, lse, one_minus_p, dphi, label_local, s: float, grad_scale: float,
              grad_loss_dev=None, dw_out=None):
     """K3.  Returns (dxhat fp32 [B, D] partial over this shard's classes, dW fp32 [C_local, D])."""

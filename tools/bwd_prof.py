@@ -1,0 +1,29 @@
+"""Runs the single-launch backward once per given role split with ARCFACE_B200_BWD_PROF=1 (wait-time report on stderr)."""
+import math, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from multimodalsimilar_b200 import ops
+
+dev = torch.device("cuda:0")
+B, D, C = 512, 512, 1000000
+g = torch.Generator(device=dev).manual_seed(0)
+bound = math.sqrt(6.0 / (C + D))
+w = torch.empty(C, D, device=dev).uniform_(-bound, bound, generator=g)
+x = torch.randn(B, D, device=dev, generator=g)
+y = torch.randint(0, C, (B,), device=dev, generator=g)
+xhat, inv_nx, xhat_t = ops.normalize_cast(x, want_transpose=True)
+lm = ops.label_margin(x, w, inv_nx, None, y, 0, C, 64.0, 0.5, False)
+what, inv_nw, rmax, rsum, rarg = ops.forward_rows_fused(xhat, w, lm.label_local, 64.0, 0)
+lse, arg, zl, omp, loss = ops.finalize_rows(rmax.view(1, B), rsum.view(1, B), rarg.view(1, B), lm.z_label.view(1, B), y)
+dw = torch.empty_like(w)
+for split in sys.argv[1:] or ["30,30,14"]:
+    os.environ["ARCFACE_B200_BWD_SPLIT"] = split
+    os.environ.pop("ARCFACE_B200_BWD_PROF", None)
+    for _ in range(2):
+        ops.backward(xhat, xhat_t, what, inv_nw, lse, omp, lm.dphi, lm.label_local, 64.0, 1.0 / B, dw_out=dw)
+    torch.cuda.synchronize()
+    os.environ["ARCFACE_B200_BWD_PROF"] = "1"
+    print("== split", split, file=sys.stderr, flush=True)
+    ops.backward(xhat, xhat_t, what, inv_nw, lse, omp, lm.dphi, lm.label_local, 64.0, 1.0 / B, dw_out=dw)
+    torch.cuda.synchronize()
