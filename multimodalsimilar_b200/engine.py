@@ -1,0 +1,286 @@
+"""Step engine of the ArcFace head: the kernel sequence of one forward / backward, run either eagerly or as
+two replayed CUDA graphs.
+
+One sequence serves both public modules: `ArcMarginProduct` (group = None, the whole class range on one GPU)
+and `ShardedArcMarginProduct` (class shard per rank, three NCCL collectives per step: all-gather of the local
+embeddings + labels, all-gather of the packed per-row statistics, reduce-scatter of the embedding gradient;
+reference counterpart: nn.DataParallel at nlp_classifier_train_daodian_v2_dist.py:85).
+
+Why graphs: at 8 GPUs one rank's kernels for the north-star shape take ~0.4 ms, less than the host needs to
+issue ~60 small torch / ctypes calls, so the eager step is host-bound (0.84 ms measured).  `GraphedStep` captures
+the forward (kernels + collectives) and the backward once per signature -- every buffer, including `what`, the
+softmax statistics and dW, lives in the graph's private pool -- and replays them: two launches per step.
+The captured kernels are the same C-ABI calls the eager path makes (`ops`), on the capture stream.
+"""
+from __future__ import annotations
+
+import warnings
+import weakref
+from dataclasses import dataclass
+from typing import Any, Optional
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass(frozen=True)
+class StepConfig:
+    s: float
+    m: float
+    easy_margin: bool
+    class_lo: int     # first global class id of the local weight rows
+    c_total: int      # classes over all ranks
+
+
+@dataclass
+class FwdState:
+    """Everything the backward needs; no B x C tensor."""
+    loss: torch.Tensor
+    argmax_local: torch.Tensor
+    bad_flag: torch.Tensor
+    B: int
+    inv_nx: torch.Tensor
+    xhat: torch.Tensor
+    xhat_t: torch.Tensor
+    what: torch.Tensor
+    inv_nw: torch.Tensor
+    lse: torch.Tensor
+    omp: torch.Tensor
+    dphi: torch.Tensor
+    label_local: torch.Tensor
+
+
+def _world(group) -> int:
+    return 1 if group is None else dist.get_world_size(group)
+
+
+def _rank(group) -> int:
+    return 0 if group is None else dist.get_rank(group)
+
+
+def _all_gather_bytes(buf: torch.Tensor, group) -> torch.Tensor:
+    """buf uint8 [n] -> uint8 [R, n]."""
+    out = torch.empty(_world(group) * buf.numel(), dtype=torch.uint8, device=buf.device)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    return out.view(_world(group), buf.numel())
+
+
+def gather_batch(x_local: torch.Tensor, y_local: torch.Tensor, group):
+    """All ranks' embeddings [B, D] fp32 and labels [B] int64 in rank order: ONE collective over the
+    byte-packed (x | labels) of every rank."""
+    R = _world(group)
+    if R == 1:
+        return x_local, y_local
+    b, D = x_local.shape
+    xb = b * D * 4
+    packed = torch.cat([x_local.reshape(-1).view(torch.uint8), y_local.view(torch.uint8)])
+    allp = _all_gather_bytes(packed, group)
+    x_all = allp[:, :xb].contiguous().view(torch.float32).reshape(R * b, D)
+    y_all = allp[:, xb:].contiguous().view(torch.int64).reshape(R * b)
+    return x_all, y_all
+
+
+def exchange_rows(rmax, rsum, z_label, rarg, group):
+    """Per-rank statistics [B] -> [R, B] each, in ONE collective (20 bytes per row per rank)."""
+    R = _world(group)
+    B = rmax.shape[0]
+    if R == 1:
+        return rmax.view(1, B), rsum.view(1, B), z_label.view(1, B), rarg.view(1, B)
+    packed = torch.cat([rarg.view(torch.uint8), rmax.view(torch.uint8), rsum.view(torch.uint8),
+                        z_label.view(torch.uint8)])
+    allp = _all_gather_bytes(packed, group)
+    a = allp[:, : 8 * B].contiguous().view(torch.int64).reshape(R, B)
+    f = allp[:, 8 * B:].contiguous().view(torch.float32).reshape(R, 3, B)
+    return f[:, 0].contiguous(), f[:, 1].contiguous(), f[:, 2].contiguous(), a
+
+
+def reduce_scatter_rows(full: torch.Tensor, group) -> torch.Tensor:
+    """Sum `full` [R * n, D] over ranks and return this rank's n rows."""
+    R = _world(group)
+    if R == 1:
+        return full
+    rank = _rank(group)
+    n = full.shape[0] // R
+    if dist.get_backend(group) == "gloo":  # gloo has no reduce-scatter; used by the CPU tests only
+        buf = full.clone()
+        dist.all_reduce(buf, group=group)
+        return buf[rank * n:(rank + 1) * n].contiguous()
+    out = torch.empty((n,) + tuple(full.shape[1:]), dtype=full.dtype, device=full.device)
+    dist.reduce_scatter_tensor(out, full.contiguous(), group=group)
+    return out
+
+
+def forward_eager(K, group, x_local, w, y_local, cfg: StepConfig) -> FwdState:
+    """K1 (x) -> label margin -> K1 (w) + K2 -> combine -> [exchange] -> finalize.  arcface.py:45-63 + the mean
+    CrossEntropyLoss + argmax of the call sites, for the global batch against the local class rows."""
+    R, rank = _world(group), _rank(group)
+    b_loc = x_local.shape[0]
+    x_all, y_all = gather_batch(x_local, y_local, group)
+    B = x_all.shape[0]
+    xhat, inv_nx, xhat_t = K.normalize_cast(x_all, want_transpose=True)
+    lm = K.label_margin(x_all, w, inv_nx, None, y_all, cfg.class_lo, cfg.c_total, cfg.s, cfg.m, cfg.easy_margin)
+    what, inv_nw, rmax, rsum, rarg = K.forward_rows_fused(xhat, w, lm.label_local, cfg.s, cfg.class_lo)
+    rows_max, rows_sum, rows_z, rows_arg = exchange_rows(rmax, rsum, lm.z_label, rarg, group)
+    lse, argmax, _z, omp, loss = K.finalize_rows(rows_max, rows_sum, rows_arg, rows_z, y_all)
+    argmax_local = argmax if R == 1 else argmax[rank * b_loc:(rank + 1) * b_loc].contiguous()
+    return FwdState(loss, argmax_local, lm.bad_flag, B, inv_nx, xhat, xhat_t, what, inv_nw, lse, omp, lm.dphi,
+                    lm.label_local)
+
+
+def backward_eager(K, group, x_local, st: FwdState, grad_loss, cfg: StepConfig, need_dx: bool = True):
+    """K3 -> [reduce-scatter] -> normalise backward.  Returns (dx for the local rows or None, dW of the local
+    class rows)."""
+    R, rank = _world(group), _rank(group)
+    b_loc = x_local.shape[0]
+    g = grad_loss.to(torch.float32).contiguous()
+    dxhat_part, dw = K.backward(st.xhat, st.xhat_t, st.what, st.inv_nw, st.lse, st.omp, st.dphi, st.label_local,
+                                cfg.s, 1.0 / st.B, grad_loss_dev=g)
+    dx = None
+    if need_dx:
+        dxhat_loc = reduce_scatter_rows(dxhat_part, group)
+        inv_loc = st.inv_nx if R == 1 else st.inv_nx[rank * b_loc:(rank + 1) * b_loc].contiguous()
+        dx = K.normalize_bwd_x(x_local, inv_loc, dxhat_loc)
+    return dx, dw
+
+
+# ----------------------------------------------------------------------------------------- CUDA graphs
+class GraphedStep:
+    """Forward and backward of one signature captured as two CUDA graphs over static buffers."""
+
+    WARMUP = 2
+
+    def __init__(self, K, group, w: torch.Tensor, b_loc: int, cfg: StepConfig, with_backward: bool):
+        dev = w.device
+        D = w.shape[1]
+        self.K, self.group, self.cfg = K, group, cfg
+        self.w_ptr = w.data_ptr()
+        self.x = torch.zeros((b_loc, D), dtype=torch.float32, device=dev)
+        self.y = torch.zeros((b_loc,), dtype=torch.int64, device=dev)
+        self.g = torch.ones((), dtype=torch.float32, device=dev)
+        self.version = 0
+        self.with_backward = with_backward
+        # labels of the warm-up / capture runs must be valid class ids on every rank
+        self.y.fill_(cfg.class_lo)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(self.WARMUP):  # lazy initialisation (NCCL communicators, kernel attributes) outside capture
+                st = forward_eager(K, group, self.x, w, self.y, cfg)
+                if with_backward:
+                    backward_eager(K, group, self.x, st, self.g, cfg)
+            del st
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.fwd_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.fwd_graph):
+            self.st = forward_eager(K, group, self.x, w, self.y, cfg)
+        self.bwd_graph = None
+        self.dx = self.dw = None
+        if with_backward:
+            self.bwd_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.bwd_graph, pool=self.fwd_graph.pool()):
+                self.dx, self.dw = backward_eager(K, group, self.x, self.st, self.g, cfg)
+
+    def forward(self, x_local, y_local):
+        self.x.copy_(x_local)
+        self.y.copy_(y_local)
+        self.fwd_graph.replay()
+        self.version += 1
+        return self.version
+
+    def backward(self, grad_loss):
+        self.g.copy_(grad_loss.reshape(()))
+        self.bwd_graph.replay()
+
+
+class _GraphedCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, label, plan: GraphedStep, weight_ref):
+        ctx.version = plan.forward(x, label)
+        ctx.plan = plan
+        ctx.weight_ref = weight_ref
+        loss = plan.st.loss.clone()
+        argmax = plan.st.argmax_local.clone()
+        ctx.mark_non_differentiable(argmax)
+        return loss, argmax
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_argmax):
+        plan = ctx.plan
+        if ctx.version != plan.version:
+            raise RuntimeError("ArcMarginProduct (CUDA-graph mode): backward() of a forward whose buffers were reused "
+                               "by a later forward of the same head; set head.use_cuda_graph = False to keep several "
+                               "forwards in flight")
+        param = ctx.weight_ref() if ctx.weight_ref is not None else None
+        if param is not None and param.grad is not None and \
+                param.grad.untyped_storage().data_ptr() == plan.dw.untyped_storage().data_ptr():
+            # the caller accumulates gradients and .grad still aliases the buffer this replay overwrites
+            param.grad = param.grad.clone()
+        plan.backward(grad_loss)
+        dx = plan.dx.clone() if ctx.needs_input_grad[0] else None
+        dw = plan.dw.detach() if ctx.needs_input_grad[1] else None  # alias: autograd adopts it without a copy
+        return dx, dw, None, None, None
+
+
+class _EagerCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, label, K, group, cfg, validate_labels):
+        st = forward_eager(K, group, x, w, label, cfg)
+        if validate_labels and int(st.bad_flag.item()) != 0:
+            raise IndexError("ArcMarginProduct: a label is outside [0, %d)" % cfg.c_total)
+        ctx.save_for_backward(x, st.inv_nx, st.xhat, st.xhat_t, st.what, st.inv_nw, st.lse, st.omp, st.dphi,
+                              st.label_local)
+        ctx.meta = (K, group, cfg, st.B)
+        ctx.mark_non_differentiable(st.argmax_local)
+        return st.loss, st.argmax_local
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_argmax):
+        x, inv_nx, xhat, xhat_t, what, inv_nw, lse, omp, dphi, label_local = ctx.saved_tensors
+        K, group, cfg, B = ctx.meta
+        st = FwdState(None, None, None, B, inv_nx, xhat, xhat_t, what, inv_nw, lse, omp, dphi, label_local)
+        dx, dw = backward_eager(K, group, x, st, grad_loss, cfg, need_dx=ctx.needs_input_grad[0])
+        return dx, (dw if ctx.needs_input_grad[1] else None), None, None, None, None, None
+
+
+# per-head graph state lives outside the module's __dict__ so that torch.save(model) keeps working
+_PLANS: "weakref.WeakKeyDictionary[Any, dict]" = weakref.WeakKeyDictionary()
+
+ENGAGE_AFTER = 2  # eager calls with an unchanged signature before a graph is captured
+
+
+def run_step(head, K, group, x, w, label, cfg: StepConfig, validate_labels: bool):
+    """loss, argmax = one forward of `head` (autograd-connected).  Graph replay when `head.use_cuda_graph` and the
+    signature has repeated; the eager kernel sequence otherwise."""
+    use_graph = bool(getattr(head, "use_cuda_graph", False)) and x.is_cuda and not validate_labels
+    if not use_graph:
+        return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels)
+    with_bwd = torch.is_grad_enabled() and (x.requires_grad or w.requires_grad)
+    sig = (tuple(x.shape), x.device, w.data_ptr(), tuple(w.shape), cfg, with_bwd, id(group))
+    state = _PLANS.setdefault(head, {"sig": None, "seen": 0, "plan": None, "failed": False})
+    if state["failed"]:
+        return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels)
+    if state["sig"] != sig:
+        state.update(sig=sig, seen=0, plan=None)
+    if state["plan"] is None:
+        state["seen"] += 1
+        if state["seen"] <= ENGAGE_AFTER:
+            return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels)
+        try:
+            state["plan"] = GraphedStep(K, group, w.detach(), x.shape[0], cfg, with_bwd)
+        except Exception as e:  # keep training: the eager sequence computes the same thing
+            state["failed"] = True
+            warnings.warn("multimodalsimilar_b200: CUDA-graph capture failed (%r); continuing with eager launches" % (e,))
+            return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels)
+    plan: GraphedStep = state["plan"]
+    param = getattr(head, "weight", None)
+    ref = weakref.ref(param) if isinstance(param, torch.nn.Parameter) else None
+    if not with_bwd:
+        plan.forward(x, label)
+        return plan.st.loss.clone(), plan.st.argmax_local.clone()
+    return _GraphedCE.apply(x, w, label, plan, ref)
+
+
+def drop_plan(head) -> None:
+    """Forget the captured graphs of `head` (frees their memory pool)."""
+    _PLANS.pop(head, None)

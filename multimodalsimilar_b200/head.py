@@ -20,43 +20,27 @@ import torch.nn.functional as F
 from torch import nn
 from torch.nn import Parameter
 
-from . import ops
+from . import engine, ops
 
 
 class ArcFaceCEFunction(torch.autograd.Function):
-    """loss, argmax = ArcFaceCE(x, weight, label; s, m, easy_margin).
+    """loss, argmax = ArcFaceCE(x, weight, label; s, m, easy_margin)  -- the eager kernel sequence.
 
     forward : K1 (x), label margin, K1 (weight) fused into K2 (+combine, finalize)
     backward: K3 (dC^T producer, dW GEMM, dX GEMM) + normalise backward for x
-    Saved for backward: xhat / xhat^T / what (bf16), the inverse norms, lse, z_label, dphi, labels --
-    no B x C tensor.
+    Saved for backward: xhat / xhat^T / what (bf16), the inverse norms, lse, 1 - p_label, dphi, labels --
+    no B x C tensor.  (`engine.py` holds the sequence; the modules go through `engine.run_step`, which replays it
+    as two CUDA graphs once the call signature has repeated.)
     """
 
     @staticmethod
     def forward(ctx, x, weight, label, s, m, easy_margin, validate_labels):
-        B, D = x.shape
-        C = weight.shape[0]
-        xhat, inv_nx, xhat_t = ops.normalize_cast(x, want_transpose=True)
-        lm = ops.label_margin(x, weight, inv_nx, None, label, 0, C, s, m, easy_margin)
-        what, inv_nw, rmax, rsum, rarg = ops.forward_rows_fused(xhat, weight, lm.label_local, s, 0)
-        lse, argmax, _z, omp, loss = ops.finalize_rows(rmax.view(1, B), rsum.view(1, B), rarg.view(1, B),
-                                                       lm.z_label.view(1, B), label)
-        if validate_labels and int(lm.bad_flag.item()) != 0:
-            raise IndexError("ArcMarginProduct: a label is outside [0, %d)" % C)
-        ctx.save_for_backward(x, inv_nx, xhat, xhat_t, what, inv_nw, lse, omp, lm.dphi, lm.label_local)
-        ctx.s = s
-        ctx.mark_non_differentiable(argmax)
-        return loss, argmax
+        cfg = engine.StepConfig(float(s), float(m), bool(easy_margin), 0, weight.shape[0])
+        return engine._EagerCE.forward(ctx, x, weight, label, ops, None, cfg, validate_labels)
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_argmax):
-        x, inv_nx, xhat, xhat_t, what, inv_nw, lse, omp, dphi, label_local = ctx.saved_tensors
-        B = x.shape[0]
-        g = grad_loss.to(torch.float32).contiguous()
-        dxhat, dw = ops.backward(xhat, xhat_t, what, inv_nw, lse, omp, dphi, label_local, ctx.s, 1.0 / B,
-                                 grad_loss_dev=g)
-        dx = ops.normalize_bwd_x(x, inv_nx, dxhat) if ctx.needs_input_grad[0] else None
-        return dx, (dw if ctx.needs_input_grad[1] else None), None, None, None, None, None
+        return engine._EagerCE.backward(ctx, grad_loss, _grad_argmax)
 
 
 class FusedLogits:
@@ -171,7 +155,7 @@ class ArcMarginProduct(nn.Module):
     """
 
     def __init__(self, in_feature=128, out_feature=10575, s=64.0, m=0.40, easy_margin=False, *,
-                 in_features=None, out_features=None, validate_labels=False):
+                 in_features=None, out_features=None, validate_labels=False, use_cuda_graph=True):
         super().__init__()
         if in_features is not None:
             in_feature = in_features
@@ -185,6 +169,7 @@ class ArcMarginProduct(nn.Module):
         nn.init.xavier_uniform_(self.weight)  # arcface.py:24-25
         self.easy_margin = easy_margin
         self.validate_labels = validate_labels
+        self.use_cuda_graph = use_cuda_graph
         self.cos_m, self.sin_m, self.th, self.mm = ops.margin_constants(m)
 
     def update_m(self, delta):
@@ -210,8 +195,8 @@ class ArcMarginProduct(nn.Module):
         """Fused head + mean softmax cross-entropy.  Returns (loss [], argmax int64 [B])."""
         x, label = self._prep(x, label)
         w = self.weight if self.weight.is_contiguous() else self.weight.contiguous()
-        return ArcFaceCEFunction.apply(x, w, label, float(self.s), float(self.m), bool(self.easy_margin),
-                                       bool(self.validate_labels))
+        cfg = engine.StepConfig(float(self.s), float(self.m), bool(self.easy_margin), 0, w.shape[0])
+        return engine.run_step(self, ops, None, x, w, label, cfg, bool(self.validate_labels))
 
     def forward(self, x, label):
         return FusedLogits(self, x, label)

@@ -6,9 +6,12 @@ weight to every GPU each step, gathers the B x C logits to cuda:0 and reduces a 
 Here rank r owns classes [lo_r, hi_r) (weight rows, their gradient and optimiser state never leave the
 rank) and the per-step traffic is three small collectives over NCCL / NVLink:
 
-  1. all-gather the local embeddings + labels          (B x D fp32 + B int64)
+  1. all-gather the local embeddings + labels          (B x D fp32 + B int64, byte-packed: one collective)
   2. all-gather the per-row softmax statistics         (R x B x 20 bytes: max, sum-exp, label logit, argmax)
   3. reduce-scatter the embedding gradient partials    (B x D fp32)
+
+The sequence itself (and its CUDA-graph replay, which is what keeps an 8-GPU step from being host-bound) lives
+in `engine.py`; this module owns the shard bookkeeping and the reference-layout checkpoint helpers.
 
 The compute between them is the same kernel sequence as the single-GPU head, run on the local class
 shard for the whole (gathered) batch.  `kernels` is the object providing that sequence; it defaults to
@@ -23,6 +26,8 @@ import torch
 import torch.distributed as dist
 from torch import nn
 from torch.nn import Parameter
+
+from . import engine
 
 
 def shard_range(num_classes: int, world_size: int, rank: int):
@@ -40,75 +45,6 @@ def _all_gather_rows(t: torch.Tensor, group) -> torch.Tensor:
     return out
 
 
-def _reduce_scatter_rows(full: torch.Tensor, group) -> torch.Tensor:
-    """Sum `full` [R * n, ...] over ranks and return this rank's n rows."""
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    n = full.shape[0] // world
-    if dist.get_backend(group) == "gloo":  # gloo has no reduce-scatter; used by the CPU tests only
-        buf = full.clone()
-        dist.all_reduce(buf, group=group)
-        return buf[rank * n:(rank + 1) * n].contiguous()
-    out = torch.empty((n,) + tuple(full.shape[1:]), dtype=full.dtype, device=full.device)
-    dist.reduce_scatter_tensor(out, full.contiguous(), group=group)
-    return out
-
-
-def _pack_rows(rmax, rsum, z, rarg) -> torch.Tensor:
-    """One byte buffer per rank so the statistics exchange is a single collective."""
-    f = torch.stack([rmax, rsum, z]).contiguous().view(torch.uint8).reshape(-1)
-    a = rarg.contiguous().view(torch.uint8).reshape(-1)
-    return torch.cat([f, a]).unsqueeze(0)
-
-
-def _unpack_rows(buf: torch.Tensor, B: int):
-    R = buf.shape[0]
-    f = buf[:, : 12 * B].contiguous().view(torch.float32).reshape(R, 3, B)
-    a = buf[:, 12 * B:].contiguous().view(torch.int64).reshape(R, B)
-    return f[:, 0].contiguous(), f[:, 1].contiguous(), f[:, 2].contiguous(), a.contiguous()
-
-
-class ShardedArcFaceCE(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x_local, w_shard, label_local, head):
-        K, group = head.kernels, head.process_group
-        world, rank = dist.get_world_size(group), dist.get_rank(group)
-        b_loc = x_local.shape[0]
-        B = world * b_loc
-        x_all = _all_gather_rows(x_local, group)
-        y_all = _all_gather_rows(label_local, group)
-        xhat, inv_nx, xhat_t = K.normalize_cast(x_all, want_transpose=True)
-        lm = K.label_margin(x_all, w_shard, inv_nx, None, y_all, head.class_lo, head.out_feature, float(head.s),
-                            float(head.m), bool(head.easy_margin))
-        what, inv_nw, rmax, rsum, rarg = K.forward_rows_fused(xhat, w_shard, lm.label_local, float(head.s),
-                                                              head.class_lo)
-        packed = _all_gather_rows(_pack_rows(rmax, rsum, lm.z_label, rarg), group)
-        rows_max, rows_sum, rows_z, rows_arg = _unpack_rows(packed, B)
-        lse, argmax, _z, omp, loss = K.finalize_rows(rows_max, rows_sum, rows_arg, rows_z, y_all)
-        ctx.save_for_backward(x_local, inv_nx, xhat, xhat_t, what, inv_nw, lse, omp, lm.dphi, lm.label_local)
-        ctx.head = head
-        ctx.B = B
-        argmax_local = argmax[rank * b_loc:(rank + 1) * b_loc].contiguous()
-        ctx.mark_non_differentiable(argmax_local)
-        return loss, argmax_local
-
-    @staticmethod
-    def backward(ctx, grad_loss, _grad_argmax):
-        x_local, inv_nx, xhat, xhat_t, what, inv_nw, lse, omp, dphi, label_local = ctx.saved_tensors
-        head = ctx.head
-        K, group = head.kernels, head.process_group
-        rank = dist.get_rank(group)
-        b_loc = x_local.shape[0]
-        g = grad_loss.to(torch.float32).contiguous()
-        dxhat_part, dw = K.backward(xhat, xhat_t, what, inv_nw, lse, omp, dphi, label_local, float(head.s),
-                                    1.0 / ctx.B, grad_loss_dev=g)
-        dx = None
-        if ctx.needs_input_grad[0]:
-            dxhat_loc = _reduce_scatter_rows(dxhat_part, group)
-            dx = K.normalize_bwd_x(x_local, inv_nx[rank * b_loc:(rank + 1) * b_loc].contiguous(), dxhat_loc)
-        return dx, (dw if ctx.needs_input_grad[1] else None), None, None
-
-
 class ShardedArcMarginProduct(nn.Module):
     """`ArcMarginProduct` with the class dimension sharded over `process_group`.
 
@@ -119,7 +55,7 @@ class ShardedArcMarginProduct(nn.Module):
     """
 
     def __init__(self, in_feature=128, out_feature=10575, s=64.0, m=0.40, easy_margin=False, *, in_features=None,
-                 out_features=None, process_group=None, kernels=None):
+                 out_features=None, process_group=None, kernels=None, use_cuda_graph=True):
         super().__init__()
         if in_features is not None:
             in_feature = in_features
@@ -128,6 +64,7 @@ class ShardedArcMarginProduct(nn.Module):
         if kernels is None:
             from . import ops as kernels  # the CUDA library; raises later if it was not built
         self.kernels = kernels
+        self.use_cuda_graph = use_cuda_graph
         self.process_group = process_group if process_group is not None else dist.group.WORLD
         self.world_size = dist.get_world_size(self.process_group)
         self.rank = dist.get_rank(self.process_group)
@@ -161,7 +98,9 @@ class ShardedArcMarginProduct(nn.Module):
     def loss(self, x, label):
         x = x.to(torch.float32).contiguous()
         label = label.reshape(-1).to(device=x.device, dtype=torch.int64).contiguous()
-        return ShardedArcFaceCE.apply(x, self.weight.contiguous(), label, self)
+        cfg = engine.StepConfig(float(self.s), float(self.m), bool(self.easy_margin), self.class_lo, self.out_feature)
+        w = self.weight if self.weight.is_contiguous() else self.weight.contiguous()
+        return engine.run_step(self, self.kernels, self.process_group, x, w, label, cfg, False)
 
     def forward(self, x, label):
         from .head import FusedLogits

@@ -1,0 +1,114 @@
+"""CUDA-graph replay of the head step (multimodalsimilar_b200/engine.py) against the eager kernel sequence:
+same kernels, so results must be bit-identical; plus the autograd corner cases of static buffers."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import arcface_numpy as onp
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def _head(w, s, m, graph):
+    import multimodalsimilar_b200 as mm
+
+    h = mm.ArcMarginProduct(w.shape[1], w.shape[0], s=s, m=m, use_cuda_graph=graph).to(dev())
+    with torch.no_grad():
+        h.weight.copy_(torch.from_numpy(w))
+    return h
+
+
+def _step(head, x, y, grad=1.0):
+    xt = torch.from_numpy(x).to(dev()).requires_grad_(True)
+    yt = torch.from_numpy(y).to(dev())
+    head.weight.grad = None
+    loss, pred = head.loss(xt, yt)
+    (loss * grad).backward()
+    return loss.detach().clone(), pred.clone(), xt.grad.clone(), head.weight.grad.clone()
+
+
+def _same(a, b, what):
+    """Same kernels either way: loss / argmax / dW bit-identical; dX is summed over class splits by fp32 TMA
+    reduce-adds whose order is not fixed, so it is reproducible only to rounding (also eager vs eager)."""
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), what
+    torch.testing.assert_close(a[2], b[2], rtol=1e-4, atol=1e-7, msg=what)
+    assert torch.equal(a[3], b[3]), what
+
+
+@pytest.mark.parametrize("B,D,C", [(64, 128, 3000), (96, 1024, 5000)])   # CTA-pair kernels / generic (D > 512) kernels
+def test_graph_replay_equals_eager(B, D, C):
+    from multimodalsimilar_b200 import engine
+
+    s, m = 64.0, 0.4
+    _, w, _ = onp.synthetic_inputs(B, D, C, seed=1, trained_like=False)
+    eager, graph = _head(w, s, m, False), _head(w, s, m, True)
+    for it in range(6):
+        x, _, y = onp.synthetic_inputs(B, D, C, seed=10 + it, trained_like=False)
+        g = 1.0 if it % 2 == 0 else 2.5
+        a = _step(eager, x, y, g)
+        b = _step(graph, x, y, g)
+        _same(a, b, "iteration %d" % it)
+    st = engine._PLANS[graph]
+    assert st["plan"] is not None and not st["failed"], "the graph was never captured"
+    assert engine._PLANS.get(eager) is None
+
+
+def test_graph_mode_gradient_accumulation_and_margin_update():
+    B, D, C, s, m = 32, 64, 1000, 64.0, 0.3
+    _, w, _ = onp.synthetic_inputs(B, D, C, seed=2, trained_like=False)
+    eager, graph = _head(w, s, m, False), _head(w, s, m, True)
+    batches = [onp.synthetic_inputs(B, D, C, seed=20 + i, trained_like=False) for i in range(5)]
+    for h in (eager, graph):
+        h.weight.grad = None
+        for x, _, y in batches:          # no zero_grad between steps: .grad accumulates
+            xt = torch.from_numpy(x).to(dev()).requires_grad_(True)
+            loss, _ = h.loss(xt, torch.from_numpy(y).to(dev()))
+            loss.backward()
+    torch.testing.assert_close(graph.weight.grad, eager.weight.grad, rtol=1e-6, atol=1e-7)
+    # a margin update changes the kernel arguments: the plan is re-captured, results keep matching
+    for h in (eager, graph):
+        h.update_m(0.04)
+    for it in range(4):
+        x, _, y = batches[it]
+        a = _step(eager, x, y)
+        b = _step(graph, x, y)
+        _same(a, b, "after update_m, iteration %d" % it)
+
+
+def test_graph_mode_rejects_stale_backward():
+    B, D, C = 16, 64, 500
+    x, w, y = onp.synthetic_inputs(B, D, C, seed=3, trained_like=False)
+    h = _head(w, 64.0, 0.4, True)
+    for _ in range(4):
+        _step(h, x, y)
+    xt = torch.from_numpy(x).to(dev()).requires_grad_(True)
+    yt = torch.from_numpy(y).to(dev())
+    l1, _ = h.loss(xt, yt)
+    l2, _ = h.loss(xt, yt)
+    l2.backward()
+    with pytest.raises(RuntimeError, match="use_cuda_graph"):
+        l1.backward()
+
+
+def test_graph_mode_no_grad_and_pickle():
+    import io
+
+    B, D, C = 16, 64, 500
+    x, w, y = onp.synthetic_inputs(B, D, C, seed=4, trained_like=False)
+    h = _head(w, 64.0, 0.4, True)
+    e = _head(w, 64.0, 0.4, False)
+    xt, yt = torch.from_numpy(x).to(dev()), torch.from_numpy(y).to(dev())
+    with torch.no_grad():
+        ref = e.loss(xt, yt)
+        for _ in range(5):
+            got = h.loss(xt, yt)
+    assert torch.equal(ref[0], got[0]) and torch.equal(ref[1], got[1])
+    buf = io.BytesIO()
+    torch.save(h, buf)      # the reference checkpoints whole modules (cv_classifier_train_daodian.py:298-306)
+    buf.seek(0)
+    h2 = torch.load(buf, weights_only=False)
+    assert torch.equal(h2.weight, h.weight)
