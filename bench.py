@@ -246,7 +246,7 @@ def main():
     clocks = sampler.result()
     ms_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
     value = B / (ms_step * 1e-3)
-    loss_value = float(loss)
+    loss_value = float(loss.detach())
 
     # ---- kernel launches per step (our kernels only; memset / NCCL not counted)
     _, n_chunks = ops.backward_plan(B, D, c_hi - c_lo)
@@ -352,7 +352,16 @@ def main():
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Captured graphs hold NCCL kernels: release them before the communicator goes away, and leave without
+        # running destructors (destroy_process_group() with live graphs was seen to hang after the line was printed).
+        from multimodalsimilar_b200 import engine
+
+        engine.drop_plan(head)
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def stage_times(torch, ops, head, x_host, y_host, dev, s, m, c_lo, c_total, iters):

@@ -157,6 +157,12 @@ int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* xhat_t, int6
 int32_t arcface_b200_normalize_bwd_x(const float* x, const float* inv_nx, const float* dxhat, int32_t B,
                                      int32_t D, float* dx, void* stream);
 
+/* In-place a[0..na) *= *scale_dev, b[0..nb) *= *scale_dev (na, nb multiples of 4; either may be 0).  Used when the
+ * backward was run ahead of time with an upstream gradient of 1 (CUDA-graph replay of forward + backward in one
+ * launch): the gradients are linear in the upstream gradient of the scalar loss, so loss.backward() only has to
+ * apply it.  When *scale_dev == 1.0f -- loss.backward() on the head's own loss -- the kernel returns immediately. */
+int32_t arcface_b200_scale_grads(float* a, int64_t na, float* b, int64_t nb, const float* scale_dev, void* stream);
+
 /* One-call step for hosts without torch: HOST embeddings / labels in, HOST loss / argmax / dx out; the
  * class weights and their gradient stay resident on the device (w, dw are DEVICE pointers, fp32 [C x D]).
  * Copies in and out are part of the call; it returns after the results have landed in the host buffers.

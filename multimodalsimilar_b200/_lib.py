@@ -57,6 +57,7 @@ SIGNATURES = {
          c_int64, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
     ),
     "arcface_b200_normalize_bwd_x": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "arcface_b200_scale_grads": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "arcface_b200_step_workspace_bytes": (c_int32, [c_int32, c_int32, c_int64, POINTER(c_size_t)]),
     "arcface_b200_step_host": (
         c_int32,

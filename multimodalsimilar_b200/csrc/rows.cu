@@ -285,9 +285,40 @@ normalize_bwd_x_kernel(const float* __restrict__ x, const float* __restrict__ in
     }
 }
 
+// a[i] *= *g, b[i] *= *g; every thread reads the scalar and the whole grid leaves at once when it is exactly 1
+// (the common case: loss.backward() on the head's own loss), so the call then costs one empty launch.
+__global__ void __launch_bounds__(256)
+scale_grads_kernel(float* __restrict__ a, int64_t na4, float* __restrict__ b, int64_t nb4, const float* __restrict__ g) {
+    const float f = *g;
+    if (f == 1.0f) return;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < na4 + nb4; i += stride) {
+        float4* p = i < na4 ? reinterpret_cast<float4*>(a) + i : reinterpret_cast<float4*>(b) + (i - na4);
+        float4 v = *p;
+        v.x *= f; v.y *= f; v.z *= f; v.w *= f;
+        *p = v;
+    }
+}
+
 }  // namespace ab
 
 using namespace ab;
+
+extern "C" int32_t arcface_b200_scale_grads(float* a, int64_t na, float* b, int64_t nb, const float* scale_dev,
+                                            void* stream) {
+    if (int32_t rc = check_arch()) return rc;
+    AB_REQUIRE(scale_dev && (a || na == 0) && (b || nb == 0), ARCFACE_B200_E_ARG, "scale_grads: null pointer");
+    AB_REQUIRE(na >= 0 && nb >= 0 && na % 4 == 0 && nb % 4 == 0, ARCFACE_B200_E_SHAPE,
+               "scale_grads: element counts must be non-negative multiples of 4");
+    AB_REQUIRE(aligned16(a) && aligned16(b), ARCFACE_B200_E_LAYOUT, "scale_grads: pointers must be 16-byte aligned");
+    if (na + nb == 0) return ARCFACE_B200_OK;
+    const int64_t n4 = (na + nb) / 4;
+    const int64_t want = (n4 + 255) / 256;
+    const int grid = static_cast<int>(want < 8 * 148 ? want : 8 * 148);
+    scale_grads_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, na / 4, b, nb / 4, scale_dev);
+    AB_CHECK_CUDA(cudaGetLastError());
+    return ARCFACE_B200_OK;
+}
 
 extern "C" int32_t arcface_b200_normalize_cast(const float* src, int64_t rows, int32_t D, uint16_t* dst,
                                                float* inv_norm, uint16_t* dst_t, int64_t ld_t, void* stream) {

@@ -6,10 +6,10 @@ and `ShardedArcMarginProduct` (class shard per rank, three NCCL collectives per 
 embeddings + labels, all-gather of the packed per-row statistics, reduce-scatter of the embedding gradient;
 reference counterpart: nn.DataParallel at nlp_classifier_train_daodian_v2_dist.py:85).
 
-Why graphs: at 8 GPUs one rank's kernels for the north-star shape take ~0.4 ms, less than the host needs to
+Why graphs: at 8 GPUs one rank's kernels for the north-star shape take ~0.35 ms, less than the host needs to
 issue ~60 small torch / ctypes calls, so the eager step is host-bound (0.84 ms measured).  `GraphedStep` captures
-the forward (kernels + collectives) and the backward once per signature -- every buffer, including `what`, the
-softmax statistics and dW, lives in the graph's private pool -- and replays them: two launches per step.
+forward + backward (kernels and collectives) once per signature -- every buffer, including `what`, the softmax
+statistics and dW, lives in the graph's private pool -- and replays it: one launch per step.
 The captured kernels are the same C-ABI calls the eager path makes (`ops`), on the capture stream.
 """
 from __future__ import annotations
@@ -145,7 +145,14 @@ def backward_eager(K, group, x_local, st: FwdState, grad_loss, cfg: StepConfig, 
 
 # ----------------------------------------------------------------------------------------- CUDA graphs
 class GraphedStep:
-    """Forward and backward of one signature captured as two CUDA graphs over static buffers."""
+    """One signature of the step captured as ONE CUDA graph over static buffers.
+
+    with_backward: the graph holds forward AND backward, the backward run ahead of time with an upstream
+    gradient of 1.  The gradients of a scalar loss are linear in its upstream gradient, so `loss.backward()` only
+    has to apply that factor (`ops.scale_grads`, which returns immediately when it is exactly 1 -- the
+    reference's `loss.backward()` on the head's own loss) and hand the buffers to autograd: one graph launch and
+    one near-empty kernel per training step.  Without gradients (torch.no_grad) the graph holds the forward only.
+    """
 
     WARMUP = 2
 
@@ -153,52 +160,46 @@ class GraphedStep:
         dev = w.device
         D = w.shape[1]
         self.K, self.group, self.cfg = K, group, cfg
-        self.w_ptr = w.data_ptr()
         self.x = torch.zeros((b_loc, D), dtype=torch.float32, device=dev)
         self.y = torch.zeros((b_loc,), dtype=torch.int64, device=dev)
-        self.g = torch.ones((), dtype=torch.float32, device=dev)
+        self.one = torch.ones((), dtype=torch.float32, device=dev)
         self.version = 0
         self.with_backward = with_backward
-        # labels of the warm-up / capture runs must be valid class ids on every rank
-        self.y.fill_(cfg.class_lo)
+        self.y.fill_(cfg.class_lo)  # labels of the warm-up / capture runs must be valid class ids
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(self.WARMUP):  # lazy initialisation (NCCL communicators, kernel attributes) outside capture
                 st = forward_eager(K, group, self.x, w, self.y, cfg)
                 if with_backward:
-                    backward_eager(K, group, self.x, st, self.g, cfg)
+                    backward_eager(K, group, self.x, st, self.one, cfg)
             del st
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        self.fwd_graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.fwd_graph):
-            self.st = forward_eager(K, group, self.x, w, self.y, cfg)
-        self.bwd_graph = None
+        self.graph = torch.cuda.CUDAGraph()
         self.dx = self.dw = None
-        if with_backward:
-            self.bwd_graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.bwd_graph, pool=self.fwd_graph.pool()):
-                self.dx, self.dw = backward_eager(K, group, self.x, self.st, self.g, cfg)
+        with torch.cuda.graph(self.graph):
+            self.st = forward_eager(K, group, self.x, w, self.y, cfg)
+            if with_backward:
+                self.dx, self.dw = backward_eager(K, group, self.x, self.st, self.one, cfg)
 
-    def forward(self, x_local, y_local):
+    def run(self, x_local, y_local, param=None):
+        if self.with_backward and param is not None and param.grad is not None and \
+                param.grad.untyped_storage().data_ptr() == self.dw.untyped_storage().data_ptr():
+            # the caller accumulates gradients and .grad still aliases the buffer this replay overwrites
+            param.grad = param.grad.clone()
         self.x.copy_(x_local)
         self.y.copy_(y_local)
-        self.fwd_graph.replay()
+        self.graph.replay()
         self.version += 1
         return self.version
-
-    def backward(self, grad_loss):
-        self.g.copy_(grad_loss.reshape(()))
-        self.bwd_graph.replay()
 
 
 class _GraphedCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, label, plan: GraphedStep, weight_ref):
-        ctx.version = plan.forward(x, label)
+    def forward(ctx, x, w, label, plan: GraphedStep, param_ref):
+        ctx.version = plan.run(x, label, param_ref() if param_ref is not None else None)
         ctx.plan = plan
-        ctx.weight_ref = weight_ref
         loss = plan.st.loss.clone()
         argmax = plan.st.argmax_local.clone()
         ctx.mark_non_differentiable(argmax)
@@ -211,14 +212,12 @@ class _GraphedCE(torch.autograd.Function):
             raise RuntimeError("ArcMarginProduct (CUDA-graph mode): backward() of a forward whose buffers were reused "
                                "by a later forward of the same head; set head.use_cuda_graph = False to keep several "
                                "forwards in flight")
-        param = ctx.weight_ref() if ctx.weight_ref is not None else None
-        if param is not None and param.grad is not None and \
-                param.grad.untyped_storage().data_ptr() == plan.dw.untyped_storage().data_ptr():
-            # the caller accumulates gradients and .grad still aliases the buffer this replay overwrites
-            param.grad = param.grad.clone()
-        plan.backward(grad_loss)
-        dx = plan.dx.clone() if ctx.needs_input_grad[0] else None
-        dw = plan.dw.detach() if ctx.needs_input_grad[1] else None  # alias: autograd adopts it without a copy
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        g = grad_loss.to(torch.float32).reshape(1).contiguous()
+        plan.K.scale_grads(plan.dx if need_dx else None, plan.dw if need_dw else None, g)
+        dx = plan.dx.clone() if need_dx else None
+        dw = plan.dw.detach() if need_dw else None  # alias: autograd adopts it without a copy
+        ctx.version = -1  # the factor has been applied in place: a second backward would apply it twice
         return dx, dw, None, None, None
 
 
@@ -273,12 +272,11 @@ def run_step(head, K, group, x, w, label, cfg: StepConfig, validate_labels: bool
             warnings.warn("multimodalsimilar_b200: CUDA-graph capture failed (%r); continuing with eager launches" % (e,))
             return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels)
     plan: GraphedStep = state["plan"]
-    param = getattr(head, "weight", None)
-    ref = weakref.ref(param) if isinstance(param, torch.nn.Parameter) else None
     if not with_bwd:
-        plan.forward(x, label)
+        plan.run(x, label)
         return plan.st.loss.clone(), plan.st.argmax_local.clone()
-    return _GraphedCE.apply(x, w, label, plan, ref)
+    param = getattr(head, "weight", None)
+    return _GraphedCE.apply(x, w, label, plan, weakref.ref(param) if isinstance(param, torch.nn.Parameter) else None)
 
 
 def drop_plan(head) -> None:

@@ -228,6 +228,14 @@ def normalize_bwd_x(x, inv_nx, dxhat) -> torch.Tensor:
     return dx
 
 
+def scale_grads(a, b, scale_dev) -> None:
+    """In-place a *= scale, b *= scale (fp32 tensors or None; scale = DEVICE scalar); free when scale == 1."""
+    na = 0 if a is None else _req(a, torch.float32, "a").numel()
+    nb = 0 if b is None else _req(b, torch.float32, "b").numel()
+    _lib.call("arcface_b200_scale_grads", _ptr(a), na, _ptr(b), nb, _ptr(_req(scale_dev, torch.float32, "scale")),
+              _stream())
+
+
 def step_workspace_bytes(B: int, D: int, C: int) -> int:
     n = ctypes.c_size_t(0)
     _lib.call("arcface_b200_step_workspace_bytes", B, D, C, ctypes.byref(n))

@@ -31,12 +31,18 @@ def _step(head, x, y, grad=1.0):
     return loss.detach().clone(), pred.clone(), xt.grad.clone(), head.weight.grad.clone()
 
 
-def _same(a, b, what):
+def _same(a, b, what, grad=1.0):
     """Same kernels either way: loss / argmax / dW bit-identical; dX is summed over class splits by fp32 TMA
-    reduce-adds whose order is not fixed, so it is reproducible only to rounding (also eager vs eager)."""
+    reduce-adds whose order is not fixed, so it is reproducible only to rounding (also eager vs eager).
+    With an upstream gradient != 1 the eager path rounds dC = bf16(grad * ...) while the graph path runs the
+    backward with 1 and scales the fp32 result: equal up to one bf16 rounding of dC."""
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), what
-    torch.testing.assert_close(a[2], b[2], rtol=1e-4, atol=1e-7, msg=what)
-    assert torch.equal(a[3], b[3]), what
+    if grad == 1.0:
+        torch.testing.assert_close(a[2], b[2], rtol=1e-4, atol=1e-7, msg=what)
+        assert torch.equal(a[3], b[3]), what
+    else:
+        for u, v in ((a[2], b[2]), (a[3], b[3])):
+            assert float((u - v).norm() / v.norm()) <= 6e-3, what
 
 
 @pytest.mark.parametrize("B,D,C", [(64, 128, 3000), (96, 1024, 5000)])   # CTA-pair kernels / generic (D > 512) kernels
@@ -51,7 +57,7 @@ def test_graph_replay_equals_eager(B, D, C):
         g = 1.0 if it % 2 == 0 else 2.5
         a = _step(eager, x, y, g)
         b = _step(graph, x, y, g)
-        _same(a, b, "iteration %d" % it)
+        _same(a, b, "iteration %d" % it, g)
     st = engine._PLANS[graph]
     assert st["plan"] is not None and not st["failed"], "the graph was never captured"
     assert engine._PLANS.get(eager) is None
