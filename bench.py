@@ -32,6 +32,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOAD = {"B": 512, "D": 512, "C": 1000000, "s": 64.0, "m": 0.5}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of this workload on one
+# B200 (profiles/r1_v9_fwd_bwd_full_raw.csv); only meaningful for the single-GPU north-star shape.
+NCU_TRAFFIC_BYTES = {"fwd": 2.543024e9 + 0.999243e9, "k3": 1.399593e9 + 2.114164e9}
 METRIC = "arcface_head_fwd_bwd_samples_per_sec_1M_classes"
 
 
@@ -58,6 +61,7 @@ class ClockSampler(threading.Thread):
         self.index = index
         self.stop_flag = threading.Event()
         self.sm = []
+        self.power = []
         self.mask = 0
         self.max_mhz = None
         self.error = None
@@ -79,6 +83,10 @@ class ClockSampler(threading.Thread):
             while not self.stop_flag.is_set():
                 self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
                 try:
+                    self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                except Exception:
+                    pass
+                try:
                     self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
                 except Exception:
                     pass
@@ -92,8 +100,11 @@ class ClockSampler(threading.Thread):
         if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "error": self.error or "no samples"}
         s = sorted(self.sm)
-        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "samples": len(s),
-                "reasons": [n for b, n in self.REASONS.items() if self.mask & b]}
+        out = {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "samples": len(s),
+               "reasons": [n for b, n in self.REASONS.items() if self.mask & b]}
+        if self.power:
+            out["power_w_max"] = max(self.power)
+        return out
 
 
 def run_reference(args):
@@ -251,7 +262,8 @@ def main():
     # ---- kernel launches per step (our kernels only; memset / NCCL not counted)
     _, n_chunks = ops.backward_plan(B, D, c_hi - c_lo)
     k3_launches = ops.backward_launches(B, D, c_hi - c_lo)
-    launches_per_step = 1 + 1 + 1 + 1 + 1 + k3_launches + 1  # K1(x), label, K1(w)+K2, combine, finalize, K3, bwd-x
+    # K1(x), label, K1(w)+K2, combine, finalize, K3, bwd-x, scale_grads -- replayed from one CUDA graph per step
+    launches_per_step = 1 + 1 + 1 + 1 + 1 + k3_launches + 1 + 1
     gpu_launches = launches_per_step * args.steps
 
     # ---- end-to-end with host buffers
@@ -329,7 +341,9 @@ def main():
     bnd, work, unit, peak, name = cand[top]
     achieved = work / (stages[top] * 1e-3)
     roofline = {"kernel": name, "bound": bnd, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
-                "traffic": None, "ms_per_launch_group": stages[top], "share_of_step": stages[top] / comp_ms,
+                "traffic": NCU_TRAFFIC_BYTES[top] if (world == 1 and not args.classes) else None,
+                "traffic_source": "profiles/r1_v9_fwd_bwd_full_raw.csv (ncu --set full, per launch)",
+                "ms_per_launch_group": stages[top], "share_of_step": stages[top] / comp_ms,
                 "peak_source": peaks["source"]}
 
     cpu_baseline = None

@@ -164,6 +164,18 @@ struct PairDefaults {
     __device__ static int stream_row(const Prm& p, int i) { return p.core.s_row0 + i * 2 * ROWS; }
 };
 
+// Registers per thread a kernel of `threads` threads is launched with under __launch_bounds__(threads, 1).
+__host__ __device__ constexpr int launch_regs(int threads) {
+    int r = 65536 / threads;
+    r = r > 255 ? 255 : r;
+    return r / 8 * 8;
+}
+template <int N, int LAUNCH>
+__device__ __forceinline__ void setmaxnreg_to() {
+    if constexpr (N > LAUNCH) setmaxnreg_inc<N>();
+    else if constexpr (N < LAUNCH) setmaxnreg_dec<N>();
+}
+
 // The body of a pair kernel: `pair` of `npairs` (consecutive CTA pairs of one launch that share the policy),
 // `smem` 1024-aligned dynamic shared memory carved identically in both CTAs.
 template <class P>
@@ -238,8 +250,9 @@ __device__ __forceinline__ void pair_gemm_body(const CUtensorMap& tmS, const CUt
     // setmaxnreg is executed by whole warpgroups -- warps 0-3, 4-11, 12-... -- at the top of the branch that holds
     // the role's code, so that ptxas allocates each role against its own limit; the pool is what the CTA was
     // launched with, threads x registers, not the whole register file).
+    constexpr int LAUNCH_REGS = launch_regs(THREADS + P::AUX_WARPS * 32);
     if (warp < 4) {
-    if constexpr (P::AUX_REGS > 0) setmaxnreg_dec<P::LOW_REGS>();
+    if constexpr (P::AUX_REGS > 0) setmaxnreg_to<P::LOW_REGS, LAUNCH_REGS>();
     if (warp == 0) {
         // ---------------- TMA producer (both CTAs): whole warp walks the schedule, one elected lane issues
         const uint32_t res_bar_leader = mapa_u32(smem_u32(res_bar), 0);
@@ -326,7 +339,7 @@ __device__ __forceinline__ void pair_gemm_body(const CUtensorMap& tmS, const CUt
     }
     } else if (warp < 4 + EPI_WARPS) {
         // ---------------- epilogue (both CTAs)
-        if constexpr (P::AUX_REGS > 0) setmaxnreg_dec<P::EPI_REGS>();
+        if constexpr (P::AUX_REGS > 0) setmaxnreg_to<P::EPI_REGS, LAUNCH_REGS>();
         EpiCtx ctx;
         ctx.extra = sExtra;
         ctx.staging = smem_u32(sStaging) + (warp - 4) * STAGING_PER_WARP;
@@ -368,7 +381,7 @@ __device__ __forceinline__ void pair_gemm_body(const CUtensorMap& tmS, const CUt
             prof[7] = n_tiles;
         }
     } else if constexpr (P::AUX_WARPS > 0) {
-        if constexpr (P::AUX_REGS > 0) setmaxnreg_inc<P::AUX_REGS>();
+        if constexpr (P::AUX_REGS > 0) setmaxnreg_to<P::AUX_REGS, LAUNCH_REGS>();
         P::aux(prm, (pair * 2 + rank) * P::AUX_WARPS + (warp - 4 - EPI_WARPS), npairs * 2 * P::AUX_WARPS, lane);
     }
 

@@ -12,6 +12,7 @@
 #include "gemm_pair.cuh"
 
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -161,15 +162,22 @@ __device__ __forceinline__ float4 ldg_stream4(const float* p) {
     return r;
 }
 
+#ifndef AB_FWD_AUX_WARPS
+#define AB_FWD_AUX_WARPS 8
+#endif
 template <bool NORM>
 struct FwdStatsPairT : pr::PairDefaults {
     static constexpr int STAGES = 4;
     static constexpr bool STAGING = false;
     static constexpr bool RES_A = true;
     static constexpr int NROW = 2 * pr::ROWS;
-    static constexpr int AUX_WARPS = NORM ? 8 : 0;
-    // setmaxnreg register reallocation between the roles (gemm_pair.cuh): off (0) -- see aux() below
-    static constexpr int LOW_REGS = 0, EPI_REGS = 0, AUX_REGS = 0;
+    static constexpr int AUX_WARPS = NORM ? AB_FWD_AUX_WARPS : 0;
+    // 16 helper warps: the CTA is launched with 72 registers per thread (896 threads) and the roles trade
+    // registers with setmaxnreg (gemm_pair.cuh): producer / MMA / allocator warps 40, epilogue 96, helpers 64.
+    // The helper loop is latency-bound per warp (global load -> shuffle reduction -> sqrt -> convert -> store), so
+    // what raises its throughput is MORE warps each holding one row pair, not a deeper pipeline per warp.
+    static constexpr bool WIDE = NORM && AB_FWD_AUX_WARPS == 16;
+    static constexpr int LOW_REGS = WIDE ? 40 : 0, EPI_REGS = WIDE ? 96 : 0, AUX_REGS = WIDE ? 64 : 0;
     static constexpr int RUN = 32;  // consecutive rows a helper warp normalises between two counter updates
 
     struct Params {
@@ -188,6 +196,7 @@ struct FwdStatsPairT : pr::PairDefaults {
         float* inv_nw;           // out: 1 / max(||w||, 1e-12)
         int* ready;              // [ceil(C / 128)] rows published per 128-row block (zeroed before the launch)
         int debug;               // measurements only: 1 = the GEMM does not wait for the helper warps
+        int pf_dist;             // helper warps prefetch their row pair j + pf_dist into L2 (0 = off)
     };
 
     __device__ static void prologue(const Params&, uint8_t*, int, int, int) {}
@@ -295,12 +304,38 @@ struct FwdStatsPairT : pr::PairDefaults {
                     }
                 }
             };
+            // DRAM -> L2 prefetch of the pair `pf_dist` ahead: the bytes in flight beyond the two register pairs
+            // live in L2, so the loads below see L2 latency instead of queued-DRAM latency
+            const int pfd = p.pf_dist;
+            const uint32_t pair_bytes = static_cast<uint32_t>(2 * p.D * sizeof(float));
+            auto ahead = [&](int64_t j) {
+                if (pfd > 0 && lane == 0 && j + pfd < n_pairs) {
+                    const int64_t r = row_of(j + pfd);
+                    if (r + 2 <= p.C) bulk_prefetch_l2(p.w + r * p.D, pair_bytes);
+                }
+            };
+            if (pfd > 0 && lane == 0)
+                for (int64_t j = 2; j < pfd && j < n_pairs; ++j) {
+                    const int64_t r = row_of(j);
+                    if (r + 2 <= p.C) bulk_prefetch_l2(p.w + r * p.D, pair_bytes);
+                }
+            if constexpr (WIDE) {
+                RowPair a;
+                for (int64_t j = 0; j < n_pairs; ++j) {
+                    fetch(j, a);
+                    ahead(j);
+                    retire(j, a);
+                }
+                return;
+            }
             RowPair a, b;
             fetch(0, a);
             for (int64_t j = 0; j < n_pairs; j += 2) {
                 fetch(j + 1, b);
+                ahead(j);
                 retire(j, a);
                 fetch(j + 2, a);
+                ahead(j + 1);
                 retire(j + 1, b);
             }
         }
@@ -528,10 +563,39 @@ static int32_t launch_fwd_pairs(const uint16_t* xhat, const uint16_t* what, cons
     p.debug = 0;
     if (const char* dbg = getenv("ARCFACE_B200_FWD_DEBUG")) p.debug = atoi(dbg);
     if (p.debug == 2) p.core.s_blocks = 0;  // measurements only: helper warps alone
+    p.pf_dist = 0;
+    if (const char* pf = getenv("ARCFACE_B200_FWD_PF")) p.pf_dist = atoi(pf);
     CUtensorMap tmS, tmR;
     if (int32_t rc = make_tmap_kmajor(&tmS, what, D, C_local, D, pr::ROWS)) return rc;
     if (int32_t rc = make_tmap_kmajor(&tmR, xhat, D, B, D, pr::ROWS)) return rc;
-    return pr::launch_pair<P>(tmS, tmR, tmS, p, groups, 0, st);
+    // measurements only (ARCFACE_B200_FWD_PROF=1): where each role waits; synchronises and prints to stderr
+    static unsigned long long* prof_dev = nullptr;
+    const char* pe = getenv("ARCFACE_B200_FWD_PROF");
+    const bool prof = pe != nullptr && atoi(pe) == 1;
+    const int n_cta = 2 * groups * p.core.n_res;
+    if (prof) {
+        if (prof_dev == nullptr) AB_CHECK_CUDA(cudaMalloc(&prof_dev, 512 * 16 * sizeof(unsigned long long)));
+        AB_CHECK_CUDA(cudaMemsetAsync(prof_dev, 0, 512 * 16 * sizeof(unsigned long long), st));
+        p.core.prof = prof_dev;
+        p.core.prof_cta = 0;
+    }
+    const int32_t rc = pr::launch_pair<P>(tmS, tmR, tmS, p, groups, 0, st);
+    if (prof && rc == ARCFACE_B200_OK) {
+        static unsigned long long host[512 * 16];
+        AB_CHECK_CUDA(cudaStreamSynchronize(st));
+        AB_CHECK_CUDA(cudaMemcpy(host, prof_dev, sizeof(host), cudaMemcpyDeviceToHost));
+        double a[8] = {0};
+        int n = 0;
+        for (int c = 0; c < n_cta && c < 512; ++c) {
+            for (int k = 0; k < 8; ++k) a[k] += static_cast<double>(host[c * 16 + k]);
+            ++n;
+        }
+        // [2], [3] exist in leader CTAs only (n / 2 of them)
+        fprintf(stderr, "[fwd prof] ctas=%d tiles/cta=%.1f body=%.0f cyc | producer: helper rows %.0f, free stage %.0f | "
+                        "MMA: operands %.0f, free accumulator %.0f | epilogue: accumulator %.0f, inside tile %.0f\n",
+                n, a[7] / n, a[6] / n, a[0] / n, a[1] / n, a[2] / (n / 2), a[3] / (n / 2), a[4] / n, a[5] / n);
+    }
+    return rc;
 }
 
 extern "C" int32_t arcface_b200_forward_parts(int32_t B, int32_t D, int64_t C_local, int32_t* n_parts) {
