@@ -119,6 +119,16 @@ int32_t arcface_b200_finalize_rows(const float* rows_max, const float* rows_sum,
                                    float* lse, int64_t* argmax, float* z_label_out, float* one_minus_p,
                                    float* loss, void* stream);
 
+/* The same with the per-rank rows at a stride: rank r's values start rank_stride_f32 floats (rows_max, rows_sum,
+ * rows_z_label) / rank_stride_i64 int64s (rows_arg) after rank r - 1's.  Lets the class-sharded head all-gather ONE
+ * packed buffer per rank ([arg int64 x B | max | sum | z_label fp32 x B]: strides 5 B floats and 5 B / 2 int64s, B even)
+ * and merge it in place, without unpacking kernels. */
+int32_t arcface_b200_finalize_rows_strided(const float* rows_max, const float* rows_sum, const int64_t* rows_arg,
+                                           const float* rows_z_label, const int64_t* label, int32_t n_ranks, int32_t B,
+                                           int64_t rank_stride_f32, int64_t rank_stride_i64, float* lse,
+                                           int64_t* argmax, float* z_label_out, float* one_minus_p, float* loss,
+                                           void* stream);
+
 /* Materialise out[b, c] = scale * cos[b, c] (label column overridden by z_label when given).  Eval path
  * (forward_test, scale = 1) and the debug / small-C path behind the lazy logits object. */
 int32_t arcface_b200_logits(const uint16_t* xhat, const uint16_t* what, const float* z_label,

@@ -46,6 +46,9 @@ SIGNATURES = {
     "arcface_b200_finalize_rows": (
         c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                   c_void_p, c_void_p, c_void_p]),
+    "arcface_b200_finalize_rows_strided": (
+        c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64, c_int64, c_void_p,
+                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "arcface_b200_logits": (
         c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64, c_float, c_void_p, c_int64, c_void_p]),
     "arcface_b200_backward_workspace_bytes": (c_int32, [c_int32, c_int32, c_int64, POINTER(c_size_t)]),

@@ -208,7 +208,7 @@ combine_partials_kernel(const float* __restrict__ pm, const float* __restrict__ 
 __global__ void __launch_bounds__(256)
 finalize_rows_kernel(const float* __restrict__ rm, const float* __restrict__ rs, const int64_t* __restrict__ ra,
                      const float* __restrict__ rz, const int64_t* __restrict__ label, int n_ranks, int B,
-                     float* __restrict__ lse, int64_t* __restrict__ argmax, float* __restrict__ z_out,
+                     int64_t fstride, int64_t astride, float* __restrict__ lse, int64_t* __restrict__ argmax, float* __restrict__ z_out,
                      float* __restrict__ one_minus_p, float* __restrict__ loss) {
     __shared__ float red[256];
     float acc = 0.f;
@@ -216,16 +216,16 @@ finalize_rows_kernel(const float* __restrict__ rm, const float* __restrict__ rs,
         float Mx = -INFINITY, Sx = 0.f, Z = 0.f;
         int64_t Ax = 0;
         for (int r = 0; r < n_ranks; ++r) {
-            const float m = rm[static_cast<int64_t>(r) * B + b];
-            const float s = rs[static_cast<int64_t>(r) * B + b];
+            const float m = rm[r * fstride + b];
+            const float s = rs[r * fstride + b];
             if (m > Mx) {  // strict: the lower rank (lower class range) keeps ties
                 Sx = Sx * expf(Mx - m) + s;
                 Mx = m;
-                Ax = ra[static_cast<int64_t>(r) * B + b];
+                Ax = ra[r * astride + b];
             } else if (m > -INFINITY) {
                 Sx += s * expf(m - Mx);
             }
-            Z += rz[static_cast<int64_t>(r) * B + b];
+            Z += rz[r * fstride + b];
         }
         const int64_t y = label[b];
         float l, omp, ce;
@@ -379,20 +379,32 @@ extern "C" int32_t arcface_b200_combine_partials(const float* part_max, const fl
     return ARCFACE_B200_OK;
 }
 
-extern "C" int32_t arcface_b200_finalize_rows(const float* rows_max, const float* rows_sum, const int64_t* rows_arg,
-                                              const float* rows_z_label, const int64_t* label, int32_t n_ranks,
-                                              int32_t B, float* lse, int64_t* argmax, float* z_label_out,
-                                              float* one_minus_p, float* loss, void* stream) {
+extern "C" int32_t arcface_b200_finalize_rows_strided(const float* rows_max, const float* rows_sum,
+                                                      const int64_t* rows_arg, const float* rows_z_label,
+                                                      const int64_t* label, int32_t n_ranks, int32_t B,
+                                                      int64_t rank_stride_f32, int64_t rank_stride_i64, float* lse,
+                                                      int64_t* argmax, float* z_label_out, float* one_minus_p,
+                                                      float* loss, void* stream) {
     if (int32_t rc = check_arch()) return rc;
     AB_REQUIRE(rows_max && rows_sum && rows_arg && rows_z_label && label && lse && argmax && z_label_out &&
                    one_minus_p && loss,
                ARCFACE_B200_E_ARG, "finalize_rows: null pointer");
     AB_REQUIRE(n_ranks >= 1 && B >= 1, ARCFACE_B200_E_SHAPE, "finalize_rows: bad shape");
+    AB_REQUIRE(rank_stride_f32 >= B && rank_stride_i64 >= B, ARCFACE_B200_E_LAYOUT, "finalize_rows: rank stride < B");
     finalize_rows_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(rows_max, rows_sum, rows_arg, rows_z_label,
-                                                                          label, n_ranks, B, lse, argmax, z_label_out,
+                                                                          label, n_ranks, B, rank_stride_f32,
+                                                                          rank_stride_i64, lse, argmax, z_label_out,
                                                                           one_minus_p, loss);
     AB_CHECK_CUDA(cudaGetLastError());
     return ARCFACE_B200_OK;
+}
+
+extern "C" int32_t arcface_b200_finalize_rows(const float* rows_max, const float* rows_sum, const int64_t* rows_arg,
+                                              const float* rows_z_label, const int64_t* label, int32_t n_ranks,
+                                              int32_t B, float* lse, int64_t* argmax, float* z_label_out,
+                                              float* one_minus_p, float* loss, void* stream) {
+    return arcface_b200_finalize_rows_strided(rows_max, rows_sum, rows_arg, rows_z_label, label, n_ranks, B, B, B, lse,
+                                              argmax, z_label_out, one_minus_p, loss, stream);
 }
 
 extern "C" int32_t arcface_b200_normalize_bwd_x(const float* x, const float* inv_nx, const float* dxhat, int32_t B,

@@ -65,15 +65,17 @@ def _all_gather_bytes(buf: torch.Tensor, group) -> torch.Tensor:
     return out.view(_world(group), buf.numel())
 
 
-def gather_batch(x_local: torch.Tensor, y_local: torch.Tensor, group):
+def gather_batch(x_local: torch.Tensor, y_local: torch.Tensor, group, packed=None):
     """All ranks' embeddings [B, D] fp32 and labels [B] int64 in rank order: ONE collective over the
-    byte-packed (x | labels) of every rank."""
+    byte-packed (x | labels) of every rank.  `packed`: the caller already holds x_local / y_local as views of one
+    uint8 buffer laid out that way (the graph's static input), so nothing has to be concatenated."""
     R = _world(group)
     if R == 1:
         return x_local, y_local
     b, D = x_local.shape
     xb = b * D * 4
-    packed = torch.cat([x_local.reshape(-1).view(torch.uint8), y_local.view(torch.uint8)])
+    if packed is None:
+        packed = torch.cat([x_local.reshape(-1).view(torch.uint8), y_local.view(torch.uint8)])
     allp = _all_gather_bytes(packed, group)
     x_all = allp[:, :xb].contiguous().view(torch.float32).reshape(R * b, D)
     y_all = allp[:, xb:].contiguous().view(torch.int64).reshape(R * b)
@@ -110,18 +112,27 @@ def reduce_scatter_rows(full: torch.Tensor, group) -> torch.Tensor:
     return out
 
 
-def forward_eager(K, group, x_local, w, y_local, cfg: StepConfig) -> FwdState:
+def forward_eager(K, group, x_local, w, y_local, cfg: StepConfig, packed_xy=None) -> FwdState:
     """K1 (x) -> label margin -> K1 (w) + K2 -> combine -> [exchange] -> finalize.  arcface.py:45-63 + the mean
     CrossEntropyLoss + argmax of the call sites, for the global batch against the local class rows."""
     R, rank = _world(group), _rank(group)
     b_loc = x_local.shape[0]
-    x_all, y_all = gather_batch(x_local, y_local, group)
+    x_all, y_all = gather_batch(x_local, y_local, group, packed_xy)
     B = x_all.shape[0]
     xhat, inv_nx, xhat_t = K.normalize_cast(x_all, want_transpose=True)
-    lm = K.label_margin(x_all, w, inv_nx, None, y_all, cfg.class_lo, cfg.c_total, cfg.s, cfg.m, cfg.easy_margin)
-    what, inv_nw, rmax, rsum, rarg = K.forward_rows_fused(xhat, w, lm.label_local, cfg.s, cfg.class_lo)
-    rows_max, rows_sum, rows_z, rows_arg = exchange_rows(rmax, rsum, lm.z_label, rarg, group)
-    lse, argmax, _z, omp, loss = K.finalize_rows(rows_max, rows_sum, rows_arg, rows_z, y_all)
+    if R > 1 and B % 2 == 0 and hasattr(K, "finalize_rows_packed"):
+        # the kernels fill one packed buffer, the exchange is one all-gather, the merge reads it in place
+        buf, v_max, v_sum, v_z, v_arg = K.packed_stats(B, x_all.device)
+        lm = K.label_margin(x_all, w, inv_nx, None, y_all, cfg.class_lo, cfg.c_total, cfg.s, cfg.m, cfg.easy_margin,
+                            z_out=v_z)
+        what, inv_nw, _, _, _ = K.forward_rows_fused(xhat, w, lm.label_local, cfg.s, cfg.class_lo,
+                                                     out=(v_max, v_sum, v_arg))
+        lse, argmax, _z, omp, loss = K.finalize_rows_packed(_all_gather_bytes(buf, group), y_all)
+    else:
+        lm = K.label_margin(x_all, w, inv_nx, None, y_all, cfg.class_lo, cfg.c_total, cfg.s, cfg.m, cfg.easy_margin)
+        what, inv_nw, rmax, rsum, rarg = K.forward_rows_fused(xhat, w, lm.label_local, cfg.s, cfg.class_lo)
+        rows_max, rows_sum, rows_z, rows_arg = exchange_rows(rmax, rsum, lm.z_label, rarg, group)
+        lse, argmax, _z, omp, loss = K.finalize_rows(rows_max, rows_sum, rows_arg, rows_z, y_all)
     argmax_local = argmax if R == 1 else argmax[rank * b_loc:(rank + 1) * b_loc].contiguous()
     return FwdState(loss, argmax_local, lm.bad_flag, B, inv_nx, xhat, xhat_t, what, inv_nw, lse, omp, lm.dphi,
                     lm.label_local)
@@ -160,8 +171,10 @@ class GraphedStep:
         dev = w.device
         D = w.shape[1]
         self.K, self.group, self.cfg = K, group, cfg
-        self.x = torch.zeros((b_loc, D), dtype=torch.float32, device=dev)
-        self.y = torch.zeros((b_loc,), dtype=torch.int64, device=dev)
+        # static inputs as views of one buffer laid out (x | labels): the sharded gather sends it as is
+        self.xy = torch.zeros(b_loc * D * 4 + b_loc * 8, dtype=torch.uint8, device=dev)
+        self.x = self.xy[: b_loc * D * 4].view(torch.float32).view(b_loc, D)
+        self.y = self.xy[b_loc * D * 4:].view(torch.int64)
         self.one = torch.ones((), dtype=torch.float32, device=dev)
         self.version = 0
         self.with_backward = with_backward
@@ -170,7 +183,7 @@ class GraphedStep:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(self.WARMUP):  # lazy initialisation (NCCL communicators, kernel attributes) outside capture
-                st = forward_eager(K, group, self.x, w, self.y, cfg)
+                st = forward_eager(K, group, self.x, w, self.y, cfg, self.xy)
                 if with_backward:
                     backward_eager(K, group, self.x, st, self.one, cfg)
             del st
@@ -179,7 +192,7 @@ class GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         self.dx = self.dw = None
         with torch.cuda.graph(self.graph):
-            self.st = forward_eager(K, group, self.x, w, self.y, cfg)
+            self.st = forward_eager(K, group, self.x, w, self.y, cfg, self.xy)
             if with_backward:
                 self.dx, self.dw = backward_eager(K, group, self.x, self.st, self.one, cfg)
 

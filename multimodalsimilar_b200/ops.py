@@ -73,7 +73,7 @@ class LabelMargin:
     bad_flag: torch.Tensor     # int32 [1] set when a label is outside [0, C_total)
 
 
-def label_margin(x, w, inv_nx, inv_nw, label, class_offset, c_total, s, m, easy_margin) -> LabelMargin:
+def label_margin(x, w, inv_nx, inv_nw, label, class_offset, c_total, s, m, easy_margin, z_out=None) -> LabelMargin:
     _req(x, torch.float32, "x")
     _req(w, torch.float32, "weight")
     _req(label, torch.int64, "label")
@@ -81,7 +81,7 @@ def label_margin(x, w, inv_nx, inv_nw, label, class_offset, c_total, s, m, easy_
     dev = x.device
     out = LabelMargin(
         torch.empty(B, dtype=torch.float32, device=dev),
-        torch.empty(B, dtype=torch.float32, device=dev),
+        z_out if z_out is not None else torch.empty(B, dtype=torch.float32, device=dev),
         torch.empty(B, dtype=torch.float32, device=dev),
         torch.empty(B, dtype=torch.int32, device=dev),
         torch.zeros(1, dtype=torch.int32, device=dev),
@@ -121,7 +121,7 @@ def forward_rows(xhat, what, label_local, s: float, class_offset: int = 0):
     return rmax, rsum, rarg
 
 
-def forward_rows_fused(xhat, weight, label_local, s: float, class_offset: int = 0):
+def forward_rows_fused(xhat, weight, label_local, s: float, class_offset: int = 0, out=None):
     """K1 (class weights) + K2 + per-shard combine in one GEMM launch: the forward kernel's helper warps
     normalise and cast `weight` (fp32 [C, D]) while its tcgen05 pipeline consumes the rows already
     published.  Returns (what bf16 [C, D], inv_nw fp32 [C], row_max, row_sum, row_arg) -- the first two are
@@ -142,9 +142,12 @@ def forward_rows_fused(xhat, weight, label_local, s: float, class_offset: int = 
     ws = torch.empty(max(16, nws.value), dtype=torch.uint8, device=dev)
     _lib.call("arcface_b200_forward_stats_fused", _ptr(xhat), _ptr(weight), _ptr(label_local), B, D, C, s,
               _ptr(what), _ptr(inv_nw), _ptr(pmax), _ptr(psum), _ptr(parg), n_parts, _ptr(ws), ws.numel(), _stream())
-    rmax = torch.empty(B, dtype=torch.float32, device=dev)
-    rsum = torch.empty(B, dtype=torch.float32, device=dev)
-    rarg = torch.empty(B, dtype=torch.int64, device=dev)
+    if out is not None:  # (row_max fp32 [B], row_sum fp32 [B], row_arg int64 [B]) to fill, e.g. views of a packed buffer
+        rmax, rsum, rarg = out
+    else:
+        rmax = torch.empty(B, dtype=torch.float32, device=dev)
+        rsum = torch.empty(B, dtype=torch.float32, device=dev)
+        rarg = torch.empty(B, dtype=torch.int64, device=dev)
     _lib.call("arcface_b200_combine_partials", _ptr(pmax), _ptr(psum), _ptr(parg), n_parts, B, class_offset,
               _ptr(rmax), _ptr(rsum), _ptr(rarg), _stream())
     return what, inv_nw, rmax, rsum, rarg
@@ -164,6 +167,37 @@ def finalize_rows(rows_max, rows_sum, rows_arg, rows_z, label):
               _ptr(_req(rows_sum, torch.float32, "rows_sum")), _ptr(_req(rows_arg, torch.int64, "rows_arg")),
               _ptr(_req(rows_z, torch.float32, "rows_z")), _ptr(_req(label, torch.int64, "label")), R, B, _ptr(lse),
               _ptr(arg), _ptr(z), _ptr(omp), _ptr(loss), _stream())
+    return lse, arg, z, omp, loss
+
+
+STATS_BYTES_PER_ROW = 20  # packed per-rank statistics: [arg int64 x B | max fp32 x B | sum fp32 x B | z_label fp32 x B]
+
+
+def packed_stats(B: int, device):
+    """One rank's statistics buffer (uint8 [20 B]) and the typed views the kernels fill: (buf, max, sum, z, arg)."""
+    buf = torch.empty(STATS_BYTES_PER_ROW * B, dtype=torch.uint8, device=device)
+    arg = buf[: 8 * B].view(torch.int64)
+    f = buf[8 * B:].view(torch.float32)
+    return buf, f[:B], f[B:2 * B], f[2 * B:], arg
+
+
+def finalize_rows_packed(allp, label):
+    """`finalize_rows` over the all-gathered packed statistics (uint8 [R, 20 B], B even), read in place."""
+    R, nbytes = allp.shape
+    B = nbytes // STATS_BYTES_PER_ROW
+    if B % 2 != 0:
+        raise ValueError("packed statistics need an even batch size")
+    dev = allp.device
+    base = allp.data_ptr()
+    lse = torch.empty(B, dtype=torch.float32, device=dev)
+    arg = torch.empty(B, dtype=torch.int64, device=dev)
+    z = torch.empty(B, dtype=torch.float32, device=dev)
+    omp = torch.empty(B, dtype=torch.float32, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    _req(allp, torch.uint8, "packed statistics")
+    _lib.call("arcface_b200_finalize_rows_strided", ctypes.c_void_p(base + 8 * B), ctypes.c_void_p(base + 12 * B),
+              ctypes.c_void_p(base), ctypes.c_void_p(base + 16 * B), _ptr(_req(label, torch.int64, "label")), R, B,
+              5 * B, 5 * B // 2, _ptr(lse), _ptr(arg), _ptr(z), _ptr(omp), _ptr(loss), _stream())
     return lse, arg, z, omp, loss
 
 

@@ -1,0 +1,117 @@
+"""Class-sharded head on REAL GPUs over NCCL (needs >= 2 devices; skipped on a one-GPU box): every rank's loss /
+argmax / dx / dW shard against the dense single-GPU head on the same inputs, for the eager sequence and for the
+CUDA-graph replay (packed single-collective exchanges, in-place strided merge)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, case, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import multimodalsimilar_b200 as mm
+    from multimodalsimilar_b200 import engine
+    from oracle import arcface_numpy as onp
+
+    B, D, C, s, m, graph = case
+    _, w, _ = onp.synthetic_inputs(B, D, C, seed=11, trained_like=False)
+    head = mm.ShardedArcMarginProduct(D, C, s=s, m=m, use_cuda_graph=graph).to(dev)
+    head.load_full_weight(torch.from_numpy(w))
+    dense = None
+    if rank == 0:
+        dense = mm.ArcMarginProduct(D, C, s=s, m=m, use_cuda_graph=False).to(dev)
+        with torch.no_grad():
+            dense.weight.copy_(torch.from_numpy(w))
+    b_loc = B // world
+    ok = True
+    msg = ""
+    for it in range(5):   # graph mode: two eager calls, the capture, two replays
+        x, _, y = onp.synthetic_inputs(B, D, C, seed=30 + it, trained_like=(it % 2 == 1))
+        xl = torch.from_numpy(x[rank * b_loc:(rank + 1) * b_loc]).to(dev).requires_grad_(True)
+        yl = torch.from_numpy(y[rank * b_loc:(rank + 1) * b_loc]).to(dev)
+        head.weight.grad = None
+        loss, pred = head.loss(xl, yl)
+        loss.backward()
+        got = [loss.detach().cpu(), pred.cpu(), xl.grad.cpu(), head.weight.grad.cpu()]
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(got, gathered, dst=0)
+        if rank == 0:
+            xt = torch.from_numpy(x).to(dev).requires_grad_(True)
+            dense.weight.grad = None
+            dl, dp = dense.loss(xt, torch.from_numpy(y).to(dev))
+            dl.backward()
+            for r in range(world):
+                l_r, p_r, dx_r, dw_r = gathered[r]
+                lo, hi = mm.shard_range(C, world, r)
+                try:
+                    assert abs(float(l_r) - float(dl)) <= 1e-5 * max(1.0, abs(float(dl))), "loss"
+                    assert torch.equal(p_r, dp[r * b_loc:(r + 1) * b_loc].cpu()), "argmax"
+                    # same kernels on both sides; lse is merged in a different order (per rank, then across ranks),
+                    # which can flip the bf16 rounding of a few dC entries: one bf16 ulp of the largest term
+                    rdx = xt.grad[r * b_loc:(r + 1) * b_loc].cpu()
+                    rdw = dense.weight.grad[lo:hi].cpu()
+                    torch.testing.assert_close(dx_r, rdx, rtol=2e-3, atol=4e-3 * float(rdx.abs().max()))
+                    torch.testing.assert_close(dw_r, rdw, rtol=2e-3, atol=4e-3 * float(rdw.abs().max()))
+                    assert float((dw_r - rdw).norm() / rdw.norm()) <= 1e-3, "dW norm"
+                except AssertionError as e:
+                    ok = False
+                    msg += "iteration %d rank %d: %s\n" % (it, r, str(e)[:300])
+    if rank == 0:
+        if graph:
+            st = engine._PLANS.get(head)
+            if not (st and st["plan"] is not None and not st["failed"]):
+                ok, msg = False, msg + "the graph was never captured\n"
+        with open(os.path.join(out_dir, "result.txt"), "w") as f:
+            f.write("OK" if ok else "FAIL\n" + msg)
+    engine.drop_plan(head)
+    torch.cuda.synchronize()
+    dist.barrier()
+    sys.stdout.flush()
+    os._exit(0)   # see bench.py: no destructor-time teardown of a communicator captured graphs have used
+
+
+@pytest.mark.parametrize("case", [
+    (64, 128, 3001, 64.0, 0.4, False),    # eager, ragged class split
+    (64, 128, 3001, 64.0, 0.4, True),     # graph replay
+    (128, 512, 20000, 64.0, 0.5, True),   # bench-like D
+])
+def test_two_gpu_sharded_head_matches_dense(case, tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, case, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+    for p in procs:
+        if p.is_alive():
+            p.kill()
+            pytest.fail("worker timed out")
+    res = open(os.path.join(str(tmp_path), "result.txt")).read()
+    assert res == "OK", res
