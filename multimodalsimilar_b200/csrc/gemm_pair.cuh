@@ -106,6 +106,16 @@ struct Stager {
             bulk_commit();
         }
     }
+    // the same with an L2 eviction policy on the written lines (0 = none)
+    __device__ __forceinline__ void commit(const CUtensorMap* tm, int c0, int c1, uint64_t pol) const {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            if (pol != 0) tma_store_2d_hint(tm, buf, c0, c1, pol);
+            else tma_store_2d(tm, buf, c0, c1);
+            bulk_commit();
+        }
+    }
     __device__ __forceinline__ void drain() const {
         if (lane == 0) bulk_wait<0>();
         __syncwarp();

@@ -165,6 +165,14 @@ __device__ __forceinline__ float4 ldg_stream4(const float* p) {
 #ifndef AB_FWD_AUX_WARPS
 #define AB_FWD_AUX_WARPS 8
 #endif
+__device__ __forceinline__ float4 ldg_stream4_hint(const float* p, uint64_t pol) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+
 template <bool NORM>
 struct FwdStatsPairT : pr::PairDefaults {
     static constexpr int STAGES = 4;
@@ -197,6 +205,7 @@ struct FwdStatsPairT : pr::PairDefaults {
         int* ready;              // [ceil(C / 128)] rows published per 128-row block (zeroed before the launch)
         int debug;               // measurements only: 1 = the GEMM does not wait for the helper warps
         int pf_dist;             // helper warps prefetch their row pair j + pf_dist into L2 (0 = off)
+        int evict_first;         // 1: the fp32 weight stream is loaded with an L2 evict-first policy
     };
 
     __device__ static void prologue(const Params&, uint8_t*, int, int, int) {}
@@ -217,7 +226,7 @@ struct FwdStatsPairT : pr::PairDefaults {
     struct RowPair {
         float4 v[2][2][2];  // [row][chunk][half]
     };
-    __device__ static __forceinline__ void load_pair(const Params& p, int64_t r0, int lane, RowPair& rp) {
+    __device__ static __forceinline__ void load_pair(const Params& p, int64_t r0, int lane, RowPair& rp, uint64_t pol) {
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const int64_t row = min(r0 + r, static_cast<int64_t>(p.C) - 1);  // clamp: the tail re-reads the last row
@@ -226,8 +235,13 @@ struct FwdStatsPairT : pr::PairDefaults {
             for (int ch = 0; ch < 2; ++ch) {
                 const int d = (lane + 32 * ch) * 8;
                 if (d < p.D) {
-                    rp.v[r][ch][0] = ldg_stream4(src + d);
-                    rp.v[r][ch][1] = ldg_stream4(src + d + 4);
+                    if (pol != 0) {
+                        rp.v[r][ch][0] = ldg_stream4_hint(src + d, pol);
+                        rp.v[r][ch][1] = ldg_stream4_hint(src + d + 4, pol);
+                    } else {
+                        rp.v[r][ch][0] = ldg_stream4(src + d);
+                        rp.v[r][ch][1] = ldg_stream4(src + d + 4);
+                    }
                 } else {
                     rp.v[r][ch][0] = make_float4(0.f, 0.f, 0.f, 0.f);
                     rp.v[r][ch][1] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -288,8 +302,9 @@ struct FwdStatsPairT : pr::PairDefaults {
             if (u >= n_runs) return;
             const int64_t n_pairs = ((n_runs - u + nu - 1) / nu) * PPR;  // of this warp (even)
             auto row_of = [&](int64_t j) { return (u + (j / PPR) * nu) * RUN + (j % PPR) * 2; };
+            const uint64_t pol = p.evict_first ? l2_policy_evict_first() : 0ull;
             auto fetch = [&](int64_t j, RowPair& rp) {
-                if (j < n_pairs) load_pair(p, row_of(j), lane, rp);
+                if (j < n_pairs) load_pair(p, row_of(j), lane, rp, pol);
             };
             auto retire = [&](int64_t j, const RowPair& rp) {
                 const int64_t r = row_of(j);
@@ -565,6 +580,8 @@ static int32_t launch_fwd_pairs(const uint16_t* xhat, const uint16_t* what, cons
     if (p.debug == 2) p.core.s_blocks = 0;  // measurements only: helper warps alone
     p.pf_dist = 0;
     if (const char* pf = getenv("ARCFACE_B200_FWD_PF")) p.pf_dist = atoi(pf);
+    p.evict_first = 0;
+    if (const char* ef = getenv("ARCFACE_B200_FWD_EVICT")) p.evict_first = atoi(ef);
     CUtensorMap tmS, tmR;
     if (int32_t rc = make_tmap_kmajor(&tmS, what, D, C_local, D, pr::ROWS)) return rc;
     if (int32_t rc = make_tmap_kmajor(&tmR, xhat, D, B, D, pr::ROWS)) return rc;

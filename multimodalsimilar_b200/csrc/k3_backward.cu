@@ -811,6 +811,7 @@ struct BwdDWpT : pr::PairDefaults {
         const __nv_bfloat16* what;
         float* dw;  // out [C][D] fp32
         Ring ring;  // FUSED only
+        int evict_first;  // 1: dW is stored with an L2 evict-first policy (it is never read back by this kernel)
     };
     static constexpr int EXTRA_BYTES = 16;  // FUSED: [0] = 1 + the last block this CTA's producer has acquired
 
@@ -850,6 +851,7 @@ struct BwdDWpT : pr::PairDefaults {
         float inwn;
         const volatile int* acquired;  // FUSED: see EXTRA_BYTES
         bool have_scalars;
+        uint64_t pol;
         unsigned long long* prof;  // measurements only: [0] scalars [1] tmem load [2] math [3] staging wait [4] store issue
         unsigned long long pacc[5];
         __device__ __forceinline__ unsigned long long tick() const { return prof != nullptr ? clock64() : 0ull; }
@@ -858,6 +860,7 @@ struct BwdDWpT : pr::PairDefaults {
               d0(c.res * NCOL + c.half * 128), acquired(reinterpret_cast<const volatile int*>(c.extra)),
               have_scalars(false), prof(c.prof) {
             for (int k = 0; k < 5; ++k) pacc[k] = 0;
+            pol = p.evict_first ? l2_policy_evict_first() : 0ull;
         }
         __device__ __forceinline__ int class_of(int i) const {
             return p.c_begin + i * NCOL + rank * pr::ROWS + quad * 32 + lane;
@@ -926,7 +929,7 @@ struct BwdDWpT : pr::PairDefaults {
             for (int k = 0; k < 8; ++k)
                 stager.put(k, __float_as_uint(o[4 * k]), __float_as_uint(o[4 * k + 1]), __float_as_uint(o[4 * k + 2]),
                            __float_as_uint(o[4 * k + 3]));
-            stager.commit(tm_out, dg, crow0);  // rows >= C / columns >= D are clipped by the TMA
+            stager.commit(tm_out, dg, crow0, pol);  // rows >= C / columns >= D are clipped by the TMA
             if (prof != nullptr) { pacc[1] += t1 - t0; pacc[2] += t2 - t1; pacc[3] += t3 - t2; pacc[4] += tick() - t3; }
         }
         __device__ void tile(int i, int i_next, uint32_t taddr) {
@@ -1350,6 +1353,7 @@ extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* x
             p.q = q; p.q_slots = pl.q_slots; p.inv_nw = inv_nw;
             p.what = reinterpret_cast<const __nv_bfloat16*>(what);
             p.dw = dw;
+            p.evict_first = env_is("ARCFACE_B200_BWD_EVICT", "1") ? 1 : 0;
             p.ring = ring;
         }
         {
@@ -1485,6 +1489,7 @@ extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* x
             p.q = q; p.q_slots = pl.q_slots; p.inv_nw = inv_nw;
             p.what = reinterpret_cast<const __nv_bfloat16*>(what);
             p.dw = dw;
+            p.evict_first = env_is("ARCFACE_B200_BWD_EVICT", "1") ? 1 : 0;
             int groups = (nsm / 2) / p.core.n_res;
             if (groups < 1) groups = 1;
             if (groups > p.core.s_blocks) groups = p.core.s_blocks;

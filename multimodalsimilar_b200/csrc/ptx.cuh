@@ -134,6 +134,19 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem
                  ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1)
                  : "memory");
 }
+// L2 eviction-priority policies for streaming data that is never read again by this kernel (fp32 weights in, fp32
+// gradients out): keeps the re-used lines (bf16 what, the dC^T ring) from being pushed out by the stream.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* m, uint32_t smem_src, int32_t c0, int32_t c1,
+                                                  uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1), "l"(pol)
+                 : "memory");
+}
 // element-wise fp32 add into global memory (the reduction happens in L2)
 __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t smem_src, int32_t c0, int32_t c1) {
     asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
