@@ -11,6 +11,8 @@ package does not load it, the first op does, and raises if it is missing -- ther
 """
 from .head import ArcFaceCEFunction, ArcMarginProduct, FusedLogits  # noqa: F401
 from .sharded import ShardedArcMarginProduct, shard_range  # noqa: F401
+from .checkpoint import install_reference_shim, load_reference_head, reference_state_dict  # noqa: F401
 
-__all__ = ["ArcMarginProduct", "ShardedArcMarginProduct", "ArcFaceCEFunction", "FusedLogits", "shard_range"]
+__all__ = ["ArcMarginProduct", "ShardedArcMarginProduct", "ArcFaceCEFunction", "FusedLogits", "shard_range",
+           "install_reference_shim", "load_reference_head", "reference_state_dict"]
 __version__ = "0.1.0"

@@ -154,6 +154,11 @@ class ArcMarginProduct(nn.Module):
     `out_feature=` (multimodal_classifier.py:22); `in_features=` / `out_features=` are accepted as aliases.
     """
 
+    # class-level defaults: a module unpickled from a REFERENCE checkpoint (checkpoint.install_reference_shim)
+    # has only the reference's attributes in its __dict__
+    validate_labels = False
+    use_cuda_graph = True
+
     def __init__(self, in_feature=128, out_feature=10575, s=64.0, m=0.40, easy_margin=False, *,
                  in_features=None, out_features=None, validate_labels=False, use_cuda_graph=True):
         super().__init__()

@@ -118,3 +118,30 @@ def test_graph_mode_no_grad_and_pickle():
     buf.seek(0)
     h2 = torch.load(buf, weights_only=False)
     assert torch.equal(h2.weight, h.weight)
+
+
+def test_graph_mode_two_heads_share_an_embedding():
+    """Two heads on one embedding with the 10 / 5 loss weights of nlp_classifier_train_daodian_v3_dist.py:164-166:
+    every head replays its own graph, upstream gradients != 1 go through scale_grads, dx accumulates over heads."""
+    B, D, s = 32, 64, 64.0
+    _, w1, _ = onp.synthetic_inputs(B, D, 700, seed=5, trained_like=False)
+    _, w2, _ = onp.synthetic_inputs(B, D, 90, seed=6, trained_like=False)
+    eager = (_head(w1, s, 0.4, False), _head(w2, s, 0.2, False))
+    graph = (_head(w1, s, 0.4, True), _head(w2, s, 0.2, True))
+    for it in range(5):
+        x, _, y1 = onp.synthetic_inputs(B, D, 700, seed=40 + it, trained_like=False)
+        y2 = (y1 % 90).astype(np.int64)
+        res = []
+        for heads in (eager, graph):
+            xt = torch.from_numpy(x).to(dev()).requires_grad_(True)
+            for h in heads:
+                h.weight.grad = None
+            l1, p1 = heads[0].loss(xt, torch.from_numpy(y1).to(dev()))
+            l2, p2 = heads[1].loss(xt, torch.from_numpy(y2).to(dev()))
+            (10.0 * l1 + 5.0 * l2).backward()
+            res.append((l1.detach().clone(), l2.detach().clone(), p1.clone(), p2.clone(), xt.grad.clone(),
+                        heads[0].weight.grad.clone(), heads[1].weight.grad.clone()))
+        a, b = res
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+        for u, v in zip(a[4:], b[4:]):
+            assert float((u - v).norm() / v.norm()) <= 6e-3, "iteration %d" % it
