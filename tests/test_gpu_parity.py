@@ -299,6 +299,8 @@ def torch_oracle(x, w, y, s, m, easy, grad=1.0, dtype=torch.float32):
     (512, 512, 1000000, 64.0, 0.5, True),
     (128, 64, 600000, 64.0, 0.4, True),      # small B: chunks of > 200k classes
     (1024, 512, 300000, 64.0, 0.5, False),   # BASELINE config 5 batch (B = 1024)
+    (512, 1024, 125000, 64.0, 0.4, True),    # BASELINE config 3: one rank's class shard of the RoBERTa-large head
+    (512, 2816, 50000, 64.0, 0.5, False),    # BASELINE config 4 width (two-stream concat embedding), reduced C
 ])
 def test_full_size_against_gpu_oracle_and_invariants(B, D, C, s, m, trained):
     x, w, y = onp.synthetic_inputs(B, D, C, seed=5, trained_like=trained)
