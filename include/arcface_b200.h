@@ -135,6 +135,22 @@ int32_t arcface_b200_logits(const uint16_t* xhat, const uint16_t* what, const fl
                             const int32_t* label_local, int32_t B, int32_t D, int64_t C_local, float scale,
                             float* out, int64_t ld_out, void* stream);
 
+/* K4 -- fused cosine top-k (eval / retrieval): out_val[b, j], out_idx[b, j] = the k largest scale * cos[b, c] of row b
+ * over the C rows of `what`, descending, ties by ascending index; out_idx = local index + class_offset.  Replaces
+ * top-k / argmax over ArcMarginProduct.forward_test's B x C output (arcface.py:65-67) and the brute-force
+ * faiss.IndexFlat(METRIC_INNER_PRODUCT).search(x, k) over L2-normalised embeddings (daodian_infer.py:225-230,
+ * 295-302) without building the B x C matrix: two passes of the cosine GEMM (segment maxima -> per-row threshold ->
+ * candidates above it) and a shared-memory sort.  Exact.  1 <= k <= 128, any D (multiple of 8); rows with fewer than
+ * k classes are padded with (-inf, -1).  xhat / what: bf16 rows already L2-normalised (arcface_b200_normalize_cast). */
+int32_t arcface_b200_topk_workspace_bytes(int32_t B, int32_t D, int64_t C, int32_t k, size_t* bytes);
+int32_t arcface_b200_cosine_topk(const uint16_t* xhat, const uint16_t* what, int32_t B, int32_t D, int64_t C, int32_t k,
+                                 float scale, int64_t class_offset, float* out_val, int64_t* out_idx, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+/* Merge n_per_row (value, global index) candidates per row -- e.g. the all-gathered per-rank top-k lists of a
+ * class-sharded catalogue, [B][n_per_row], n_per_row <= 16384 -- into the k best, same order as above. */
+int32_t arcface_b200_topk_merge(const float* val, const int64_t* idx, int32_t B, int32_t n_per_row, int32_t k,
+                                float* out_val, int64_t* out_idx, void* stream);
+
 /* Workspace (bytes) arcface_b200_backward needs. */
 int32_t arcface_b200_backward_workspace_bytes(int32_t B, int32_t D, int64_t C_local, size_t* bytes);
 /* How arcface_b200_backward walks the classes: classes per scratch chunk and number of chunks

@@ -51,6 +51,11 @@ SIGNATURES = {
                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "arcface_b200_logits": (
         c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64, c_float, c_void_p, c_int64, c_void_p]),
+    "arcface_b200_topk_workspace_bytes": (c_int32, [c_int32, c_int32, c_int64, c_int32, POINTER(c_size_t)]),
+    "arcface_b200_cosine_topk": (
+        c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int64, c_int32, c_float, c_int64, c_void_p, c_void_p,
+                  c_void_p, c_size_t, c_void_p]),
+    "arcface_b200_topk_merge": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "arcface_b200_backward_workspace_bytes": (c_int32, [c_int32, c_int32, c_int64, POINTER(c_size_t)]),
     "arcface_b200_backward_plan": (c_int32, [c_int32, c_int32, c_int64, POINTER(c_int64), POINTER(c_int32)]),
     "arcface_b200_backward_launches": (c_int32, [c_int32, c_int32, c_int64, POINTER(c_int32)]),

@@ -241,5 +241,14 @@ class ArcMarginProduct(nn.Module):
         rmax, _, rarg = ops.forward_rows(xhat, what, None, 1.0, 0)
         return rarg, rmax
 
+    @torch.no_grad()
+    def predict_topk(self, x, k: int):
+        """The k best classes per row by cosine, descending, without the B x C matrix: (cosines fp32 [B, k],
+        class ids int64 [B, k]).  What top-k over `forward_test(x)` returns (arcface.py:65-67)."""
+        x = x.to(torch.float32).contiguous()
+        xhat, _, _ = ops.normalize_cast(x)
+        what, _, _ = ops.normalize_cast(self.weight.detach().contiguous())
+        return ops.cosine_topk(xhat, what, k)
+
     def extra_repr(self):
         return ""

@@ -213,6 +213,34 @@ def logits(xhat, what, z_label, label_local, scale: float) -> torch.Tensor:
     return out
 
 
+def cosine_topk(xhat, what, k: int, scale: float = 1.0, class_offset: int = 0):
+    """K4.  (values fp32 [B, k], indices int64 [B, k]) of the k largest scale * cos per row, descending."""
+    _req(xhat, torch.bfloat16, "xhat")
+    _req(what, torch.bfloat16, "what")
+    B, D = xhat.shape
+    C = what.shape[0]
+    dev = xhat.device
+    n = ctypes.c_size_t(0)
+    _lib.call("arcface_b200_topk_workspace_bytes", B, D, C, k, ctypes.byref(n))
+    ws = torch.empty(max(16, n.value), dtype=torch.uint8, device=dev)
+    val = torch.empty((B, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((B, k), dtype=torch.int64, device=dev)
+    _lib.call("arcface_b200_cosine_topk", _ptr(xhat), _ptr(what), B, D, C, k, scale, class_offset, _ptr(val), _ptr(idx),
+              _ptr(ws), ws.numel(), _stream())
+    return val, idx
+
+
+def topk_merge(val, idx, k: int):
+    """Merge [B, n] (value, global index) candidates into the k best per row."""
+    _req(val, torch.float32, "val")
+    _req(idx, torch.int64, "idx")
+    B, n = val.shape
+    out_v = torch.empty((B, k), dtype=torch.float32, device=val.device)
+    out_i = torch.empty((B, k), dtype=torch.int64, device=val.device)
+    _lib.call("arcface_b200_topk_merge", _ptr(val), _ptr(idx), B, n, k, _ptr(out_v), _ptr(out_i), _stream())
+    return out_v, out_i
+
+
 def backward_workspace_bytes(B: int, D: int, c_local: int) -> int:
     n = ctypes.c_size_t(0)
     _lib.call("arcface_b200_backward_workspace_bytes", B, D, c_local, ctypes.byref(n))

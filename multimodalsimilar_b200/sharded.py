@@ -110,6 +110,27 @@ class ShardedArcMarginProduct(nn.Module):
     def logits(self, x, label=None):
         raise NotImplementedError("the sharded head never materialises the B x C logits; use loss() / predict()")
 
+    @torch.no_grad()
+    def predict_topk(self, x, k: int):
+        """Global top-k classes by cosine for this rank's rows: every rank ranks the gathered batch against its class
+        shard (fused top-k kernel), the per-rank lists are all-gathered and merged on the device.
+        Returns (cosines fp32 [b_local, k], global class ids int64 [b_local, k])."""
+        K, group = self.kernels, self.process_group
+        x = x.to(torch.float32).contiguous()
+        b_loc = x.shape[0]
+        x_all = _all_gather_rows(x, group)
+        xhat, _, _ = K.normalize_cast(x_all)
+        what, _, _ = K.normalize_cast(self.weight.detach().contiguous())
+        v, i = K.cosine_topk(xhat, what, k, 1.0, self.class_lo)            # [B, k] over the local classes
+        B = x_all.shape[0]
+        vs = _all_gather_rows(v.unsqueeze(0), group)                       # [R, B, k]
+        is_ = _all_gather_rows(i.unsqueeze(0), group)
+        cand_v = vs.permute(1, 0, 2).reshape(B, -1).contiguous()
+        cand_i = is_.permute(1, 0, 2).reshape(B, -1).contiguous()
+        mv, mi = K.topk_merge(cand_v, cand_i, k)
+        return (mv[self.rank * b_loc:(self.rank + 1) * b_loc].contiguous(),
+                mi[self.rank * b_loc:(self.rank + 1) * b_loc].contiguous())
+
     # ------------------------------------------------------------------ checkpoint compatibility
     @torch.no_grad()
     def gather_weight(self) -> torch.Tensor:

@@ -178,3 +178,23 @@ def synthetic_inputs(B, D, C, seed=0, trained_like=False, dtype=np.float32):
     else:
         x = rng.standard_normal((B, D)).astype(dtype)
     return x, w, label
+
+
+def cosine_topk(x, w, k):
+    """Exact top-k by cosine, descending, ties by ascending index: (values [B, k], indices int64 [B, k]).
+
+    Restates top-k over ArcMarginProduct.forward_test (/root/reference/arcface.py:65-67) and the product's retrieval
+    call faiss.normalize_L2 + IndexFlat(d, METRIC_INNER_PRODUCT).search(x, k) (/root/reference/daodian_infer.py:
+    225-230, 295-302).  faiss is a third-party dependency absent from the container (unpinned in the reference); its
+    documented semantics for a flat inner-product index are an exhaustive scan returning the k highest scores in
+    decreasing order, padded with (-inf, -1) when the index holds fewer than k rows.  tests/test_oracle.py pins this
+    function against the golden `cos` matrices produced by the reference's own forward_test."""
+    cos = forward_test(np.asarray(x, dtype=np.float64), np.asarray(w, dtype=np.float64))
+    B, C = cos.shape
+    order = np.argsort(-cos, axis=1, kind="stable")[:, :k]
+    vals = np.take_along_axis(cos, order, axis=1)
+    if C < k:
+        vals = np.concatenate([vals, np.full((B, k - C), -np.inf, dtype=vals.dtype)], axis=1)
+        order = np.concatenate([order, np.full((B, k - C), -1, dtype=order.dtype)], axis=1)
+    return vals, order.astype(np.int64)
+

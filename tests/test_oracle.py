@@ -96,3 +96,19 @@ def test_row_stats_consistency():
     zmax, lse = onp.row_stats(z)
     assert abs(np.mean(lse - z[np.arange(16), y]) - onp.cross_entropy(z, y)) < 1e-9
     assert np.all(zmax == z.max(axis=1))
+
+
+@pytest.mark.parametrize("name", ["base", "tie", "trained", "ragged"])
+def test_topk_oracle_against_reference_cosines(golden, name):
+    """oracle.cosine_topk against top-k of the golden `cos` matrix (the reference's forward_test output)."""
+    x, w, _, _, _, _, _ = _case(golden, name)
+    cos = golden[name + "/cos"].astype(np.float64)
+    for k in (1, 5, cos.shape[1], cos.shape[1] + 3):
+        vals, idx = onp.cosine_topk(x, w, k)
+        kk = min(k, cos.shape[1])
+        ref_vals = -np.sort(-cos, axis=1)[:, :kk]
+        np.testing.assert_allclose(vals[:, :kk], ref_vals, rtol=0, atol=2e-6)
+        # indices: the reference's own cosines at the returned positions are the top-k values
+        np.testing.assert_allclose(np.take_along_axis(cos, idx[:, :kk], axis=1), ref_vals, rtol=0, atol=2e-6)
+        if k > kk:
+            assert np.all(np.isneginf(vals[:, kk:])) and np.all(idx[:, kk:] == -1)
