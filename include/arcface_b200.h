@@ -189,6 +189,15 @@ int32_t arcface_b200_normalize_bwd_x(const float* x, const float* inv_nx, const 
  * apply it.  When *scale_dev == 1.0f -- loss.backward() on the head's own loss -- the kernel returns immediately. */
 int32_t arcface_b200_scale_grads(float* a, int64_t na, float* b, int64_t nb, const float* scale_dev, void* stream);
 
+/* Fused head optimiser: one torch.optim.AdamW step (decoupled weight decay, bias correction for step number `step`
+ * >= 1) on the fp32 class-weight rows, in place on w / exp_avg / exp_avg_sq, and -- when what / inv_nw are given --
+ * the NEXT forward's K1 in the same pass: what = bf16(w_new / max(||w_new||, 1e-12)), inv_nw = 1 / max(||w_new||, 1e-12).
+ * Replaces AdamW(model.classifier.parameters()).step() (nlp_classifier_train.py:94-97, 131-133) plus
+ * F.normalize(self.weight) of the following forward (arcface.py:47): 30 bytes per weight instead of 28 + 6. */
+int32_t arcface_b200_adamw_normalize(float* w, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t rows,
+                                     int32_t D, double lr, double beta1, double beta2, double eps, double weight_decay,
+                                     int64_t step, uint16_t* what, float* inv_nw, void* stream);
+
 /* One-call step for hosts without torch: HOST embeddings / labels in, HOST loss / argmax / dx out; the
  * class weights and their gradient stay resident on the device (w, dw are DEVICE pointers, fp32 [C x D]).
  * Copies in and out are part of the call; it returns after the results have landed in the host buffers.

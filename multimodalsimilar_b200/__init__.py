@@ -11,9 +11,10 @@ package does not load it, the first op does, and raises if it is missing -- ther
 """
 from .head import ArcFaceCEFunction, ArcMarginProduct, FusedLogits  # noqa: F401
 from .sharded import ShardedArcMarginProduct, shard_range  # noqa: F401
+from .optim import FusedHeadAdamW  # noqa: F401
 from .retrieval import CosineIndex, cosine_topk  # noqa: F401
 from .checkpoint import install_reference_shim, load_reference_head, reference_state_dict  # noqa: F401
 
 __all__ = ["ArcMarginProduct", "ShardedArcMarginProduct", "ArcFaceCEFunction", "FusedLogits", "shard_range",
-           "CosineIndex", "cosine_topk", "install_reference_shim", "load_reference_head", "reference_state_dict"]
+           "FusedHeadAdamW", "CosineIndex", "cosine_topk", "install_reference_shim", "load_reference_head", "reference_state_dict"]
 __version__ = "0.1.0"

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
+from ctypes import c_double, POINTER, c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libarcface_b200.so")
@@ -66,6 +66,9 @@ SIGNATURES = {
     ),
     "arcface_b200_normalize_bwd_x": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "arcface_b200_scale_grads": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "arcface_b200_adamw_normalize": (
+        c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_double, c_double, c_double, c_double,
+                  c_double, c_int64, c_void_p, c_void_p, c_void_p]),
     "arcface_b200_step_workspace_bytes": (c_int32, [c_int32, c_int32, c_int64, POINTER(c_size_t)]),
     "arcface_b200_step_host": (
         c_int32,

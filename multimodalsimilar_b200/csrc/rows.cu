@@ -300,9 +300,97 @@ scale_grads_kernel(float* __restrict__ a, int64_t na4, float* __restrict__ b, in
     }
 }
 
+// Fused head optimiser: one AdamW step on the class-weight rows AND the next step's K1
+// in the same pass.  Reference: `AdamW(model.classifier.parameters(), lr=1e-2)` + optimizer.step()
+// (nlp_classifier_train.py:94-97, 131-133) followed, one forward later, by F.normalize(self.weight) (arcface.py:47).
+// Update rule = torch.optim.AdamW (decoupled weight decay):
+//   w *= 1 - lr * wd;  m += (1 - b1) (g - m);  v = b2 v + (1 - b2) g^2;  w -= step_size * m / (sqrt(v) / sqrt(bc2) + eps)
+// with step_size = lr / (1 - b1^t), bc2 = 1 - b2^t computed by the caller.  One warp per row: the first sweep
+// updates w / m / v and accumulates ||w_new||^2, the second re-reads the freshly written row (L1 / L2) and writes
+// bf16 what = w_new / max(||w_new||, 1e-12) and inv_nw -- the only extra HBM traffic is the 2-byte what store.
+__global__ void __launch_bounds__(256)
+adamw_normalize_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                       int64_t rows, int D, float decay, float one_minus_b1, float b2, float one_minus_b2,
+                       float step_size, float inv_bc2_sqrt, float eps, __nv_bfloat16* __restrict__ what,
+                       float* __restrict__ inv_nw) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float* wp = w + row * D;
+    const float* gp = g + row * D;
+    float* mp = m + row * D;
+    float* vp = v + row * D;
+    float ss = 0.f;
+    for (int d = lane * 4; d < D; d += 128) {
+        float4 a = *reinterpret_cast<float4*>(wp + d);
+        const float4 gg = *reinterpret_cast<const float4*>(gp + d);
+        float4 mm = *reinterpret_cast<float4*>(mp + d);
+        float4 vv = *reinterpret_cast<float4*>(vp + d);
+        float* af = reinterpret_cast<float*>(&a);
+        const float* gf = reinterpret_cast<const float*>(&gg);
+        float* mf = reinterpret_cast<float*>(&mm);
+        float* vf = reinterpret_cast<float*>(&vv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float gj = gf[j];
+            float p = af[j] * decay;
+            const float mj = mf[j] + one_minus_b1 * (gj - mf[j]);
+            const float vj = vf[j] * b2 + one_minus_b2 * (gj * gj);
+            const float denom = sqrtf(vj) * inv_bc2_sqrt + eps;
+            p = p - step_size * (mj / denom);
+            af[j] = p; mf[j] = mj; vf[j] = vj;
+            ss += p * p;
+        }
+        *reinterpret_cast<float4*>(wp + d) = a;
+        *reinterpret_cast<float4*>(mp + d) = mm;
+        *reinterpret_cast<float4*>(vp + d) = vv;
+    }
+    if (what == nullptr) return;
+    ss = warp_sum(ss);
+    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    if (lane == 0) inv_nw[row] = inv;
+    __nv_bfloat16* op = what + row * D;
+    for (int d = lane * 4; d < D; d += 128) {
+        const float4 a = *reinterpret_cast<const float4*>(wp + d);  // this lane wrote these four values above
+        uint2 o;
+        o.x = pack_bf16x2(a.x * inv, a.y * inv);
+        o.y = pack_bf16x2(a.z * inv, a.w * inv);
+        *reinterpret_cast<uint2*>(op + d) = o;
+    }
+}
+
 }  // namespace ab
 
 using namespace ab;
+
+extern "C" int32_t arcface_b200_adamw_normalize(float* w, const float* grad, float* exp_avg, float* exp_avg_sq,
+                                                int64_t rows, int32_t D, double lr, double beta1, double beta2,
+                                                double eps, double weight_decay, int64_t step, uint16_t* what,
+                                                float* inv_nw, void* stream) {
+    if (int32_t rc = check_arch()) return rc;
+    AB_REQUIRE(w && grad && exp_avg && exp_avg_sq, ARCFACE_B200_E_ARG, "adamw_normalize: null pointer");
+    AB_REQUIRE((what == nullptr) == (inv_nw == nullptr), ARCFACE_B200_E_ARG,
+               "adamw_normalize: what and inv_nw must both be given or both be null");
+    AB_REQUIRE(rows >= 0 && D >= 8 && D % 8 == 0, ARCFACE_B200_E_SHAPE, "adamw_normalize: D=%d must be a positive multiple of 8", D);
+    AB_REQUIRE(step >= 1 && lr >= 0. && beta1 >= 0. && beta1 < 1. && beta2 >= 0. && beta2 < 1. && eps >= 0.,
+               ARCFACE_B200_E_ARG, "adamw_normalize: invalid hyper-parameter");
+    AB_REQUIRE(aligned16(w) && aligned16(grad) && aligned16(exp_avg) && aligned16(exp_avg_sq) && aligned16(what),
+               ARCFACE_B200_E_LAYOUT, "adamw_normalize: pointers must be 16-byte aligned");
+    if (rows == 0) return ARCFACE_B200_OK;
+    // scalars are formed in double and rounded once, like the Python floats torch.optim.AdamW passes to its kernels
+    const double bc1 = 1.0 - pow(beta1, static_cast<double>(step));
+    const double bc2 = 1.0 - pow(beta2, static_cast<double>(step));
+    const int wpb = 8;
+    const int64_t nblk = (rows + wpb - 1) / wpb;
+    AB_REQUIRE(nblk < (1ll << 31), ARCFACE_B200_E_SHAPE, "adamw_normalize: too many rows");
+    adamw_normalize_kernel<<<static_cast<unsigned>(nblk), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        w, grad, exp_avg, exp_avg_sq, rows, D, static_cast<float>(1.0 - lr * weight_decay),
+        static_cast<float>(1.0 - beta1), static_cast<float>(beta2), static_cast<float>(1.0 - beta2),
+        static_cast<float>(lr / bc1), static_cast<float>(1.0 / sqrt(bc2)), static_cast<float>(eps),
+        reinterpret_cast<__nv_bfloat16*>(what), inv_nw);
+    AB_CHECK_CUDA(cudaGetLastError());
+    return ARCFACE_B200_OK;
+}
 
 extern "C" int32_t arcface_b200_scale_grads(float* a, int64_t na, float* b, int64_t nb, const float* scale_dev,
                                             void* stream) {

@@ -112,7 +112,17 @@ def reduce_scatter_rows(full: torch.Tensor, group) -> torch.Tensor:
     return out
 
 
-def forward_eager(K, group, x_local, w, y_local, cfg: StepConfig, packed_xy=None) -> FwdState:
+def _rows(K, xhat, w, label_local, cfg, w_cache, out=None):
+    """(what, inv_nw, max, sum, arg): K1 (w) fused into K2, or K2 alone on the rows a fused optimiser step left
+    behind (`w_cache` = (what, inv_nw), optim.FusedHeadAdamW)."""
+    kw = {} if out is None else {"out": out}
+    if w_cache is not None:
+        what, inv_nw = w_cache
+        return (what, inv_nw) + tuple(K.forward_rows(xhat, what, label_local, cfg.s, cfg.class_lo, **kw))
+    return K.forward_rows_fused(xhat, w, label_local, cfg.s, cfg.class_lo, **kw)
+
+
+def forward_eager(K, group, x_local, w, y_local, cfg: StepConfig, packed_xy=None, w_cache=None) -> FwdState:
     """K1 (x) -> label margin -> K1 (w) + K2 -> combine -> [exchange] -> finalize.  arcface.py:45-63 + the mean
     CrossEntropyLoss + argmax of the call sites, for the global batch against the local class rows."""
     R, rank = _world(group), _rank(group)
@@ -125,12 +135,11 @@ def forward_eager(K, group, x_local, w, y_local, cfg: StepConfig, packed_xy=None
         buf, v_max, v_sum, v_z, v_arg = K.packed_stats(B, x_all.device)
         lm = K.label_margin(x_all, w, inv_nx, None, y_all, cfg.class_lo, cfg.c_total, cfg.s, cfg.m, cfg.easy_margin,
                             z_out=v_z)
-        what, inv_nw, _, _, _ = K.forward_rows_fused(xhat, w, lm.label_local, cfg.s, cfg.class_lo,
-                                                     out=(v_max, v_sum, v_arg))
+        what, inv_nw, _, _, _ = _rows(K, xhat, w, lm.label_local, cfg, w_cache, out=(v_max, v_sum, v_arg))
         lse, argmax, _z, omp, loss = K.finalize_rows_packed(_all_gather_bytes(buf, group), y_all)
     else:
         lm = K.label_margin(x_all, w, inv_nx, None, y_all, cfg.class_lo, cfg.c_total, cfg.s, cfg.m, cfg.easy_margin)
-        what, inv_nw, rmax, rsum, rarg = K.forward_rows_fused(xhat, w, lm.label_local, cfg.s, cfg.class_lo)
+        what, inv_nw, rmax, rsum, rarg = _rows(K, xhat, w, lm.label_local, cfg, w_cache)
         rows_max, rows_sum, rows_z, rows_arg = exchange_rows(rmax, rsum, lm.z_label, rarg, group)
         lse, argmax, _z, omp, loss = K.finalize_rows(rows_max, rows_sum, rows_arg, rows_z, y_all)
     argmax_local = argmax if R == 1 else argmax[rank * b_loc:(rank + 1) * b_loc].contiguous()
@@ -167,7 +176,7 @@ class GraphedStep:
 
     WARMUP = 2
 
-    def __init__(self, K, group, w: torch.Tensor, b_loc: int, cfg: StepConfig, with_backward: bool):
+    def __init__(self, K, group, w: torch.Tensor, b_loc: int, cfg: StepConfig, with_backward: bool, w_cache=None):
         dev = w.device
         D = w.shape[1]
         self.K, self.group, self.cfg = K, group, cfg
@@ -183,7 +192,7 @@ class GraphedStep:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(self.WARMUP):  # lazy initialisation (NCCL communicators, kernel attributes) outside capture
-                st = forward_eager(K, group, self.x, w, self.y, cfg, self.xy)
+                st = forward_eager(K, group, self.x, w, self.y, cfg, self.xy, w_cache)
                 if with_backward:
                     backward_eager(K, group, self.x, st, self.one, cfg)
             del st
@@ -192,7 +201,7 @@ class GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         self.dx = self.dw = None
         with torch.cuda.graph(self.graph):
-            self.st = forward_eager(K, group, self.x, w, self.y, cfg, self.xy)
+            self.st = forward_eager(K, group, self.x, w, self.y, cfg, self.xy, w_cache)
             if with_backward:
                 self.dx, self.dw = backward_eager(K, group, self.x, self.st, self.one, cfg)
 
@@ -236,8 +245,8 @@ class _GraphedCE(torch.autograd.Function):
 
 class _EagerCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, label, K, group, cfg, validate_labels):
-        st = forward_eager(K, group, x, w, label, cfg)
+    def forward(ctx, x, w, label, K, group, cfg, validate_labels, w_cache=None):
+        st = forward_eager(K, group, x, w, label, cfg, None, w_cache)
         if validate_labels and int(st.bad_flag.item()) != 0:
             raise IndexError("ArcMarginProduct: a label is outside [0, %d)" % cfg.c_total)
         ctx.save_for_backward(x, st.inv_nx, st.xhat, st.xhat_t, st.what, st.inv_nw, st.lse, st.omp, st.dphi,
@@ -252,11 +261,14 @@ class _EagerCE(torch.autograd.Function):
         K, group, cfg, B = ctx.meta
         st = FwdState(None, None, None, B, inv_nx, xhat, xhat_t, what, inv_nw, lse, omp, dphi, label_local)
         dx, dw = backward_eager(K, group, x, st, grad_loss, cfg, need_dx=ctx.needs_input_grad[0])
-        return dx, (dw if ctx.needs_input_grad[1] else None), None, None, None, None, None
+        return dx, (dw if ctx.needs_input_grad[1] else None), None, None, None, None, None, None
 
 
 # per-head graph state lives outside the module's __dict__ so that torch.save(model) keeps working
 _PLANS: "weakref.WeakKeyDictionary[Any, dict]" = weakref.WeakKeyDictionary()
+
+# head -> (what bf16 [C, D], inv_nw fp32 [C], weight._version, weight.data_ptr()) written by optim.FusedHeadAdamW
+_W_CACHE: "weakref.WeakKeyDictionary[Any, tuple]" = weakref.WeakKeyDictionary()
 
 ENGAGE_AFTER = 2  # eager calls with an unchanged signature before a graph is captured
 
@@ -264,26 +276,32 @@ ENGAGE_AFTER = 2  # eager calls with an unchanged signature before a graph is ca
 def run_step(head, K, group, x, w, label, cfg: StepConfig, validate_labels: bool):
     """loss, argmax = one forward of `head` (autograd-connected).  Graph replay when `head.use_cuda_graph` and the
     signature has repeated; the eager kernel sequence otherwise."""
+    # normalised rows left behind by a fused optimiser step: valid while the weight has not been touched since
+    w_cache = None
+    cache = _W_CACHE.get(head)
+    if cache is not None and x.is_cuda and cache[2] == w._version and cache[3] == w.data_ptr():
+        w_cache = (cache[0], cache[1])
     use_graph = bool(getattr(head, "use_cuda_graph", False)) and x.is_cuda and not validate_labels
     if not use_graph:
-        return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels)
+        return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels, w_cache)
     with_bwd = torch.is_grad_enabled() and (x.requires_grad or w.requires_grad)
-    sig = (tuple(x.shape), x.device, w.data_ptr(), tuple(w.shape), cfg, with_bwd, id(group))
+    sig = (tuple(x.shape), x.device, w.data_ptr(), tuple(w.shape), cfg, with_bwd, id(group),
+           w_cache[0].data_ptr() if w_cache is not None else 0)
     state = _PLANS.setdefault(head, {"sig": None, "seen": 0, "plan": None, "failed": False})
     if state["failed"]:
-        return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels)
+        return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels, w_cache)
     if state["sig"] != sig:
         state.update(sig=sig, seen=0, plan=None)
     if state["plan"] is None:
         state["seen"] += 1
         if state["seen"] <= ENGAGE_AFTER:
-            return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels)
+            return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels, w_cache)
         try:
-            state["plan"] = GraphedStep(K, group, w.detach(), x.shape[0], cfg, with_bwd)
+            state["plan"] = GraphedStep(K, group, w.detach(), x.shape[0], cfg, with_bwd, w_cache)
         except Exception as e:  # keep training: the eager sequence computes the same thing
             state["failed"] = True
             warnings.warn("multimodalsimilar_b200: CUDA-graph capture failed (%r); continuing with eager launches" % (e,))
-            return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels)
+            return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels, w_cache)
     plan: GraphedStep = state["plan"]
     if not with_bwd:
         plan.run(x, label)

@@ -40,7 +40,7 @@ class ArcFaceCEFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_argmax):
-        return engine._EagerCE.backward(ctx, grad_loss, _grad_argmax)
+        return engine._EagerCE.backward(ctx, grad_loss, _grad_argmax)[:7]
 
 
 class FusedLogits:

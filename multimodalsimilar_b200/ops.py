@@ -99,7 +99,7 @@ def forward_parts(B: int, D: int, c_local: int) -> int:
     return n.value
 
 
-def forward_rows(xhat, what, label_local, s: float, class_offset: int = 0):
+def forward_rows(xhat, what, label_local, s: float, class_offset: int = 0, out=None):
     """K2 + per-shard combine over every column except the row's label column (label_local, or None for
     the eval path).  Returns (row_max fp32 [B], row_sum fp32 [B], row_arg int64 [B])."""
     _req(xhat, torch.bfloat16, "xhat")
@@ -113,9 +113,12 @@ def forward_rows(xhat, what, label_local, s: float, class_offset: int = 0):
     parg = torch.empty((n_parts, B), dtype=torch.int32, device=dev)
     _lib.call("arcface_b200_forward_stats", _ptr(xhat), _ptr(what), _ptr(label_local), B, D, C, s,
               _ptr(pmax), _ptr(psum), _ptr(parg), n_parts, _stream())
-    rmax = torch.empty(B, dtype=torch.float32, device=dev)
-    rsum = torch.empty(B, dtype=torch.float32, device=dev)
-    rarg = torch.empty(B, dtype=torch.int64, device=dev)
+    if out is not None:
+        rmax, rsum, rarg = out
+    else:
+        rmax = torch.empty(B, dtype=torch.float32, device=dev)
+        rsum = torch.empty(B, dtype=torch.float32, device=dev)
+        rarg = torch.empty(B, dtype=torch.int64, device=dev)
     _lib.call("arcface_b200_combine_partials", _ptr(pmax), _ptr(psum), _ptr(parg), n_parts, B, class_offset,
               _ptr(rmax), _ptr(rsum), _ptr(rarg), _stream())
     return rmax, rsum, rarg
@@ -296,6 +299,19 @@ def scale_grads(a, b, scale_dev) -> None:
     nb = 0 if b is None else _req(b, torch.float32, "b").numel()
     _lib.call("arcface_b200_scale_grads", _ptr(a), na, _ptr(b), nb, _ptr(_req(scale_dev, torch.float32, "scale")),
               _stream())
+
+
+def adamw_normalize(w, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, what=None, inv_nw=None):
+    """One AdamW step in place on (w, exp_avg, exp_avg_sq) [rows, D] fp32; optionally emits the next forward's
+    normalised bf16 rows `what` [rows, D] and `inv_nw` [rows] in the same pass."""
+    for t, name in ((w, "w"), (grad, "grad"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        _req(t, torch.float32, name)
+    rows, D = w.shape
+    if what is not None:
+        _req(what, torch.bfloat16, "what")
+        _req(inv_nw, torch.float32, "inv_nw")
+    _lib.call("arcface_b200_adamw_normalize", _ptr(w), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), rows, D, lr, beta1,
+              beta2, eps, weight_decay, step, _ptr(what), _ptr(inv_nw), _stream())
 
 
 def step_workspace_bytes(B: int, D: int, C: int) -> int:
