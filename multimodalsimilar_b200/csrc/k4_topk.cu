@@ -7,7 +7,7 @@
 // .search(x, k) with k = 13 / 26 / 100 (daodian_infer.py:225-230, 295-302).
 //
 // Exact, three launches on the shared tcgen05 GEMM core (gemm_core.cuh; any D):
-//   1. SegMax  : cosine GEMM whose epilogue keeps only the maximum of every 128-column segment   [n_seg][B]
+//   1. SegMax  : cosine GEMM whose epilogue keeps only the maximum of every 128-column segment   [B][n_seg]
 //      select  : tau[b] = k-th largest segment maximum of row b (radix select).  At most k - 1 segments hold an
 //                element > tau, so at most 128 (k - 1) elements exceed it, and at least k elements are >= tau.
 //   2. Emit    : the same GEMM again (bit-identical accumulators); the epilogue appends every element > tau, and
@@ -38,8 +38,8 @@ struct TopkCommon {
         int B, D, C;
         int m_tiles, n_tiles;
         int n_seg;          // ceil(C / 128)
-        int ld;             // leading dimension of segmax (>= B)
-        float* segmax;      // pass 1 out: [n_seg][ld]
+        int ld;             // leading dimension of segmax (>= n_seg)
+        float* segmax;      // pass 1 out: [B][ld] (row-major: the select kernel streams a row)
         const float* tau;   // pass 2 in:  [B]
         int k, cap;
         int* cnt;           // [B] candidates appended
@@ -101,7 +101,7 @@ struct TopkSegMax : TopkCommon {
                     }
                 }
                 const int seg = (t.n0 + h * TOPK_SEG) / TOPK_SEG;
-                if (seg < p.n_seg && row < p.B) p.segmax[static_cast<int64_t>(seg) * p.ld + row] = m;
+                if (seg < p.n_seg && row < p.B) p.segmax[static_cast<int64_t>(row) * p.ld + seg] = m;
             }
         }
         __device__ void finish() {}
@@ -135,15 +135,14 @@ struct TopkEmit : TopkCommon {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
                 if (!(m >= tau)) continue;  // the common case: nothing of this chunk can be a candidate
-#pragma unroll 1
+                // fully unrolled so that v[] stays in registers (a dynamic index would push it to local memory)
+#pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float x = __uint_as_float(v[j]);
                     const int col = col0 + j;
-                    if (col >= p.C) break;
-                    if (x > tau) {
-                        append(row, x, col);
-                    } else if (x == tau) {
-                        if (atomicAdd(p.eq + row, 1) < p.k) append(row, x, col);
+                    if (x >= tau && col < p.C) {
+                        if (x > tau) append(row, x, col);
+                        else if (atomicAdd(p.eq + row, 1) < p.k) append(row, x, col);
                     }
                 }
             }
@@ -161,17 +160,21 @@ __device__ __forceinline__ float fkey_inv(uint32_t k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-// tau[b] = k-th largest of segmax[:, b] (n values at stride ld); -inf when n < k.  One CTA per row, 8-bit radix
+// tau[b] = k-th largest of segmax[b, 0..n); -inf when n < k.  One CTA per row, 8-bit radix
 // select from the most significant byte down.
 __global__ void __launch_bounds__(256) topk_select_kernel(const float* __restrict__ segmax, int n, int ld, int k,
-                                                          float* __restrict__ tau) {
+                                                          int cached, float* __restrict__ tau) {
     __shared__ unsigned hist[256];
     __shared__ unsigned s_prefix, s_k;
+    extern __shared__ uint32_t row_keys[];  // the row's keys when they fit (cached = 1): read from global once
     const int b = blockIdx.x;
     if (n < k) {
         if (threadIdx.x == 0) tau[b] = -INFINITY;
         return;
     }
+    const float* src = segmax + static_cast<int64_t>(b) * ld;
+    if (cached)
+        for (int i = threadIdx.x; i < n; i += blockDim.x) row_keys[i] = fkey(src[i]);
     if (threadIdx.x == 0) { s_prefix = 0u; s_k = static_cast<unsigned>(k); }
     unsigned mask = 0u;
     for (int shift = 24; shift >= 0; shift -= 8) {
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(256) topk_select_kernel(const float* __restric
         __syncthreads();
         const unsigned prefix = s_prefix;
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const uint32_t key = fkey(segmax[static_cast<int64_t>(i) * ld + b]);
+            const uint32_t key = cached ? row_keys[i] : fkey(src[i]);
             if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
         }
         __syncthreads();
@@ -259,7 +262,7 @@ struct TopkPlan {
 static TopkPlan topk_plan(int B, int64_t C, int k) {
     TopkPlan pl;
     pl.n_seg = static_cast<int>((C + TOPK_SEG - 1) / TOPK_SEG);
-    pl.ld = (B + 31) / 32 * 32;
+    pl.ld = (pl.n_seg + 31) / 32 * 32;
     const int64_t cap = static_cast<int64_t>(TOPK_SEG) * k;
     const int64_t all = static_cast<int64_t>(pl.n_seg) * TOPK_SEG;
     pl.cap = static_cast<int>(cap < all ? cap : all);
@@ -267,7 +270,7 @@ static TopkPlan topk_plan(int B, int64_t C, int k) {
     pl.n_tiles = static_cast<int>((C + TopkCommon::BLOCK_N - 1) / TopkCommon::BLOCK_N);
     auto up = [](size_t v) { return (v + 255) / 256 * 256; };
     size_t o = 0;
-    pl.off_segmax = o; o = up(o + static_cast<size_t>(pl.n_seg) * pl.ld * 4);
+    pl.off_segmax = o; o = up(o + static_cast<size_t>(B) * pl.ld * 4);
     pl.off_tau = o;    o = up(o + static_cast<size_t>(B) * 4);
     pl.off_cnt = o;    o = up(o + static_cast<size_t>(B) * 4);
     pl.off_eq = o;     o = up(o + static_cast<size_t>(B) * 4);
@@ -345,7 +348,9 @@ extern "C" int32_t arcface_b200_cosine_topk(const uint16_t* xhat, const uint16_t
     const int64_t total = static_cast<int64_t>(pl.m_tiles) * pl.n_tiles;
     const int grid = static_cast<int>(total < sm_count() ? total : sm_count());
     if (int32_t rc = launch_gemm<TopkSegMax>(tmA, tmB, tmA, p, grid, 0, st)) return rc;
-    topk_select_kernel<<<B, 256, 0, st>>>(p.segmax, pl.n_seg, pl.ld, k, reinterpret_cast<float*>(ws + pl.off_tau));
+    const int cached = pl.n_seg <= 11 * 1024 ? 1 : 0;  // 44 KB of dynamic shared memory at most (default limit 48 KB)
+    topk_select_kernel<<<B, 256, cached ? static_cast<size_t>(pl.n_seg) * 4 : 0, st>>>(
+        p.segmax, pl.n_seg, pl.ld, k, cached, reinterpret_cast<float*>(ws + pl.off_tau));
     AB_CHECK_CUDA(cudaGetLastError());
     AB_CHECK_CUDA(cudaMemsetAsync(ws + pl.off_cnt, 0, pl.off_val - pl.off_cnt, st));  // cnt and eq
     if (int32_t rc = launch_gemm<TopkEmit>(tmA, tmB, tmA, p, grid, 0, st)) return rc;
