@@ -78,6 +78,18 @@ def _worker(rank, world, port, case, out_dir):
                 except AssertionError as e:
                     ok = False
                     msg += "iteration %d rank %d: %s\n" % (it, r, str(e)[:300])
+    # global top-k over the class shards (fused top-k per rank + all-gather + device merge) against the dense head
+    x, _, _ = onp.synthetic_inputs(B, D, C, seed=77, trained_like=True)
+    xl = torch.from_numpy(x[rank * b_loc:(rank + 1) * b_loc]).to(dev)
+    tv, ti = head.predict_topk(xl, 10)
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object([tv.cpu(), ti.cpu()], gathered, dst=0)
+    if rank == 0:
+        dv, di = dense.predict_topk(torch.from_numpy(x).to(dev), 10)
+        for r in range(world):
+            if not (torch.equal(gathered[r][0], dv[r * b_loc:(r + 1) * b_loc].cpu())
+                    and torch.equal(gathered[r][1], di[r * b_loc:(r + 1) * b_loc].cpu())):
+                ok, msg = False, msg + "predict_topk differs on rank %d\n" % r
     if rank == 0:
         if graph:
             st = engine._PLANS.get(head)
@@ -96,6 +108,7 @@ def _worker(rank, world, port, case, out_dir):
     (64, 128, 3001, 64.0, 0.4, False),    # eager, ragged class split
     (64, 128, 3001, 64.0, 0.4, True),     # graph replay
     (128, 512, 20000, 64.0, 0.5, True),   # bench-like D
+    (64, 1024, 5001, 64.0, 0.4, True),    # BASELINE config 3 width (D > 512: generic kernels), graph replay
 ])
 def test_two_gpu_sharded_head_matches_dense(case, tmp_path):
     if torch.cuda.device_count() < 2:
