@@ -198,6 +198,22 @@ int32_t arcface_b200_adamw_normalize(float* w, const float* grad, float* exp_avg
                                      int32_t D, double lr, double beta1, double beta2, double eps, double weight_decay,
                                      int64_t step, uint16_t* what, float* inv_nw, void* stream);
 
+/* One-shot exchange over peer-mapped memory (NVLink): stores bytes_per_peer bytes from src (+ r * src_stride for peer r;
+ * src_stride = 0 sends the same bytes to everyone = all-gather, src_stride = bytes_per_peer = scatter) into slot `rank`
+ * of every rank's receive buffer (peer_bufs[r] + rank * slot_stride), raises this call's flag on every rank and
+ * returns (stream order) once every rank's flag for the same call has arrived here.  peer_bufs / peer_flags: HOST
+ * arrays of `world` device addresses valid in this process (torch.distributed._symmetric_memory buffer_ptrs);
+ * flags = uint32 [8][16] per rank, zeroed once; sync_dev = uint32 [16] of local device memory, zeroed once.  All ranks
+ * must issue the same sequence of calls per channel.  Replaces the latency-bound NCCL all-gather / reduce-scatter of
+ * the class-sharded step (sharded.py; nn.DataParallel's gather / reduce in the reference). */
+int32_t arcface_b200_p2p_exchange(const void* src, size_t bytes_per_peer, size_t src_stride, const uint64_t* peer_bufs,
+                                  const uint64_t* peer_flags, int32_t rank, int32_t world, size_t slot_stride,
+                                  int32_t channel, uint32_t* sync_dev, void* stream);
+/* normalize_bwd_x over the SUM of n_parts partial dxhat buffers ([n_parts][B][D], part_stride floats apart), summed in
+ * index order: the reduce half of the reduce-scatter, fused. */
+int32_t arcface_b200_normalize_bwd_x_sum(const float* x, const float* inv_nx, const float* parts, int32_t n_parts,
+                                         int64_t part_stride, int32_t B, int32_t D, float* dx, void* stream);
+
 /* One-call step for hosts without torch: HOST embeddings / labels in, HOST loss / argmax / dx out; the
  * class weights and their gradient stay resident on the device (w, dw are DEVICE pointers, fp32 [C x D]).
  * Copies in and out are part of the call; it returns after the results have landed in the host buffers.

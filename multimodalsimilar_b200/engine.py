@@ -65,7 +65,7 @@ def _all_gather_bytes(buf: torch.Tensor, group) -> torch.Tensor:
     return out.view(_world(group), buf.numel())
 
 
-def gather_batch(x_local: torch.Tensor, y_local: torch.Tensor, group, packed=None):
+def gather_batch(x_local: torch.Tensor, y_local: torch.Tensor, group, packed=None, peer=None):
     """All ranks' embeddings [B, D] fp32 and labels [B] int64 in rank order: ONE collective over the
     byte-packed (x | labels) of every rank.  `packed`: the caller already holds x_local / y_local as views of one
     uint8 buffer laid out that way (the graph's static input), so nothing has to be concatenated."""
@@ -76,7 +76,10 @@ def gather_batch(x_local: torch.Tensor, y_local: torch.Tensor, group, packed=Non
     xb = b * D * 4
     if packed is None:
         packed = torch.cat([x_local.reshape(-1).view(torch.uint8), y_local.view(torch.uint8)])
-    allp = _all_gather_bytes(packed, group)
+    if peer is not None and packed.numel() % 16 == 0:
+        allp = peer.all_gather_bytes(0, packed)     # stores over NVLink + flags (csrc/p2p.cu)
+    else:
+        allp = _all_gather_bytes(packed, group)
     x_all = allp[:, :xb].contiguous().view(torch.float32).reshape(R * b, D)
     y_all = allp[:, xb:].contiguous().view(torch.int64).reshape(R * b)
     return x_all, y_all
@@ -122,12 +125,12 @@ def _rows(K, xhat, w, label_local, cfg, w_cache, out=None):
     return K.forward_rows_fused(xhat, w, label_local, cfg.s, cfg.class_lo, **kw)
 
 
-def forward_eager(K, group, x_local, w, y_local, cfg: StepConfig, packed_xy=None, w_cache=None) -> FwdState:
+def forward_eager(K, group, x_local, w, y_local, cfg: StepConfig, packed_xy=None, w_cache=None, peer=None) -> FwdState:
     """K1 (x) -> label margin -> K1 (w) + K2 -> combine -> [exchange] -> finalize.  arcface.py:45-63 + the mean
     CrossEntropyLoss + argmax of the call sites, for the global batch against the local class rows."""
     R, rank = _world(group), _rank(group)
     b_loc = x_local.shape[0]
-    x_all, y_all = gather_batch(x_local, y_local, group, packed_xy)
+    x_all, y_all = gather_batch(x_local, y_local, group, packed_xy, peer)
     B = x_all.shape[0]
     xhat, inv_nx, xhat_t = K.normalize_cast(x_all, want_transpose=True)
     if R > 1 and B % 2 == 0 and hasattr(K, "finalize_rows_packed"):
@@ -136,7 +139,11 @@ def forward_eager(K, group, x_local, w, y_local, cfg: StepConfig, packed_xy=None
         lm = K.label_margin(x_all, w, inv_nx, None, y_all, cfg.class_lo, cfg.c_total, cfg.s, cfg.m, cfg.easy_margin,
                             z_out=v_z)
         what, inv_nw, _, _, _ = _rows(K, xhat, w, lm.label_local, cfg, w_cache, out=(v_max, v_sum, v_arg))
-        lse, argmax, _z, omp, loss = K.finalize_rows_packed(_all_gather_bytes(buf, group), y_all)
+        if peer is not None and buf.numel() % 16 == 0:
+            allp = peer.all_gather_bytes(1, buf)
+        else:
+            allp = _all_gather_bytes(buf, group)
+        lse, argmax, _z, omp, loss = K.finalize_rows_packed(allp, y_all)
     else:
         lm = K.label_margin(x_all, w, inv_nx, None, y_all, cfg.class_lo, cfg.c_total, cfg.s, cfg.m, cfg.easy_margin)
         what, inv_nw, rmax, rsum, rarg = _rows(K, xhat, w, lm.label_local, cfg, w_cache)
@@ -147,7 +154,7 @@ def forward_eager(K, group, x_local, w, y_local, cfg: StepConfig, packed_xy=None
                     lm.label_local)
 
 
-def backward_eager(K, group, x_local, st: FwdState, grad_loss, cfg: StepConfig, need_dx: bool = True):
+def backward_eager(K, group, x_local, st: FwdState, grad_loss, cfg: StepConfig, need_dx: bool = True, peer=None):
     """K3 -> [reduce-scatter] -> normalise backward.  Returns (dx for the local rows or None, dW of the local
     class rows)."""
     R, rank = _world(group), _rank(group)
@@ -157,9 +164,12 @@ def backward_eager(K, group, x_local, st: FwdState, grad_loss, cfg: StepConfig, 
                                 cfg.s, 1.0 / st.B, grad_loss_dev=g)
     dx = None
     if need_dx:
-        dxhat_loc = reduce_scatter_rows(dxhat_part, group)
         inv_loc = st.inv_nx if R == 1 else st.inv_nx[rank * b_loc:(rank + 1) * b_loc].contiguous()
-        dx = K.normalize_bwd_x(x_local, inv_loc, dxhat_loc)
+        if peer is not None and R > 1:
+            # every rank stores its partial rows into the owner's buffer; the sum is fused into the normalise backward
+            dx = K.normalize_bwd_x_sum(x_local, inv_loc, peer.scatter_rows(dxhat_part))
+        else:
+            dx = K.normalize_bwd_x(x_local, inv_loc, reduce_scatter_rows(dxhat_part, group))
     return dx, dw
 
 
@@ -176,7 +186,8 @@ class GraphedStep:
 
     WARMUP = 2
 
-    def __init__(self, K, group, w: torch.Tensor, b_loc: int, cfg: StepConfig, with_backward: bool, w_cache=None):
+    def __init__(self, K, group, w: torch.Tensor, b_loc: int, cfg: StepConfig, with_backward: bool, w_cache=None,
+                 peer=None):
         dev = w.device
         D = w.shape[1]
         self.K, self.group, self.cfg = K, group, cfg
@@ -192,18 +203,18 @@ class GraphedStep:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(self.WARMUP):  # lazy initialisation (NCCL communicators, kernel attributes) outside capture
-                st = forward_eager(K, group, self.x, w, self.y, cfg, self.xy, w_cache)
+                st = forward_eager(K, group, self.x, w, self.y, cfg, self.xy, w_cache, peer)
                 if with_backward:
-                    backward_eager(K, group, self.x, st, self.one, cfg)
+                    backward_eager(K, group, self.x, st, self.one, cfg, True, peer)
             del st
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         self.dx = self.dw = None
         with torch.cuda.graph(self.graph):
-            self.st = forward_eager(K, group, self.x, w, self.y, cfg, self.xy, w_cache)
+            self.st = forward_eager(K, group, self.x, w, self.y, cfg, self.xy, w_cache, peer)
             if with_backward:
-                self.dx, self.dw = backward_eager(K, group, self.x, self.st, self.one, cfg)
+                self.dx, self.dw = backward_eager(K, group, self.x, self.st, self.one, cfg, True, peer)
 
     def run(self, x_local, y_local, param=None):
         if self.with_backward and param is not None and param.grad is not None and \
@@ -245,23 +256,28 @@ class _GraphedCE(torch.autograd.Function):
 
 class _EagerCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, label, K, group, cfg, validate_labels, w_cache=None):
-        st = forward_eager(K, group, x, w, label, cfg, None, w_cache)
+    def forward(ctx, x, w, label, K, group, cfg, validate_labels, w_cache=None, peer=None):
+        st = forward_eager(K, group, x, w, label, cfg, None, w_cache, peer)
         if validate_labels and int(st.bad_flag.item()) != 0:
             raise IndexError("ArcMarginProduct: a label is outside [0, %d)" % cfg.c_total)
         ctx.save_for_backward(x, st.inv_nx, st.xhat, st.xhat_t, st.what, st.inv_nw, st.lse, st.omp, st.dphi,
                               st.label_local)
-        ctx.meta = (K, group, cfg, st.B)
+        ctx.meta = (K, group, cfg, st.B, peer)
         ctx.mark_non_differentiable(st.argmax_local)
         return st.loss, st.argmax_local
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_argmax):
         x, inv_nx, xhat, xhat_t, what, inv_nw, lse, omp, dphi, label_local = ctx.saved_tensors
-        K, group, cfg, B = ctx.meta
+        K, group, cfg, B, peer = ctx.meta
         st = FwdState(None, None, None, B, inv_nx, xhat, xhat_t, what, inv_nw, lse, omp, dphi, label_local)
-        dx, dw = backward_eager(K, group, x, st, grad_loss, cfg, need_dx=ctx.needs_input_grad[0])
-        return dx, (dw if ctx.needs_input_grad[1] else None), None, None, None, None, None, None
+        if peer is not None and not ctx.needs_input_grad[0]:
+            # the exchange is a rendezvous of all ranks: it cannot be skipped by one of them
+            dx, dw = backward_eager(K, group, x, st, grad_loss, cfg, True, peer)
+            dx = None
+        else:
+            dx, dw = backward_eager(K, group, x, st, grad_loss, cfg, ctx.needs_input_grad[0], peer)
+        return dx, (dw if ctx.needs_input_grad[1] else None), None, None, None, None, None, None, None
 
 
 # per-head graph state lives outside the module's __dict__ so that torch.save(model) keeps working
@@ -269,6 +285,39 @@ _PLANS: "weakref.WeakKeyDictionary[Any, dict]" = weakref.WeakKeyDictionary()
 
 # head -> (what bf16 [C, D], inv_nw fp32 [C], weight._version, weight.data_ptr()) written by optim.FusedHeadAdamW
 _W_CACHE: "weakref.WeakKeyDictionary[Any, tuple]" = weakref.WeakKeyDictionary()
+
+# head -> PeerExchange (csrc/p2p.cu) or False when symmetric memory is unavailable for its group
+_PEERS: "weakref.WeakKeyDictionary[Any, Any]" = weakref.WeakKeyDictionary()
+
+
+def _peer_for(head, group, x):
+    """The head's peer-memory exchange for this batch shape, created collectively on first use.  Any rank failing
+    (no NVLink peer mapping, gloo group ...) sends every rank back to the NCCL collectives."""
+    st = _PEERS.get(head)
+    if st is False:
+        return None
+    b_loc, D = x.shape
+    if st is not None and st.matches(b_loc, D):
+        return st
+    if dist.get_world_size(group) < 2 or dist.get_backend(group) != "nccl":
+        _PEERS[head] = False
+        return None
+    peer, err = None, None
+    try:
+        from .p2p import PeerExchange
+
+        peer = PeerExchange(group, x.device, b_loc, D)
+    except Exception as e:  # noqa: BLE001
+        err = e
+    ok = torch.tensor([1 if peer is not None else 0], dtype=torch.int32, device=x.device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    if int(ok.item()) == 0:
+        warnings.warn("multimodalsimilar_b200: peer-memory exchange unavailable (%r); using NCCL collectives" % (err,))
+        _PEERS[head] = False
+        return None
+    _PEERS[head] = peer
+    return peer
+
 
 ENGAGE_AFTER = 2  # eager calls with an unchanged signature before a graph is captured
 
@@ -281,27 +330,28 @@ def run_step(head, K, group, x, w, label, cfg: StepConfig, validate_labels: bool
     cache = _W_CACHE.get(head)
     if cache is not None and x.is_cuda and cache[2] == w._version and cache[3] == w.data_ptr():
         w_cache = (cache[0], cache[1])
+    peer = _peer_for(head, group, x) if (group is not None and x.is_cuda and getattr(head, "use_p2p", False)) else None
     use_graph = bool(getattr(head, "use_cuda_graph", False)) and x.is_cuda and not validate_labels
     if not use_graph:
-        return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels, w_cache)
+        return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels, w_cache, peer)
     with_bwd = torch.is_grad_enabled() and (x.requires_grad or w.requires_grad)
     sig = (tuple(x.shape), x.device, w.data_ptr(), tuple(w.shape), cfg, with_bwd, id(group),
-           w_cache[0].data_ptr() if w_cache is not None else 0)
+           w_cache[0].data_ptr() if w_cache is not None else 0, id(peer))
     state = _PLANS.setdefault(head, {"sig": None, "seen": 0, "plan": None, "failed": False})
     if state["failed"]:
-        return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels, w_cache)
+        return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels, w_cache, peer)
     if state["sig"] != sig:
         state.update(sig=sig, seen=0, plan=None)
     if state["plan"] is None:
         state["seen"] += 1
         if state["seen"] <= ENGAGE_AFTER:
-            return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels, w_cache)
+            return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels, w_cache, peer)
         try:
-            state["plan"] = GraphedStep(K, group, w.detach(), x.shape[0], cfg, with_bwd, w_cache)
+            state["plan"] = GraphedStep(K, group, w.detach(), x.shape[0], cfg, with_bwd, w_cache, peer)
         except Exception as e:  # keep training: the eager sequence computes the same thing
             state["failed"] = True
             warnings.warn("multimodalsimilar_b200: CUDA-graph capture failed (%r); continuing with eager launches" % (e,))
-            return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels, w_cache)
+            return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels, w_cache, peer)
     plan: GraphedStep = state["plan"]
     if not with_bwd:
         plan.run(x, label)

@@ -293,6 +293,18 @@ def normalize_bwd_x(x, inv_nx, dxhat) -> torch.Tensor:
     return dx
 
 
+def normalize_bwd_x_sum(x, inv_nx, parts) -> torch.Tensor:
+    """normalize_bwd_x over the sum of `parts` fp32 [R, B, D] (fixed order)."""
+    _req(x, torch.float32, "x")
+    if parts.dtype != torch.float32 or parts.stride(-1) != 1 or parts.stride(1) != parts.shape[2]:
+        raise RuntimeError("parts must be fp32 [R, B, D] with contiguous rows")
+    B, D = x.shape
+    dx = torch.empty_like(x)
+    _lib.call("arcface_b200_normalize_bwd_x_sum", _ptr(x), _ptr(inv_nx), _ptr(parts), parts.shape[0], parts.stride(0), B, D,
+              _ptr(dx), _stream())
+    return dx
+
+
 def scale_grads(a, b, scale_dev) -> None:
     """In-place a *= scale, b *= scale (fp32 tensors or None; scale = DEVICE scalar); free when scale == 1."""
     na = 0 if a is None else _req(a, torch.float32, "a").numel()

@@ -55,7 +55,7 @@ class ShardedArcMarginProduct(nn.Module):
     """
 
     def __init__(self, in_feature=128, out_feature=10575, s=64.0, m=0.40, easy_margin=False, *, in_features=None,
-                 out_features=None, process_group=None, kernels=None, use_cuda_graph=True):
+                 out_features=None, process_group=None, kernels=None, use_cuda_graph=True, use_p2p=True):
         super().__init__()
         if in_features is not None:
             in_feature = in_features
@@ -65,6 +65,7 @@ class ShardedArcMarginProduct(nn.Module):
             from . import ops as kernels  # the CUDA library; raises later if it was not built
         self.kernels = kernels
         self.use_cuda_graph = use_cuda_graph
+        self.use_p2p = use_p2p      # exchanges through peer-mapped memory (p2p.py) instead of NCCL when available
         self.process_group = process_group if process_group is not None else dist.group.WORLD
         self.world_size = dist.get_world_size(self.process_group)
         self.rank = dist.get_rank(self.process_group)

@@ -1,4 +1,4 @@
-"""Class-sharded head on REAL GPUs over NCCL (needs >= 2 devices; skipped on a one-GPU box): every rank's loss /
+"""Class-sharded head on REAL GPUs over NCCL and over peer-mapped memory (needs >= 2 devices; skipped on a one-GPU box): every rank's loss /
 argmax / dx / dW shard against the dense single-GPU head on the same inputs, for the eager sequence and for the
 CUDA-graph replay (packed single-collective exchanges, in-place strided merge)."""
 import os
@@ -35,9 +35,9 @@ def _worker(rank, world, port, case, out_dir):
     from multimodalsimilar_b200 import engine
     from oracle import arcface_numpy as onp
 
-    B, D, C, s, m, graph = case
+    B, D, C, s, m, graph, p2p = case
     _, w, _ = onp.synthetic_inputs(B, D, C, seed=11, trained_like=False)
-    head = mm.ShardedArcMarginProduct(D, C, s=s, m=m, use_cuda_graph=graph).to(dev)
+    head = mm.ShardedArcMarginProduct(D, C, s=s, m=m, use_cuda_graph=graph, use_p2p=p2p).to(dev)
     head.load_full_weight(torch.from_numpy(w))
     dense = None
     if rank == 0:
@@ -91,6 +91,8 @@ def _worker(rank, world, port, case, out_dir):
                     and torch.equal(gathered[r][1], di[r * b_loc:(r + 1) * b_loc].cpu())):
                 ok, msg = False, msg + "predict_topk differs on rank %d\n" % r
     if rank == 0:
+        if p2p and not engine._PEERS.get(head):
+            ok, msg = False, msg + "the peer-memory exchange was not used\n"
         if graph:
             st = engine._PLANS.get(head)
             if not (st and st["plan"] is not None and not st["failed"]):
@@ -105,10 +107,11 @@ def _worker(rank, world, port, case, out_dir):
 
 
 @pytest.mark.parametrize("case", [
-    (64, 128, 3001, 64.0, 0.4, False),    # eager, ragged class split
-    (64, 128, 3001, 64.0, 0.4, True),     # graph replay
-    (128, 512, 20000, 64.0, 0.5, True),   # bench-like D
-    (64, 1024, 5001, 64.0, 0.4, True),    # BASELINE config 3 width (D > 512: generic kernels), graph replay
+    (64, 128, 3001, 64.0, 0.4, False, False),   # eager, NCCL collectives, ragged class split
+    (64, 128, 3001, 64.0, 0.4, False, True),    # eager, peer-memory exchanges (csrc/p2p.cu)
+    (64, 128, 3001, 64.0, 0.4, True, True),     # graph replay over peer memory
+    (128, 512, 20000, 64.0, 0.5, True, False),  # bench-like D, graph replay over NCCL
+    (64, 1024, 5001, 64.0, 0.4, True, True),    # BASELINE config 3 width (D > 512: generic kernels)
 ])
 def test_two_gpu_sharded_head_matches_dense(case, tmp_path):
     if torch.cuda.device_count() < 2:
