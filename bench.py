@@ -212,7 +212,8 @@ def main():
         head.out_feature = C
         c_lo, c_hi = 0, C
     else:
-        head = mm.ShardedArcMarginProduct(D, world, s=s, m=m)  # tiny init; real shard installed below
+        # ARCFACE_B200_P2P=0: exchanges through NCCL instead of peer-mapped memory (A/B measurements)
+        head = mm.ShardedArcMarginProduct(D, world, s=s, m=m, use_p2p=os.environ.get("ARCFACE_B200_P2P", "1") != "0")
         head.out_feature = C
         head.class_lo, head.class_hi = mm.shard_range(C, world, rank)
         c_lo, c_hi = head.class_lo, head.class_hi
