@@ -5,6 +5,9 @@ Public surface (mirrors /root/reference/arcface.py):
     ShardedArcMarginProduct  the same head class-sharded over a process group (PartialFC-style)
     ArcFaceCEFunction        the autograd.Function behind both
     ops                      tensor-level wrappers over the C ABI (include/arcface_b200.h)
+    CosineIndex, cosine_topk fused cosine top-k / faiss-style flat inner-product index (retrieval.py, K4)
+    FusedHeadAdamW           AdamW for head weights that also emits the next forward's normalised rows (optim.py)
+    install_reference_shim, load_reference_head, reference_state_dict   reference checkpoint compatibility
 
 The compute lives in libarcface_b200.so (hand-written sm_100a CUDA: tcgen05 / TMEM / TMA); importing the
 package does not load it, the first op does, and raises if it is missing -- there is no fallback path.

@@ -1,23 +1,26 @@
-"""Step engine of the ArcFace head: the kernel sequence of one forward / backward, run either eagerly or as
-two replayed CUDA graphs.
+"""Step engine of the ArcFace head: the kernel sequence of one forward / backward, run either eagerly or as ONE
+replayed CUDA graph.
 
 One sequence serves both public modules: `ArcMarginProduct` (group = None, the whole class range on one GPU)
-and `ShardedArcMarginProduct` (class shard per rank, three NCCL collectives per step: all-gather of the local
+and `ShardedArcMarginProduct` (class shard per rank, three exchanges per step: all-gather of the packed local
 embeddings + labels, all-gather of the packed per-row statistics, reduce-scatter of the embedding gradient;
-reference counterpart: nn.DataParallel at nlp_classifier_train_daodian_v2_dist.py:85).
+reference counterpart: nn.DataParallel at nlp_classifier_train_daodian_v2_dist.py:85).  The exchanges run over
+peer-mapped memory (p2p.py / csrc/p2p.cu) when the head enables it and the group supports it, else over NCCL.
 
 Why graphs: at 8 GPUs one rank's kernels for the north-star shape take ~0.35 ms, less than the host needs to
 issue ~60 small torch / ctypes calls, so the eager step is host-bound (0.84 ms measured).  `GraphedStep` captures
-forward + backward (kernels and collectives) once per signature -- every buffer, including `what`, the softmax
-statistics and dW, lives in the graph's private pool -- and replays it: one launch per step.
+forward + backward (kernels and exchanges) once per signature -- every buffer, including `what`, the softmax
+statistics and dW, lives in the graph's private pool -- and replays it: one launch per step (0.45 ms measured).
 The captured kernels are the same C-ABI calls the eager path makes (`ops`), on the capture stream.
+
+Also here: the weight cache a fused optimiser step leaves behind (`_W_CACHE`, optim.py), consumed by `run_step`.
 """
 from __future__ import annotations
 
 import warnings
 import weakref
 from dataclasses import dataclass
-from typing import Any, Optional
+from typing import Any
 
 import torch
 import torch.distributed as dist

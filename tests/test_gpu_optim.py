@@ -1,6 +1,5 @@
 """Fused head optimiser: `FusedHeadAdamW` against torch.optim.AdamW, the normalised rows it
 emits against K1, and a training loop whose forwards run from those rows against the ordinary loop."""
-import numpy as np
 import pytest
 import torch
 
