@@ -265,6 +265,8 @@ def main():
     k3_launches = ops.backward_launches(B, D, c_hi - c_lo)
     # K1(x), label, K1(w)+K2, combine, finalize, K3, bwd-x, scale_grads -- replayed from one CUDA graph per step
     launches_per_step = 1 + 1 + 1 + 1 + 1 + k3_launches + 1 + 1
+    if world > 1 and getattr(head, "use_p2p", False):
+        launches_per_step += 3  # the three peer-memory exchange kernels (csrc/p2p.cu) that replace the NCCL collectives
     gpu_launches = launches_per_step * args.steps
 
     # ---- end-to-end with host buffers
