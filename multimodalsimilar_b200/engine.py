@@ -168,9 +168,10 @@ def backward_eager(K, group, x_local, st: FwdState, grad_loss, cfg: StepConfig, 
     dx = None
     if need_dx:
         inv_loc = st.inv_nx if R == 1 else st.inv_nx[rank * b_loc:(rank + 1) * b_loc].contiguous()
-        if peer is not None and R > 1:
-            # every rank stores its partial rows into the owner's buffer; the sum is fused into the normalise backward
-            dx = K.normalize_bwd_x_sum(x_local, inv_loc, peer.scatter_rows(dxhat_part))
+        parts = peer.scatter_rows(dxhat_part) if (peer is not None and R > 1) else None
+        if parts is not None:
+            # every rank stored its partial rows into the owner's buffer; the sum is fused into the normalise backward
+            dx = K.normalize_bwd_x_sum(x_local, inv_loc, parts)
         else:
             dx = K.normalize_bwd_x(x_local, inv_loc, reduce_scatter_rows(dxhat_part, group))
     return dx, dw
@@ -193,7 +194,7 @@ class GraphedStep:
                  peer=None):
         dev = w.device
         D = w.shape[1]
-        self.K, self.group, self.cfg = K, group, cfg
+        self.K, self.group, self.cfg, self.peer = K, group, cfg, peer
         # static inputs as views of one buffer laid out (x | labels): the sharded gather sends it as is
         self.xy = torch.zeros(b_loc * D * 4 + b_loc * 8, dtype=torch.uint8, device=dev)
         self.x = self.xy[: b_loc * D * 4].view(torch.float32).view(b_loc, D)
@@ -227,6 +228,8 @@ class GraphedStep:
         self.x.copy_(x_local)
         self.y.copy_(y_local)
         self.graph.replay()
+        if self.peer is not None:  # what the replay just issued on the device (p2p.PeerExchange.last_channel)
+            self.peer.last_channel = 2 if self.with_backward else 1
         self.version += 1
         return self.version
 

@@ -48,6 +48,11 @@ class PeerExchange:
         self._flags = (ctypes.c_uint64 * 16)(*(ptrs + [0] * (16 - len(ptrs))))
         self._bufs = [(ctypes.c_uint64 * 16)(*([p + off for p in ptrs] + [0] * (16 - len(ptrs)))) for off in self.off]
         self.sync = torch.zeros(16, dtype=torch.int32, device=device)   # [call number, arrival counter] per channel
+        # Host-side record of the last channel ISSUED (eagerly or by a graph replay).  Channels 0 and 1 are always
+        # separated by the other one, which is what makes their buffers safe to reuse (csrc/p2p.cu); two scatters in
+        # a row (two backwards of one head without a forward between them) are not, so the second one is declined
+        # and the caller takes the NCCL reduce-scatter instead.  Every rank sees the same call sequence.
+        self.last_channel = -1
         torch.cuda.synchronize(device)
         dist.barrier(group=group)   # every rank's flags are zero before anyone stores to them
 
@@ -58,6 +63,7 @@ class PeerExchange:
         _lib.call("arcface_b200_p2p_exchange", ctypes.c_void_p(src.data_ptr()), bytes_per_peer, src_stride,
                   self._bufs[channel], self._flags, self.rank, self.world, self.slot[channel], channel,
                   ctypes.c_void_p(self.sync.data_ptr()), torch.cuda.current_stream().cuda_stream)
+        self.last_channel = channel
         lo = self.off[channel]
         return self.buf[lo: lo + self.slot[channel] * self.world].view(self.world, self.slot[channel])
 
@@ -70,7 +76,10 @@ class PeerExchange:
 
     def scatter_rows(self, full: torch.Tensor) -> torch.Tensor:
         """full fp32 [R * b_loc, D] (this rank's partial for every rank's rows) -> fp32 [R, b_loc, D]: the partials
-        every rank sent for THIS rank's rows (to be summed by normalize_bwd_x_sum)."""
+        every rank sent for THIS rank's rows (to be summed by normalize_bwd_x_sum); None when the previous exchange
+        was a scatter too (see `last_channel`)."""
+        if self.last_channel == 2:
+            return None
         b_loc = full.shape[0] // self.world
         n = b_loc * self.D * 4
         if n > self.slot[2]:
