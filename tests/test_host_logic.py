@@ -93,3 +93,66 @@ def test_margin_constants_helper():
         cm, sm_, th, mmv = ops.margin_constants(m)
         assert (cm, sm_, th, mmv) == (math.cos(m), math.sin(m), math.cos(math.pi - m), math.sin(math.pi - m) * m)
         assert np.isclose(th, -cm) and np.isclose(mmv, m * sm_)
+
+
+def test_fused_optimizer_rejects_what_it_cannot_update():
+    """FusedHeadAdamW is for fp32 [C, D] CUDA head weights; anything else is an error, not a silent fallback."""
+    import multimodalsimilar_b200 as mm
+
+    p = torch.nn.Parameter(torch.zeros(8, 16))
+    opt = mm.FusedHeadAdamW([p], lr=1e-2)
+    assert opt.param_groups[0]["lr"] == 1e-2 and opt.param_groups[0]["betas"] == (0.9, 0.999)
+    opt.step()                       # no gradient yet: nothing to do
+    p.grad = torch.zeros_like(p)
+    with pytest.raises(RuntimeError, match="CUDA head weights"):
+        opt.step()
+    with pytest.raises(ValueError):
+        mm.FusedHeadAdamW([p], lr=-1.0)
+    # LR schedulers drive it like any torch optimiser
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda step: 0.5)
+    assert abs(opt.param_groups[0]["lr"] - 5e-3) < 1e-12 and sched is not None
+
+
+def test_cosine_index_argument_checks():
+    import multimodalsimilar_b200 as mm
+
+    with pytest.raises(ValueError):
+        mm.CosineIndex(12)            # d must be a multiple of 8
+    index = mm.CosineIndex(16, device="cpu")
+    assert index.ntotal == 0
+    with pytest.raises(ValueError):
+        index.search(torch.zeros(2, 16), 0)
+    with pytest.raises(ValueError):
+        index.search(torch.zeros(2, 16), 129)
+    with pytest.raises(RuntimeError, match="empty"):
+        index.search(torch.zeros(2, 16), 5)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        index.add(torch.zeros(4, 16))   # there is no CPU path
+
+
+def test_stand_in_shard_merge_equals_global_statistics():
+    """The per-shard statistics + finalize merge (the contract of include/arcface_b200.h, restated by the test-only
+    stand-in) reproduce the oracle's global loss / argmax for any contiguous class split."""
+    import numpy as np
+
+    from oracle import arcface_numpy as onp
+    from tests import _cpu_kernels as K
+
+    B, D, C, s, m = 6, 16, 41, 30.0, 0.5
+    x, w, y = onp.synthetic_inputs(B, D, C, seed=3, trained_like=False)
+    z = onp.forward_logits(x, w, y, s, m, False, dtype=np.float64)
+    for R in (1, 2, 3, 5):
+        bounds = [round(i * C / R) for i in range(R + 1)]
+        xt, yt = torch.from_numpy(x), torch.from_numpy(y)
+        xhat, inv_nx, _ = K.normalize_cast(xt)
+        rows = []
+        for r in range(R):
+            lo, hi = bounds[r], bounds[r + 1]
+            ws = torch.from_numpy(w[lo:hi])
+            lm = K.label_margin(xt, ws, inv_nx, None, yt, lo, C, s, m, False)
+            what, inv_nw, rmax, rsum, rarg = K.forward_rows_fused(xhat, ws, lm.label_local, s, lo)
+            rows.append((rmax, rsum, lm.z_label, rarg))
+        lse, arg, zl, omp, loss = K.finalize_rows(torch.stack([t[0] for t in rows]), torch.stack([t[1] for t in rows]),
+                                                  torch.stack([t[3] for t in rows]), torch.stack([t[2] for t in rows]), yt)
+        assert abs(float(loss) - onp.cross_entropy(z, y)) <= 1e-5
+        np.testing.assert_array_equal(arg.numpy(), onp.argmax(z))
