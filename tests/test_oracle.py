@@ -112,3 +112,29 @@ def test_topk_oracle_against_reference_cosines(golden, name):
         np.testing.assert_allclose(np.take_along_axis(cos, idx[:, :kk], axis=1), ref_vals, rtol=0, atol=2e-6)
         if k > kk:
             assert np.all(np.isneginf(vals[:, kk:])) and np.all(idx[:, kk:] == -1)
+
+
+@pytest.mark.parametrize("easy", [False, True])
+def test_oracle_backward_is_the_gradient_of_the_oracle_loss(easy):
+    """Central finite differences of the fp64 oracle loss against oracle.backward (independent of the goldens)."""
+    B, D, C, s, m = 4, 8, 11, 16.0, 0.35
+    x, w, y = onp.synthetic_inputs(B, D, C, seed=13, trained_like=False)
+    x, w = x.astype(np.float64), w.astype(np.float64)
+
+    def loss(xx, ww):
+        return onp.cross_entropy(onp.forward_logits(xx, ww, y, s, m, easy, dtype=np.float64), y)
+
+    dx, dw = onp.backward(x, w, y, s, m, easy, dtype=np.float64)
+    h = 1e-6
+    rng = np.random.RandomState(0)
+    for _ in range(12):
+        b, d = rng.randint(B), rng.randint(D)
+        xp, xm = x.copy(), x.copy()
+        xp[b, d] += h
+        xm[b, d] -= h
+        assert abs((loss(xp, w) - loss(xm, w)) / (2 * h) - dx[b, d]) <= 1e-6 * max(1.0, abs(dx[b, d]))
+        c, d = rng.randint(C), rng.randint(D)
+        wp, wm = w.copy(), w.copy()
+        wp[c, d] += h
+        wm[c, d] -= h
+        assert abs((loss(x, wp) - loss(x, wm)) / (2 * h) - dw[c, d]) <= 1e-6 * max(1.0, abs(dw[c, d]))
