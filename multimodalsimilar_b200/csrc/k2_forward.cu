@@ -163,7 +163,7 @@ __device__ __forceinline__ float4 ldg_stream4(const float* p) {
 }
 
 #ifndef AB_FWD_AUX_WARPS
-#define AB_FWD_AUX_WARPS 8
+#define AB_FWD_AUX_WARPS 16
 #endif
 __device__ __forceinline__ float4 ldg_stream4_hint(const float* p, uint64_t pol) {
     float4 r;

@@ -71,6 +71,10 @@ def probe(name, fn, env=None, seconds=1.5):
     time.sleep(0.5)
 
 
+if os.environ.get("PROBE_ONLY") == "fwd":   # A/B of forward variants: two passes over the fused forward only
+    for _ in range(2):
+        probe("forward fused (K1w + K2)", lambda: ops.forward_rows_fused(xhat, w, lm.label_local, 64.0, 0))
+    sys.exit(0)
 a = torch.randn(8192, 8192, device=dev, dtype=torch.bfloat16)
 b = torch.randn(8192, 8192, device=dev, dtype=torch.bfloat16)
 probe("cuBLAS bf16 8192^3", lambda: torch.matmul(a, b))
