@@ -1,22 +1,33 @@
 #!/usr/bin/env python
 """bench.py -- ArcFace head fwd+bwd samples/s on B200 (BASELINE.json metric), one JSON line on stdout.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config ns|c1|c2|c3|c4|c5_100k|c5_1m|c5_10m]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload: the north-star shape the metric is quoted on -- B=512, D=512, C=1,000,000, s=64, m=0.5, synthetic
-embeddings / labels / xavier-uniform weights.  One step = K1 (normalise + cast of x) + label margin + K1 of the
-class weights fused into K2 (cosine GEMM with margin / softmax / argmax epilogue) + K3 (dC^T, dW, dX GEMMs)
-+ normalise backward; the optimiser is excluded.  At N > 1 the head is class-sharded
-over the ranks (fixed global problem: strong scaling) with three NCCL collectives per step.
+Headline workload: the north-star shape the metric is quoted on -- B=512, D=512, C=1,000,000, s=64, m=0.5,
+synthetic embeddings / labels / xavier-uniform weights.  One step = K1 (normalise + cast of x) + label margin +
+K1 of the class weights fused into K2 (cosine GEMM with margin / softmax / argmax epilogue) + K3 (dC^T, dW, dX
+GEMMs) + normalise backward; the optimiser is excluded.  At N > 1 the head is class-sharded
+over the ranks (fixed global problem: strong scaling) with three exchanges per step (peer memory or NCCL: see
+`exchange`).  The synthetic weight matrix is a function of (seed, class id) only, so every N sees the same problem.
 
-`value`   : device-timed (CUDA events, max over ranks), inputs resident in HBM.
-`e2e`     : the same step through the host-buffer C-ABI call (N=1) / the public module API (N>1), with
-            the pinned-host -> device copy of x / labels and the device -> host read of loss / argmax / dx
-            inside the timed region.
-`roofline`: for the stage with the largest share of the step, timed live with CUDA events.
-`cpu_baseline` (N=1, rank 0): the reference's dense fp32 PyTorch path (oracle/arcface_torch_cpu.py port)
-            on the host cores, on a bounded class sample scaled linearly in C.
+`value`      : device-timed (CUDA events, max over ranks), inputs resident in HBM; mean over the K steps
+               (`ms_per_step`), with the per-step median and best beside it.
+`sustained`  : the same step looped for >= 1 s (the power-capped regime), with the clocks seen there.
+`e2e`        : the same step through the host-buffer C-ABI call (N=1) / the public module API (N>1), with
+               the pinned-host -> device copy of x / labels and the device -> host read of loss / argmax / dx
+               inside the timed region.
+`parity`     : computed IN THIS RUN on every rank: loss / argmax / dx / dW-shard of the timed head against the fp32
+               restatement of the reference evaluated on the same GPU on identical inputs
+               (oracle/arcface_torch_chunked.py, the checker), max over ranks, with the north-star gates.
+`roofline`   : for the stage with the largest share of the step, timed live with CUDA events (N=1).
+`roofline_step`: t_roof / t_step for the whole step against BOTH measured bf16 peaks (burst and sustained);
+               `frac` is the one matching the clocks sampled during the timed region (`regime`).
+`configs`    : the other BASELINE.json configurations (c2..c5), each timed and parity-checked the same way
+               (short runs; not the headline).  --config X makes X the headline instead and skips the others.
+`gpu_reference`: the reference's dense fp32 eager op sequence (oracle/arcface_torch_cpu.py port) timed on the same
+               B200 (N=1, rank 0): the GPU kernel chain to beat, reported, not part of the product.
+`cpu_baseline` (N=1, rank 0): the same port on the host cores, on a bounded class sample scaled linearly in C.
 --impl reference: only that CPU path, as its own JSON line.
 """
 import argparse
@@ -31,11 +42,34 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-WORKLOAD = {"B": 512, "D": 512, "C": 1000000, "s": 64.0, "m": 0.5}
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of this workload on one
-# B200 (profiles/r1_v9_fwd_bwd_full_raw.csv); only meaningful for the single-GPU north-star shape.
-NCU_TRAFFIC_BYTES = {"fwd": 2.543024e9 + 0.999243e9, "k3": 1.399593e9 + 2.114164e9}
+# BASELINE.json `configs` (c1..c5 + the north-star shape the metric is quoted on)
+CONFIGS = {
+    "ns": {"B": 512, "D": 512, "C": 1000000, "s": 64.0, "m": 0.5,
+           "what": "north-star shape (BASELINE.json metric shape)"},
+    "c1": {"B": 64, "D": 512, "C": 1000, "s": 30.0, "m": 0.5, "what": "BASELINE config 1 (the reference's CPU case)"},
+    "c2": {"B": 256, "D": 1792, "C": 100000, "s": 64.0, "m": 0.2,
+           "what": "BASELINE config 2: EfficientNet-B4 embedding head"},
+    "c3": {"B": 512, "D": 1024, "C": 1000000, "s": 64.0, "m": 0.4,
+           "what": "BASELINE config 3: RoBERTa-wwm-ext-large embedding head"},
+    "c4": {"B": 512, "D": 2816, "C": 1000000, "s": 64.0, "m": 0.5,
+           "what": "BASELINE config 4: two-stream multimodal concat embedding"},
+    "c5_100k": {"B": 1024, "D": 512, "C": 100000, "s": 64.0, "m": 0.5, "what": "BASELINE config 5: class sweep, C=100k"},
+    "c5_1m": {"B": 1024, "D": 512, "C": 1000000, "s": 64.0, "m": 0.5, "what": "BASELINE config 5: class sweep, C=1M"},
+    "c5_10m": {"B": 1024, "D": 512, "C": 10000000, "s": 64.0, "m": 0.5, "what": "BASELINE config 5: class sweep, C=10M"},
+}
+EXTRA_CONFIGS = ["c2", "c3", "c4", "c5_100k", "c5_1m", "c5_10m"]
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of the north-star
+# workload on one B200; only meaningful for the single-GPU north-star shape.
+NCU_TRAFFIC = {"fwd": 2.543024e9 + 0.999243e9, "k3": 1.399593e9 + 2.114164e9,
+               "source": "profiles/r1_v9_fwd_bwd_full_raw.csv (ncu --set full, per launch)"}
 METRIC = "arcface_head_fwd_bwd_samples_per_sec_1M_classes"
+WEIGHT_SEED = 1234
+WEIGHT_BLOCK = 65536
+
+# north_star gates
+LOSS_RTOL = 1e-3
+GRAD_ATOL = 2e-2
+LOGIT_ATOL = 2e-2
 
 
 def load_peaks():
@@ -90,7 +124,7 @@ class ClockSampler(threading.Thread):
                     self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
                 except Exception:
                     pass
-                time.sleep(0.02)
+                time.sleep(0.004)
         except Exception as e:  # pragma: no cover
             self.error = repr(e)
 
@@ -107,6 +141,17 @@ class ClockSampler(threading.Thread):
         return out
 
 
+def workload_config(name, cfg, n_gpus, exchange=None):
+    par = "single GPU" if n_gpus == 1 else "class-sharded x%d (PartialFC-style), exchanges over %s" % (
+        n_gpus, {"p2p": "peer-mapped memory (csrc/p2p.cu)", "nccl": "NCCL"}.get(exchange, "peer memory or NCCL"))
+    return {"workload": "ArcFace head fwd+bwd, %s: B=%d D=%d C=%d s=%g m=%g" % (cfg["what"], cfg["B"], cfg["D"], cfg["C"],
+                                                                                cfg["s"], cfg["m"]),
+            "name": name, "global_batch": cfg["B"], "embedding_dim": cfg["D"], "classes": cfg["C"], "parallelism": par,
+            "l2": "inputs exceed L2: fp32 class weights %.2f GB per step over all ranks, no flush needed"
+            % (cfg["C"] * cfg["D"] * 4 / 1e9) if cfg["C"] * cfg["D"] * 4 / max(1, n_gpus) > 126e6 else
+            "weights of one rank fit in L2 (%.0f MB): warm-L2 number" % (cfg["C"] * cfg["D"] * 4 / max(1, n_gpus) / 1e6)}
+
+
 def run_reference(args):
     """The reference's own CPU implementation of the path (port, see oracle/arcface_torch_cpu.py)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -116,7 +161,8 @@ def run_reference(args):
 
     from oracle import arcface_torch_cpu as otc
 
-    w = WORKLOAD
+    name = args.config or "ns"
+    w = CONFIGS[name]
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     total_budget = args.ref_budget
@@ -147,147 +193,229 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_full * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "config": workload_config(name, w, args.gpus),
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus):
-    w = WORKLOAD
-    return {"workload": "ArcFace head fwd+bwd, north-star shape B=%d D=%d C=%d s=%g m=%g (BASELINE.json metric shape)"
-            % (w["B"], w["D"], w["C"], w["s"], w["m"]),
-            "global_batch": w["B"], "embedding_dim": w["D"], "classes": w["C"],
-            "parallelism": "single GPU" if n_gpus == 1 else "class-sharded x%d (PartialFC-style), NCCL" % n_gpus,
-            "l2": "inputs exceed L2: fp32 class weights %.2f GB per step, no flush needed"
-            % (w["C"] * w["D"] * 4 / 1e9)}
-
-
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ref-budget", type=float, default=150.0, help="host seconds the reference arm may spend")
-    ap.add_argument("--classes", type=int, default=None, help="override C (debug only; invalidates the metric)")
-    args = ap.parse_args()
-    if args.classes:
-        WORKLOAD["C"] = args.classes
-    if args.impl == "reference":
-        run_reference(args)
-        return
-    if args.warmup < 3:
-        args.warmup = 3
-
-    import torch
-    import torch.distributed as dist
-
-    import multimodalsimilar_b200 as mm
-    from multimodalsimilar_b200 import ops
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world != args.gpus:
-        raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run for N > 1)" % (args.gpus, world))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-
-    w = WORKLOAD
-    B, D, C, s, m = w["B"], w["D"], w["C"], w["s"], w["m"]
-    peaks = load_peaks()
-    gen = torch.Generator(device="cpu").manual_seed(0)
-    x_host = torch.randn(B, D, generator=gen).pin_memory()
-    y_host = torch.randint(0, C, (B,), generator=gen).pin_memory()
+def class_weights(torch, C, D, lo, hi, dev):
+    """Rows [lo, hi) of the synthetic [C, D] weight matrix (xavier-uniform bound of the FULL matrix, arcface.py:25).
+    The matrix is defined block by block -- WEIGHT_BLOCK classes per block, each from its own Philox stream seeded
+    by the block index -- so a row depends on (seed, class id) only, not on how many ranks share the classes."""
     bound = math.sqrt(6.0 / (C + D))
+    out = torch.empty(hi - lo, D, device=dev)
+    g = torch.Generator(device=dev)
+    b0 = lo // WEIGHT_BLOCK * WEIGHT_BLOCK
+    while b0 < hi:
+        b1 = min(C, b0 + WEIGHT_BLOCK)
+        g.manual_seed(WEIGHT_SEED + b0 // WEIGHT_BLOCK)
+        blk = torch.empty(b1 - b0, D, device=dev).uniform_(-bound, bound, generator=g)
+        a, b = max(b0, lo), min(b1, hi)
+        out[a - lo:b - lo] = blk[a - b0:b - b0]
+        b0 = b1
+    return out
 
-    if world == 1:
-        head = mm.ArcMarginProduct(D, 8, s=s, m=m)
-        head.out_feature = C
-        c_lo, c_hi = 0, C
-    else:
-        # ARCFACE_B200_P2P=0: exchanges through NCCL instead of peer-mapped memory (A/B measurements)
-        head = mm.ShardedArcMarginProduct(D, world, s=s, m=m, use_p2p=os.environ.get("ARCFACE_B200_P2P", "1") != "0")
-        head.out_feature = C
-        head.class_lo, head.class_hi = mm.shard_range(C, world, rank)
-        c_lo, c_hi = head.class_lo, head.class_hi
-    gdev = torch.Generator(device=dev).manual_seed(1234 + rank)
-    head.weight = torch.nn.Parameter(torch.empty(c_hi - c_lo, D, device=dev).uniform_(-bound, bound, generator=gdev))
-    head = head.to(dev)
-    b_loc = B // world
-    x_dev = x_host[rank * b_loc:(rank + 1) * b_loc].to(dev).requires_grad_(True)
-    y_dev = y_host[rank * b_loc:(rank + 1) * b_loc].to(dev)
 
-    def step():
-        x_dev.grad = None
-        head.weight.grad = None
-        loss, pred = head.loss(x_dev, y_dev)
+class Job:
+    """One configuration on this process group: head, deterministic weights, synthetic batch, timing, parity."""
+
+    def __init__(self, torch, dist, mm, name, cfg, world, rank, dev):
+        self.torch, self.dist, self.mm = torch, dist, mm
+        self.name, self.cfg, self.world, self.rank, self.dev = name, cfg, world, rank, dev
+        B, D, C, s, m = cfg["B"], cfg["D"], cfg["C"], cfg["s"], cfg["m"]
+        gen = torch.Generator(device="cpu").manual_seed(0)
+        self.x_host = torch.randn(B, D, generator=gen).pin_memory()
+        self.y_host = torch.randint(0, C, (B,), generator=gen).pin_memory()
+        if world == 1:
+            head = mm.ArcMarginProduct(D, 8, s=s, m=m)
+            head.out_feature = C
+            self.c_lo, self.c_hi = 0, C
+        else:
+            # ARCFACE_B200_P2P=0: exchanges through NCCL instead of peer-mapped memory (A/B measurements)
+            head = mm.ShardedArcMarginProduct(D, world, s=s, m=m, use_p2p=os.environ.get("ARCFACE_B200_P2P", "1") != "0")
+            head.out_feature = C
+            head.class_lo, head.class_hi = mm.shard_range(C, world, rank)
+            self.c_lo, self.c_hi = head.class_lo, head.class_hi
+        head.weight = torch.nn.Parameter(class_weights(torch, C, D, self.c_lo, self.c_hi, dev))
+        self.head = head.to(dev)
+        self.b_loc = B // world
+        lo = rank * self.b_loc
+        self.x_dev = self.x_host[lo:lo + self.b_loc].to(dev).requires_grad_(True)
+        self.y_dev = self.y_host[lo:lo + self.b_loc].to(dev)
+        self.pred = None
+
+    # -- the step
+    def step(self):
+        self.x_dev.grad = None
+        self.head.weight.grad = None
+        loss, self.pred = self.head.loss(self.x_dev, self.y_dev)
         loss.backward()
         return loss
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    def max_over_ranks(v):
-        if world == 1:
+    def max_over_ranks(self, v):
+        if self.world == 1:
             return v
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        loss = step()
-    ev1.record()
-    barrier()
-    clocks = sampler.result()
-    ms_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
-    value = B / (ms_step * 1e-3)
-    loss_value = float(loss.detach())
+    def timed(self, steps, warmup, sample_clocks=True):
+        """`warmup` untimed steps, then `steps` steps between barriers; device time by CUDA events, max over ranks."""
+        torch = self.torch
+        for _ in range(warmup):
+            self.step()
+        self.barrier()
+        sampler = None
+        if sample_clocks:
+            sampler = ClockSampler(self.dev.index or 0)
+            sampler.start()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        self.barrier()
+        evs[0].record()
+        loss = None
+        for i in range(steps):
+            loss = self.step()
+            evs[i + 1].record()
+        self.barrier()
+        clocks = sampler.result() if sampler is not None else None
+        per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(steps))
+        out = {"ms_per_step": self.max_over_ranks(evs[0].elapsed_time(evs[steps]) / steps),
+               "ms_per_step_median": self.max_over_ranks(per[len(per) // 2]),
+               "ms_per_step_best": self.max_over_ranks(per[0]), "loss": float(loss.detach())}
+        if clocks is not None:
+            out["clocks"] = clocks
+        return out
 
-    # ---- kernel launches per step (our kernels only; memset / NCCL not counted)
-    _, n_chunks = ops.backward_plan(B, D, c_hi - c_lo)
-    k3_launches = ops.backward_launches(B, D, c_hi - c_lo)
-    # K1(x), label, K1(w)+K2, combine, finalize, K3, bwd-x, scale_grads -- replayed from one CUDA graph per step
-    launches_per_step = 1 + 1 + 1 + 1 + 1 + k3_launches + 1 + 1
-    if world > 1 and getattr(head, "use_p2p", False):
-        launches_per_step += 3  # the three peer-memory exchange kernels (csrc/p2p.cu) that replace the NCCL collectives
-    gpu_launches = launches_per_step * args.steps
+    def exchange(self):
+        if self.world == 1:
+            return None
+        from multimodalsimilar_b200 import engine
 
-    # ---- end-to-end with host buffers
+        return "p2p" if engine._PEERS.get(self.head) else "nccl"
+
+    # -- roofline of the whole step
+    def roofline_step(self, ms_step, peaks, clocks):
+        cfg = self.cfg
+        B, D = cfg["B"], cfg["D"]
+        c_loc = self.c_hi - self.c_lo
+        flops_alg = 6.0 * B * D * c_loc
+        bytes_alg = 8.0 * c_loc * D + 8.0 * B * D + 24.0 * B
+        t_hbm = bytes_alg / (peaks["hbm_gbs"] * 1e9)
+        t_b = max(flops_alg / (peaks["bf16_tflops"] * 1e12), t_hbm)
+        t_s = max(flops_alg / (peaks["bf16_tflops_sustained"] * 1e12), t_hbm)
+        bound = "tensor" if flops_alg / (peaks["bf16_tflops_sustained"] * 1e12) >= t_hbm else "hbm"
+        regime = "burst"
+        if clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz"):
+            regime = "burst" if clocks["sm_mhz"] >= 0.9 * clocks["sm_max_mhz"] else "sustained"
+        t = ms_step * 1e-3
+        fb, fs = t_b / t, t_s / t
+        if bound == "tensor":
+            ach, peak, unit = flops_alg / t / 1e12, peaks["bf16_tflops" if regime == "burst" else "bf16_tflops_sustained"], "TFLOP/s"
+        else:
+            ach, peak, unit = bytes_alg / t / 1e9, peaks["hbm_gbs"], "GB/s"
+        return {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "regime": regime,
+                "frac": fb if regime == "burst" else fs, "frac_burst": fb, "frac_sustained": fs,
+                "t_roof_burst_ms": t_b * 1e3, "t_roof_sustained_ms": t_s * 1e3, "algorithmic_flops": flops_alg,
+                "algorithmic_bytes": bytes_alg, "executed_flops": 8.0 * B * D * c_loc, "peak_source": peaks["source"],
+                "note": "per rank: the local class shard (1/%d of the classes) for the global batch" % self.world}
+
+    # -- parity against the fp32 restatement of the reference, in this run
+    def parity(self):
+        torch = self.torch
+        from oracle import arcface_torch_chunked as och  # the checker
+
+        cfg = self.cfg
+        B, D, C, s, m = cfg["B"], cfg["D"], cfg["C"], cfg["s"], cfg["m"]
+        loss = self.step()
+        torch.cuda.synchronize()
+        got_loss = float(loss.detach())
+        got_pred = self.pred.clone()
+        got_dx = self.x_dev.grad.clone()
+        got_dw = self.head.weight.grad   # alias of the step's buffer: no step runs until the comparison is done
+        w_full = self.head.weight.detach() if self.world == 1 else class_weights(torch, C, D, 0, C, self.dev)
+        ref = och.head_step_chunked(self.x_host.to(self.dev), w_full, self.y_host.to(self.dev), s, m, False,
+                                    chunk=32768 if B > 512 else 65536, dw_range=(self.c_lo, self.c_hi))
+        del w_full
+        lo = self.rank * self.b_loc
+        rows = slice(lo, lo + self.b_loc)
+        ref_loss = float(ref["loss"])
+        # bf16 noise floor of a logit (SURVEY.md section 7-4): rows whose reference winner leads by less cannot be
+        # expected to keep their argmax under ANY bf16 evaluation
+        noise = LOGIT_ATOL * (s / 30.0) * max(1.0, math.sqrt(512.0 / D))
+        sep = ref["top2_gap"][rows] > 2.0 * noise
+        mism_sep = int((got_pred[sep] != ref["argmax"][rows][sep]).sum())
+        match_all = float((got_pred == ref["argmax"][rows]).float().mean())
+        ddx = got_dx - ref["dx"][rows]
+        ddw = got_dw - ref["dw"]
+        vals = {
+            "loss_rel": abs(got_loss - ref_loss) / max(1.0, abs(ref_loss)),
+            "dx_max_abs": float(ddx.abs().max()), "dx_rel_fro": float(ddx.norm() / ref["dx"][rows].norm().clamp_min(1e-30)),
+            "dw_max_abs": float(ddw.abs().max()), "dw_rel_fro": float(ddw.norm() / ref["dw"].norm().clamp_min(1e-30)),
+            "argmax_mismatch_separated_rows": float(mism_sep), "argmax_mismatch_all_rows_frac": 1.0 - match_all,
+        }
+        n_sep = int(sep.sum())
+        del ref, ddx, ddw
+        if self.world > 1:
+            t = torch.tensor(list(vals.values()) + [-float(n_sep)], dtype=torch.float64, device=self.dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            for k, v in zip(list(vals.keys()), t.tolist()):
+                vals[k] = v
+            n_sep = int(-t[-1].item())   # min over ranks
+        gates = {"loss_rel<=1e-3": vals["loss_rel"] <= LOSS_RTOL,
+                 "argmax_exact_on_separated_rows": vals["argmax_mismatch_separated_rows"] == 0,
+                 "dx_max_abs<=2e-2": vals["dx_max_abs"] <= GRAD_ATOL, "dw_max_abs<=2e-2": vals["dw_max_abs"] <= GRAD_ATOL}
+        out = {"vs": "fp32 restatement of arcface.py:45-63 + CrossEntropyLoss + backward on the same GPU, identical "
+                     "inputs (oracle/arcface_torch_chunked.py); max over ranks",
+               "loss": got_loss, "loss_ref": ref_loss, "separated_rows_per_rank_min": n_sep}
+        out.update(vals)
+        out["argmax_mismatch_separated_rows"] = int(out["argmax_mismatch_separated_rows"])
+        out["gates"] = gates
+        out["ok"] = all(gates.values())
+        torch.cuda.empty_cache()
+        return out
+
+    def close(self):
+        from multimodalsimilar_b200 import engine
+
+        engine.drop_plan(self.head)
+        self.torch.cuda.synchronize()
+        del self.head
+        self.torch.cuda.empty_cache()
+
+
+def e2e_measure(job, ops, steps):
+    """The step through host buffers: pinned x / labels in, loss / argmax / dx out, copies inside the timed region."""
+    torch = job.torch
+    cfg = job.cfg
+    B, D, C, s, m = cfg["B"], cfg["D"], cfg["C"], cfg["s"], cfg["m"]
+    world, rank, dev, b_loc, head = job.world, job.rank, job.dev, job.b_loc, job.head
     h2d = b_loc * D * 4 + b_loc * 8
     d2h = 4 + b_loc * 8 + b_loc * D * 4
-    e2e_steps = max(5, min(args.steps, 50))
     if world == 1:
         loss_h = torch.zeros(1).pin_memory()
         arg_h = torch.zeros(B, dtype=torch.int64).pin_memory()
         dx_h = torch.zeros(B, D).pin_memory()
+        head.weight.grad = None
+        from multimodalsimilar_b200 import engine
+
+        engine.drop_plan(head)   # the graph's private pool holds a dW of its own
+        torch.cuda.empty_cache()
         dw = torch.empty(C, D, device=dev)
         ws = torch.empty(ops.step_workspace_bytes(B, D, C), dtype=torch.uint8, device=dev)
         wdet = head.weight.detach()
-        head.weight.grad = None
-        torch.cuda.empty_cache()
 
         def e2e_step():
-            ops.step_host(x_host, y_host, wdet, s, m, False, 1.0, loss_h, arg_h, dx_h, dw, ws)
+            ops.step_host(job.x_host, job.y_host, wdet, s, m, False, 1.0, loss_h, arg_h, dx_h, dw, ws)
     else:
-        xl_host = x_host[rank * b_loc:(rank + 1) * b_loc].contiguous().pin_memory()
-        yl_host = y_host[rank * b_loc:(rank + 1) * b_loc].contiguous().pin_memory()
+        xl_host = job.x_host[rank * b_loc:(rank + 1) * b_loc].contiguous().pin_memory()
+        yl_host = job.y_host[rank * b_loc:(rank + 1) * b_loc].contiguous().pin_memory()
         dx_h = torch.zeros(b_loc, D).pin_memory()
         arg_h = torch.zeros(b_loc, dtype=torch.int64).pin_memory()
 
@@ -303,88 +431,61 @@ def main():
 
     for _ in range(3):
         e2e_step()
-    barrier()
+    job.barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    for _ in range(steps):
         e2e_step()
     torch.cuda.synchronize()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
-    barrier()
-    e2e = {"value": B / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d * world,
-           "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_ms,
-           "api": "arcface_b200_step_host (C ABI, pinned host buffers)" if world == 1 else
-                  "ShardedArcMarginProduct.loss + backward with pinned host copies"}
+    e2e_ms = job.max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
+    job.barrier()
+    return {"value": B / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d * world,
+            "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_ms,
+            "api": "arcface_b200_step_host (C ABI, pinned host buffers)" if world == 1 else
+                   "ShardedArcMarginProduct.loss + backward with pinned host copies"}
 
-    # ---- stage breakdown + roofline (rank 0 view; live CUDA events, same inputs)
-    c_loc = c_hi - c_lo
-    stages = stage_times(torch, ops, head, x_host, y_host, dev, s, m, c_lo, C, max(5, min(args.steps, 30)))
-    flops_alg = 6.0 * B * D * c_loc
-    bytes_alg = 8.0 * c_loc * D + 8.0 * B * D + 24.0 * B
-    p_tensor = peaks["bf16_tflops_sustained"]
-    t_tensor = flops_alg / (p_tensor * 1e12)
-    t_hbm = bytes_alg / (peaks["hbm_gbs"] * 1e9)
-    t_roof = max(t_tensor, t_hbm)
-    comp_ms = stages["k1_x"] + stages["label"] + stages["fwd"] + stages["k3"] + stages["bwd_x"]
-    roofline_step = {"bound": "tensor" if t_tensor >= t_hbm else "hbm",
-                     "achieved": flops_alg / (ms_step * 1e-3) / 1e12, "peak": p_tensor, "unit": "TFLOP/s",
-                     "frac": t_roof / (ms_step * 1e-3), "t_roof_ms": t_roof * 1e3,
-                     "algorithmic_flops": flops_alg, "algorithmic_bytes": bytes_alg,
-                     "executed_flops": 8.0 * B * D * c_loc, "peak_source": peaks["source"] + " (sustained bf16)"}
-    fwd_hbm_s = (c_loc * D * 6.0 + 4.0 * c_loc) / (peaks["hbm_gbs"] * 1e9)   # fp32 W in, bf16 What + 1/||w|| out
-    fwd_tensor_s = 2.0 * B * D * c_loc / (p_tensor * 1e12)
-    fwd_cand = (("hbm", (c_loc * D * 6.0 + 4.0 * c_loc) / 1e9, "GB/s", peaks["hbm_gbs"]) if fwd_hbm_s >= fwd_tensor_s
-                else ("tensor", 2.0 * B * D * c_loc / 1e12, "TFLOP/s", p_tensor))
-    cand = {
-        "fwd": fwd_cand + ("K1(w)+K2 forward: in-kernel weight normalise/cast + cosine GEMM + softmax epilogue",),
-        "k3": ("tensor", 4.0 * B * D * c_loc / 1e12, "TFLOP/s", p_tensor,
-               "K3 backward (dC^T producer + dW GEMM + dX GEMM, %s)"
-               % ("one persistent launch, dC^T through an L2 ring" if k3_launches == 1 else "%d chunks" % n_chunks)),
-    }
-    top = max(cand, key=lambda k: stages[k])
-    bnd, work, unit, peak, name = cand[top]
-    achieved = work / (stages[top] * 1e-3)
-    roofline = {"kernel": name, "bound": bnd, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
-                "traffic": NCU_TRAFFIC_BYTES[top] if (world == 1 and not args.classes) else None,
-                "traffic_source": "profiles/r1_v9_fwd_bwd_full_raw.csv (ncu --set full, per launch)",
-                "ms_per_launch_group": stages[top], "share_of_step": stages[top] / comp_ms,
-                "peak_source": peaks["source"]}
 
-    cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
-        from oracle import arcface_torch_cpu as otc
+def gpu_reference(job):
+    """The reference's dense fp32 eager op chain (the port bench.py's reference arm times on the CPU) on this B200."""
+    torch = job.torch
+    from oracle import arcface_torch_cpu as otc
 
-        torch.set_num_threads(os.cpu_count() or 1)
-        cpu_baseline = otc.time_head_step(B, D, C, s, m, budget_s=20.0)
-        cpu_baseline = {k: cpu_baseline[k] for k in ("value", "unit", "cores", "kind", "sample")}
-
-    if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline,
-            "roofline_step": roofline_step, "stages_ms": stages, "loss": loss_value,
-        }
-        if cpu_baseline is not None:
-            line["cpu_baseline"] = cpu_baseline
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        # Captured graphs hold NCCL kernels: release them before the communicator goes away, and leave without
-        # running destructors (destroy_process_group() with live graphs was seen to hang after the line was printed).
-        from multimodalsimilar_b200 import engine
-
-        engine.drop_plan(head)
-        torch.cuda.synchronize()
-        dist.barrier()
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+    cfg = job.cfg
+    B, D, C, s, m = cfg["B"], cfg["D"], cfg["C"], cfg["s"], cfg["m"]
+    dev = job.dev
+    torch.backends.cuda.matmul.allow_tf32 = False  # the reference never enables TF32 (SURVEY.md section 2.1)
+    x, y = job.x_host.to(dev), job.y_host.to(dev)
+    w = job.head.weight.detach()
+    c_used = C
+    while True:
+        try:
+            ws, ys = w[:c_used], y.clamp_max(c_used - 1)
+            otc.head_step(x, ws, ys, s, m)
+            torch.cuda.synchronize()
+            best = float("inf")
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                otc.head_step(x, ws, ys, s, m)
+                e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            break
+        except torch.OutOfMemoryError:
+            torch.cuda.empty_cache()
+            c_used //= 2
+            if c_used < 1024:
+                return {"unavailable": "out of memory"}
+    torch.cuda.empty_cache()
+    ms = best * (C / c_used)
+    return {"value": B / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "kind": "port",
+            "what": "dense fp32 PyTorch eager op sequence of arcface.py:45-63 + CrossEntropyLoss + backward "
+                    "(oracle/arcface_torch_cpu.py) on the same B200, TF32 off, best of 3",
+            "classes_timed": c_used, "extrapolated": c_used != C}
 
 
 def stage_times(torch, ops, head, x_host, y_host, dev, s, m, c_lo, c_total, iters):
     """Average milliseconds of each stage of one rank's step (whole batch, local class shard), timed with
-    CUDA events on the launching stream, after warm-up.  The collectives of the sharded head are not part
-    of this breakdown."""
+    CUDA events on the launching stream, after warm-up (eager launches: N = 1 only)."""
     x = x_host.to(dev)
     y = y_host.to(dev)
     w = head.weight.detach()
@@ -411,7 +512,199 @@ def stage_times(torch, ops, head, x_host, y_host, dev, s, m, c_lo, c_total, iter
         if it >= 2:
             for i, n in enumerate(names):
                 acc[n] += ev[i].elapsed_time(ev[i + 1])
+    del dw
     return {n: acc[n] / iters for n in names}
+
+
+def dominant_kernel_roofline(job, ops, peaks, stages, regime, traffic_ok):
+    cfg = job.cfg
+    B, D = cfg["B"], cfg["D"]
+    c_loc = job.c_hi - job.c_lo
+    p_tensor = peaks["bf16_tflops" if regime == "burst" else "bf16_tflops_sustained"]
+    _, n_chunks = ops.backward_plan(B, D, c_loc)
+    k3_launches = ops.backward_launches(B, D, c_loc)
+    comp_ms = sum(stages.values())
+    fwd_bytes = c_loc * D * 6.0 + 4.0 * c_loc   # fp32 W in, bf16 What + 1/||w|| out
+    fwd_hbm_s = fwd_bytes / (peaks["hbm_gbs"] * 1e9)
+    fwd_tensor_s = 2.0 * B * D * c_loc / (p_tensor * 1e12)
+    fwd_cand = (("hbm", fwd_bytes / 1e9, "GB/s", peaks["hbm_gbs"]) if fwd_hbm_s >= fwd_tensor_s
+                else ("tensor", 2.0 * B * D * c_loc / 1e12, "TFLOP/s", p_tensor))
+    cand = {
+        "fwd": fwd_cand + ("K1(w)+K2 forward: in-kernel weight normalise/cast + cosine GEMM + softmax epilogue",),
+        "k3": ("tensor", 4.0 * B * D * c_loc / 1e12, "TFLOP/s", p_tensor,
+               "K3 backward (dC^T producer + dW GEMM + dX GEMM, %s)"
+               % ("one persistent launch, dC^T through an L2 ring" if k3_launches == 1 else "%d chunks" % n_chunks)),
+    }
+    top = max(cand, key=lambda k: stages[k])
+    bnd, work, unit, peak, name = cand[top]
+    achieved = work / (stages[top] * 1e-3)
+    return {"kernel": name, "bound": bnd, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
+            "peak_regime": regime, "traffic": NCU_TRAFFIC[top] if traffic_ok else None,
+            "traffic_source": NCU_TRAFFIC["source"], "ms_per_launch_group": stages[top],
+            "share_of_step": stages[top] / comp_ms, "peak_source": peaks["source"]}
+
+
+def launches_per_step(job, ops):
+    """Our kernels per step (memset / copy / NCCL nodes not counted): K1(x), label, K1(w)+K2, combine, finalize, K3,
+    bwd-x, scale_grads -- replayed from one CUDA graph -- plus the three peer-memory exchange kernels when used."""
+    cfg = job.cfg
+    n = 1 + 1 + 1 + 1 + 1 + ops.backward_launches(cfg["B"], cfg["D"], job.c_hi - job.c_lo) + 1 + 1
+    if cfg["D"] > 512:
+        n += 1   # K1 of the class weights is its own launch when the in-kernel normaliser does not cover D
+    if job.exchange() == "p2p":
+        n += 3
+    return n
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS), help="headline configuration (default: ns, "
+                    "followed by short runs of the other BASELINE configs)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other BASELINE configs")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="host seconds the reference arm may spend")
+    ap.add_argument("--classes", type=int, default=None, help="override C (debug only; invalidates the metric)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.classes:
+            CONFIGS[args.config or "ns"]["C"] = args.classes
+        run_reference(args)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+
+    import multimodalsimilar_b200 as mm
+    from multimodalsimilar_b200 import ops
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run for N > 1)" % (args.gpus, world))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    head_name = args.config or "ns"
+    cfg = dict(CONFIGS[head_name])
+    if args.classes:
+        cfg["C"] = args.classes
+    peaks = load_peaks()
+
+    job = Job(torch, dist, mm, head_name, cfg, world, rank, dev)
+    B, D, C = cfg["B"], cfg["D"], cfg["C"]
+    t = job.timed(args.steps, args.warmup)
+    ms_step = t["ms_per_step"]
+    value = B / (ms_step * 1e-3)
+    clocks = t["clocks"]
+    roof_step = job.roofline_step(ms_step, peaks, clocks)
+    exchange = job.exchange()
+
+    sustained = None
+    if not args.no_sustained:
+        n_sus = int(min(4000, max(args.steps, math.ceil(1000.0 / ms_step))))
+        ts = job.timed(n_sus, 0)
+        sustained = {"steps": n_sus, "ms_per_step": ts["ms_per_step"], "ms_per_step_median": ts["ms_per_step_median"],
+                     "value": B / (ts["ms_per_step"] * 1e-3), "clocks": ts["clocks"],
+                     "frac_sustained": roof_step["t_roof_sustained_ms"] / ts["ms_per_step"],
+                     "note": "the same step looped back to back for >= 1 s right after the timed region"}
+
+    parity = None if args.no_parity else job.parity()
+    gpu_launches = launches_per_step(job, ops) * args.steps
+
+    e2e = e2e_measure(job, ops, max(5, min(args.steps, 50)))
+
+    stages = roofline = gpu_ref = cpu_baseline = None
+    if world == 1:
+        stages = stage_times(torch, ops, job.head, job.x_host, job.y_host, dev, cfg["s"], cfg["m"], 0, C,
+                             max(5, min(args.steps, 30)))
+        roofline = dominant_kernel_roofline(job, ops, peaks, stages, roof_step["regime"],
+                                            head_name == "ns" and not args.classes)
+        gpu_ref = gpu_reference(job)
+    job.close()
+    del job
+
+    extra = None
+    if args.config is None and not args.no_extra and not args.classes:
+        extra = {}
+        for name in EXTRA_CONFIGS:
+            c = CONFIGS[name]
+            try:
+                j = Job(torch, dist, mm, name, c, world, rank, dev)
+                tt = j.timed(10, 6, sample_clocks=True)
+                r = {"B": c["B"], "D": c["D"], "C": c["C"], "s": c["s"], "m": c["m"], "ms_per_step": tt["ms_per_step"],
+                     "ms_per_step_median": tt["ms_per_step_median"], "ms_per_step_best": tt["ms_per_step_best"],
+                     "value": c["B"] / (tt["ms_per_step"] * 1e-3), "unit": "samples/s", "steps": 10, "warmup": 6,
+                     "clocks": tt["clocks"], "roofline_step": j.roofline_step(tt["ms_per_step"], peaks, tt["clocks"]),
+                     "exchange": j.exchange(), "k3_launches": ops.backward_launches(c["B"], c["D"], j.c_hi - j.c_lo),
+                     "workload": c["what"]}
+                if not args.no_parity:
+                    r["parity"] = j.parity()
+                extra[name] = r
+                j.close()
+                del j
+            except Exception as e:  # noqa: BLE001 -- one configuration failing must not lose the headline line
+                extra[name] = {"error": repr(e)[:300]}
+                torch.cuda.empty_cache()
+
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import arcface_torch_cpu as otc
+
+        torch.set_num_threads(os.cpu_count() or 1)
+        cpu_baseline = otc.time_head_step(B, D, C, cfg["s"], cfg["m"], budget_s=20.0)
+        cpu_baseline = {k: cpu_baseline[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "ms_per_step_median": t["ms_per_step_median"],
+            "ms_per_step_best": t["ms_per_step_best"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(head_name, cfg, world, exchange),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline_step": roof_step, "loss": t["loss"],
+        }
+        if exchange is not None:
+            line["exchange"] = exchange
+        if roofline is not None:
+            line["roofline"] = roofline
+        else:
+            # N > 1: no per-kernel breakdown is taken (an eager, host-bound one would not describe the replayed graph);
+            # the step-level figure of the rank's shard stands in
+            line["roofline"] = {k: roof_step[k] for k in ("bound", "achieved", "peak", "unit", "frac")}
+            line["roofline"]["traffic"] = None
+            line["roofline"]["kernel"] = "whole step of one rank (class shard)"
+        if stages is not None:
+            line["stages_ms"] = stages
+        if sustained is not None:
+            line["sustained"] = sustained
+        if parity is not None:
+            line["parity"] = parity
+        if gpu_ref is not None:
+            line["gpu_reference"] = gpu_ref
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        if extra is not None:
+            line["configs"] = extra
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        # Captured graphs hold NCCL kernels: leave without running destructors (destroy_process_group() with live
+        # graphs was seen to hang after the line was printed).
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <stdlib.h>
 
 #include "../../include/arcface_b200.h"
 
@@ -48,6 +49,14 @@ int32_t make_tmap_store(CUtensorMap* out, const void* base, int elem_bytes, uint
 // buffers that can be double-buffered).
 int32_t make_tmap_store_box(CUtensorMap* out, const void* base, int elem_bytes, uint64_t cols, uint64_t rows,
                             uint64_t row_stride_elems, int box_bytes);
+
+// Environment knobs exist in diagnostic builds only (make DIAG=1 -> libarcface_b200_diag.so); the release library
+// never reads the environment.
+#ifdef ARCFACE_B200_DIAG
+static inline const char* diag_env(const char* name) { return getenv(name); }
+#else
+static inline const char* diag_env(const char*) { return nullptr; }
+#endif
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

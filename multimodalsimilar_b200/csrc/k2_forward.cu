@@ -528,7 +528,7 @@ static void fwd_partition(int B, int64_t C, int nsm, int* m_tiles, int* n_tiles,
 // CTA-pair forward: usable when the 256-row Xhat slice fits in shared memory (D <= 512) and the device has
 // at least one pair of SMs.  ARCFACE_B200_FWD_IMPL=generic forces the streaming kernel (A/B measurements).
 static bool fwd_use_pairs(int D, int nsm) {
-    const char* v = getenv("ARCFACE_B200_FWD_IMPL");
+    const char* v = diag_env("ARCFACE_B200_FWD_IMPL");
     if (v != nullptr && strcmp(v, "generic") == 0) return false;
     return (D + pr::BK - 1) / pr::BK <= pr::MAX_KBLOCKS && nsm >= 2;
 }
@@ -576,18 +576,19 @@ static int32_t launch_fwd_pairs(const uint16_t* xhat, const uint16_t* what, cons
     p.D = D; p.w = w; p.what = reinterpret_cast<__nv_bfloat16*>(const_cast<uint16_t*>(what));
     p.inv_nw = inv_nw; p.ready = ready;
     p.debug = 0;
-    if (const char* dbg = getenv("ARCFACE_B200_FWD_DEBUG")) p.debug = atoi(dbg);
+    if (const char* dbg = diag_env("ARCFACE_B200_FWD_DEBUG")) p.debug = atoi(dbg);
     if (p.debug == 2) p.core.s_blocks = 0;  // measurements only: helper warps alone
     p.pf_dist = 0;
-    if (const char* pf = getenv("ARCFACE_B200_FWD_PF")) p.pf_dist = atoi(pf);
+    if (const char* pf = diag_env("ARCFACE_B200_FWD_PF")) p.pf_dist = atoi(pf);
     p.evict_first = 0;
-    if (const char* ef = getenv("ARCFACE_B200_FWD_EVICT")) p.evict_first = atoi(ef);
+    if (const char* ef = diag_env("ARCFACE_B200_FWD_EVICT")) p.evict_first = atoi(ef);
     CUtensorMap tmS, tmR;
     if (int32_t rc = make_tmap_kmajor(&tmS, what, D, C_local, D, pr::ROWS)) return rc;
     if (int32_t rc = make_tmap_kmajor(&tmR, xhat, D, B, D, pr::ROWS)) return rc;
-    // measurements only (ARCFACE_B200_FWD_PROF=1): where each role waits; synchronises and prints to stderr
+#ifdef ARCFACE_B200_DIAG
+    // diagnostic build only (ARCFACE_B200_FWD_PROF=1): where each role waits; allocates, synchronises, prints to stderr
     static unsigned long long* prof_dev = nullptr;
-    const char* pe = getenv("ARCFACE_B200_FWD_PROF");
+    const char* pe = diag_env("ARCFACE_B200_FWD_PROF");
     const bool prof = pe != nullptr && atoi(pe) == 1;
     const int n_cta = 2 * groups * p.core.n_res;
     if (prof) {
@@ -596,7 +597,9 @@ static int32_t launch_fwd_pairs(const uint16_t* xhat, const uint16_t* what, cons
         p.core.prof = prof_dev;
         p.core.prof_cta = 0;
     }
+#endif
     const int32_t rc = pr::launch_pair<P>(tmS, tmR, tmS, p, groups, 0, st);
+#ifdef ARCFACE_B200_DIAG
     if (prof && rc == ARCFACE_B200_OK) {
         static unsigned long long host[512 * 16];
         AB_CHECK_CUDA(cudaStreamSynchronize(st));
@@ -612,6 +615,7 @@ static int32_t launch_fwd_pairs(const uint16_t* xhat, const uint16_t* what, cons
                         "MMA: operands %.0f, free accumulator %.0f | epilogue: accumulator %.0f, inside tile %.0f\n",
                 n, a[7] / n, a[6] / n, a[0] / n, a[1] / n, a[2] / (n / 2), a[3] / (n / 2), a[4] / n, a[5] / n);
     }
+#endif
     return rc;
 }
 
@@ -675,7 +679,7 @@ extern "C" int32_t arcface_b200_forward_stats_fused(const uint16_t* xhat, const 
     if (int32_t rc = check_gemm_shape("forward_stats_fused", B, D, C_local)) return rc;
     AB_REQUIRE(aligned16(w) && aligned16(what) && aligned16(workspace), ARCFACE_B200_E_LAYOUT,
                "forward_stats_fused: pointers must be 16-byte aligned");
-    const char* impl = getenv("ARCFACE_B200_FWD_IMPL");
+    const char* impl = diag_env("ARCFACE_B200_FWD_IMPL");
     const bool split = impl != nullptr && strcmp(impl, "split") == 0;  // A/B: K1 and K2 as two launches
     if (!fwd_use_pairs(D, sm_count()) || split) {
         // shapes the in-kernel normaliser does not cover: the same two steps as separate launches

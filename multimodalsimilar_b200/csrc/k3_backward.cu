@@ -1111,8 +1111,8 @@ static int fused_max_pairs(int nsm) {
     return cached[dev] > 0 ? cached[dev] : 0;
 }
 
-static bool env_is(const char* name, const char* value) {
-    const char* v = getenv(name);
+static bool env_is(const char* name, const char* value) {  // diagnostic builds only: always false in the release library
+    const char* v = diag_env(name);
     return v != nullptr && strcmp(v, value) == 0;
 }
 
@@ -1146,7 +1146,7 @@ static BwdPlan plan_backward(int B, int D, int64_t C, int nsm) {
         const int dx_unit = (tiles + 1) / 2;           // CTA pairs per dX split
         const int pairs = fused_max_pairs(nsm);
         int a = 0, b = 0, c = 0;
-        if (const char* v = getenv("ARCFACE_B200_BWD_SPLIT")) sscanf(v, "%d,%d,%d", &a, &b, &c);
+        if (const char* v = diag_env("ARCFACE_B200_BWD_SPLIT")) sscanf(v, "%d,%d,%d", &a, &b, &c);
         if (a <= 0 || b <= 0 || c <= 0 || a + b + c > pairs) {
             // default shares, from the per-tile cycle counts of the roles (ARCFACE_B200_BWD_PROF): the dW role is
             // the slowest per tile (fp32 output staged through shared memory), the dX role the fastest
@@ -1161,7 +1161,7 @@ static BwdPlan plan_backward(int B, int D, int64_t C, int nsm) {
             pl.fused = true;
             pl.n_dc = a; pl.n_dw = b; pl.n_dx = c;
             int slots = 64;
-            if (const char* v = getenv("ARCFACE_B200_BWD_RING")) slots = atoi(v);
+            if (const char* v = diag_env("ARCFACE_B200_BWD_RING")) slots = atoi(v);
             const int min_slots = 2 * (a / n_res_dc) + 2;  // producers may run a tile or two ahead of the consumers
             if (slots < min_slots) slots = min_slots;
             if (slots > pl.n_blocks) slots = pl.n_blocks;
@@ -1185,7 +1185,7 @@ static BwdPlan plan_backward(int B, int D, int64_t C, int nsm) {
     const int64_t c_round = ((C + 127) / 128) * 128;
     int64_t chunk;
     size_t cap = generic ? (size_t(64) << 20) : (size_t(2048) << 20);
-    if (const char* v = getenv("ARCFACE_B200_BWD_CHUNK_MB")) {
+    if (const char* v = diag_env("ARCFACE_B200_BWD_CHUNK_MB")) {
         const long mb = atol(v);
         if (mb >= 1) cap = static_cast<size_t>(mb) << 20;
     }
@@ -1372,7 +1372,8 @@ extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* x
         if (int32_t rc = make_tmap_mnmajor(&tm_ring_mn, dct, B, ring_rows, pl.Bp)) return rc;
         const size_t smem = fused_smem_bytes();
         const int grid = 2 * (pl.n_dc + pl.n_dw + pl.n_dx);
-        // measurements only: ARCFACE_B200_BWD_PROF=1 prints where each role's warps waited (synchronises!)
+#ifdef ARCFACE_B200_DIAG
+        // diagnostic build only: ARCFACE_B200_BWD_PROF=1 prints where each role's warps waited (allocates, synchronises)
         static unsigned long long* prof_dev = nullptr;
         const bool prof = env_is("ARCFACE_B200_BWD_PROF", "1");
         if (prof) {
@@ -1382,9 +1383,11 @@ extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* x
             fp.dw.core.prof = prof_dev; fp.dw.core.prof_cta = 2 * pl.n_dc;
             fp.dx.prof = prof_dev; fp.dx.prof_cta = 2 * (pl.n_dc + pl.n_dw);
         }
+#endif
         fz::bwd_fused_kernel<<<grid, pr::THREADS, smem, st>>>(tm_w_k, tm_x_k, tm_ring_out, tm_ring_k, tm_xt_k, tm_dw_out,
                                                              tm_ring_mn, tm_w_mn, tm_dx_out, fp);
         AB_CHECK_CUDA(cudaGetLastError());
+#ifdef ARCFACE_B200_DIAG
         if (prof) {
             static unsigned long long host[2 * fz::MAX_PAIRS * 16];
             AB_CHECK_CUDA(cudaStreamSynchronize(st));
@@ -1425,6 +1428,7 @@ extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* x
                 }
             }
         }
+#endif
         return ARCFACE_B200_OK;
     }
 

@@ -53,6 +53,37 @@ class FwdState:
     label_local: torch.Tensor
 
 
+class LabelGuard:
+    """Out-of-range labels without a host sync in the step.
+
+    The reference raises from `one_hot.scatter_` (arcface.py:59) when a label is outside [0, C).  Here
+    `label_margin` raises a device flag instead; reading it synchronously would stall every step (and is impossible
+    inside a replayed CUDA graph), so the flag is copied to pinned host memory as part of the step and examined at
+    the START of the next call of the same head: a bad label raises IndexError one step late instead of training on
+    silently.  `validate_labels=True` keeps the synchronous check (eager launches, one sync per step)."""
+
+    def __init__(self):
+        self.host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.event = torch.cuda.Event()
+        self.armed = False
+
+    def post(self, bad_flag: torch.Tensor) -> None:
+        """Queue (or, under stream capture, record into the graph) the flag's copy to the host."""
+        self.host.copy_(bad_flag, non_blocking=True)
+
+    def mark(self) -> None:
+        self.event.record()
+        self.armed = True
+
+    def check(self, c_total: int) -> None:
+        if self.armed and self.event.query():
+            self.armed = False
+            if int(self.host[0]) != 0:
+                self.host.zero_()
+                raise IndexError("ArcMarginProduct: a label of an earlier step was outside [0, %d) (detected one step "
+                                 "late; construct the head with validate_labels=True to fail in the same step)" % c_total)
+
+
 def _world(group) -> int:
     return 1 if group is None else dist.get_world_size(group)
 
@@ -191,10 +222,10 @@ class GraphedStep:
     WARMUP = 2
 
     def __init__(self, K, group, w: torch.Tensor, b_loc: int, cfg: StepConfig, with_backward: bool, w_cache=None,
-                 peer=None):
+                 peer=None, guard=None):
         dev = w.device
         D = w.shape[1]
-        self.K, self.group, self.cfg, self.peer = K, group, cfg, peer
+        self.K, self.group, self.cfg, self.peer, self.guard = K, group, cfg, peer, guard
         # static inputs as views of one buffer laid out (x | labels): the sharded gather sends it as is
         self.xy = torch.zeros(b_loc * D * 4 + b_loc * 8, dtype=torch.uint8, device=dev)
         self.x = self.xy[: b_loc * D * 4].view(torch.float32).view(b_loc, D)
@@ -217,6 +248,8 @@ class GraphedStep:
         self.dx = self.dw = None
         with torch.cuda.graph(self.graph):
             self.st = forward_eager(K, group, self.x, w, self.y, cfg, self.xy, w_cache, peer)
+            if guard is not None:
+                guard.post(self.st.bad_flag)   # a memcpy node of the graph: the flag reaches the host with every replay
             if with_backward:
                 self.dx, self.dw = backward_eager(K, group, self.x, self.st, self.one, cfg, True, peer)
 
@@ -228,6 +261,8 @@ class GraphedStep:
         self.x.copy_(x_local)
         self.y.copy_(y_local)
         self.graph.replay()
+        if self.guard is not None:
+            self.guard.mark()
         if self.peer is not None:  # what the replay just issued on the device (p2p.PeerExchange.last_channel)
             self.peer.last_channel = 2 if self.with_backward else 1
         self.version += 1
@@ -260,12 +295,26 @@ class _GraphedCE(torch.autograd.Function):
         return dx, dw, None, None, None
 
 
-class _EagerCE(torch.autograd.Function):
+class ArcFaceCEFunction(torch.autograd.Function):
+    """loss, argmax = ArcFaceCEFunction.apply(x, weight, label, kernels, group, cfg, validate_labels[, w_cache, peer,
+    guard]) -- the autograd.Function both modules run (eagerly; `_GraphedCE` is its CUDA-graph twin).
+
+    forward : K1 (x), label margin, K1 (weight) fused into K2, combine, [exchange], finalize
+              (arcface.py:45-63 + the call sites' mean CrossEntropyLoss and argmax)
+    backward: K3 (dC^T producer, dW GEMM, dX GEMM), [reduce-scatter], normalise backward for x
+    Saved for backward: xhat / xhat^T / what (bf16), the inverse norms, lse, 1 - p_label, dphi, labels -- no B x C
+    tensor.  `kernels` is `multimodalsimilar_b200.ops`, `group` None (one GPU) or the class-shard process group,
+    `cfg` a StepConfig."""
+
     @staticmethod
-    def forward(ctx, x, w, label, K, group, cfg, validate_labels, w_cache=None, peer=None):
+    def forward(ctx, x, w, label, K, group, cfg, validate_labels, w_cache=None, peer=None, guard=None):
         st = forward_eager(K, group, x, w, label, cfg, None, w_cache, peer)
-        if validate_labels and int(st.bad_flag.item()) != 0:
-            raise IndexError("ArcMarginProduct: a label is outside [0, %d)" % cfg.c_total)
+        if validate_labels:
+            if int(st.bad_flag.item()) != 0:
+                raise IndexError("ArcMarginProduct: a label is outside [0, %d)" % cfg.c_total)
+        elif guard is not None:
+            guard.post(st.bad_flag)
+            guard.mark()
         ctx.save_for_backward(x, st.inv_nx, st.xhat, st.xhat_t, st.what, st.inv_nw, st.lse, st.omp, st.dphi,
                               st.label_local)
         ctx.meta = (K, group, cfg, st.B, peer)
@@ -283,7 +332,10 @@ class _EagerCE(torch.autograd.Function):
             dx = None
         else:
             dx, dw = backward_eager(K, group, x, st, grad_loss, cfg, ctx.needs_input_grad[0], peer)
-        return dx, (dw if ctx.needs_input_grad[1] else None), None, None, None, None, None, None, None
+        return dx, (dw if ctx.needs_input_grad[1] else None), None, None, None, None, None, None, None, None
+
+
+_EagerCE = ArcFaceCEFunction
 
 
 # per-head graph state lives outside the module's __dict__ so that torch.save(model) keeps working
@@ -294,6 +346,9 @@ _W_CACHE: "weakref.WeakKeyDictionary[Any, tuple]" = weakref.WeakKeyDictionary()
 
 # head -> PeerExchange (csrc/p2p.cu) or False when symmetric memory is unavailable for its group
 _PEERS: "weakref.WeakKeyDictionary[Any, Any]" = weakref.WeakKeyDictionary()
+
+# head -> LabelGuard (asynchronous out-of-range-label check)
+_GUARDS: "weakref.WeakKeyDictionary[Any, LabelGuard]" = weakref.WeakKeyDictionary()
 
 
 def _peer_for(head, group, x):
@@ -337,27 +392,33 @@ def run_step(head, K, group, x, w, label, cfg: StepConfig, validate_labels: bool
     if cache is not None and x.is_cuda and cache[2] == w._version and cache[3] == w.data_ptr():
         w_cache = (cache[0], cache[1])
     peer = _peer_for(head, group, x) if (group is not None and x.is_cuda and getattr(head, "use_p2p", False)) else None
+    guard = None
+    if x.is_cuda and not validate_labels:
+        guard = _GUARDS.get(head)
+        if guard is None:
+            guard = _GUARDS[head] = LabelGuard()
+        guard.check(cfg.c_total)   # raises for a bad label of the previous step
     use_graph = bool(getattr(head, "use_cuda_graph", False)) and x.is_cuda and not validate_labels
     if not use_graph:
-        return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels, w_cache, peer)
+        return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels, w_cache, peer, guard)
     with_bwd = torch.is_grad_enabled() and (x.requires_grad or w.requires_grad)
     sig = (tuple(x.shape), x.device, w.data_ptr(), tuple(w.shape), cfg, with_bwd, id(group),
            w_cache[0].data_ptr() if w_cache is not None else 0, id(peer))
     state = _PLANS.setdefault(head, {"sig": None, "seen": 0, "plan": None, "failed": False})
     if state["failed"]:
-        return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels, w_cache, peer)
+        return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels, w_cache, peer, guard)
     if state["sig"] != sig:
         state.update(sig=sig, seen=0, plan=None)
     if state["plan"] is None:
         state["seen"] += 1
         if state["seen"] <= ENGAGE_AFTER:
-            return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels, w_cache, peer)
+            return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels, w_cache, peer, guard)
         try:
-            state["plan"] = GraphedStep(K, group, w.detach(), x.shape[0], cfg, with_bwd, w_cache, peer)
+            state["plan"] = GraphedStep(K, group, w.detach(), x.shape[0], cfg, with_bwd, w_cache, peer, guard)
         except Exception as e:  # keep training: the eager sequence computes the same thing
             state["failed"] = True
             warnings.warn("multimodalsimilar_b200: CUDA-graph capture failed (%r); continuing with eager launches" % (e,))
-            return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels, w_cache, peer)
+            return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels, w_cache, peer, guard)
     plan: GraphedStep = state["plan"]
     if not with_bwd:
         plan.run(x, label)

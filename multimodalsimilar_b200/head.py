@@ -23,24 +23,7 @@ from torch.nn import Parameter
 from . import engine, ops
 
 
-class ArcFaceCEFunction(torch.autograd.Function):
-    """loss, argmax = ArcFaceCE(x, weight, label; s, m, easy_margin)  -- the eager kernel sequence.
-
-    forward : K1 (x), label margin, K1 (weight) fused into K2 (+combine, finalize)
-    backward: K3 (dC^T producer, dW GEMM, dX GEMM) + normalise backward for x
-    Saved for backward: xhat / xhat^T / what (bf16), the inverse norms, lse, 1 - p_label, dphi, labels --
-    no B x C tensor.  (`engine.py` holds the sequence; the modules go through `engine.run_step`, which replays it
-    as two CUDA graphs once the call signature has repeated.)
-    """
-
-    @staticmethod
-    def forward(ctx, x, weight, label, s, m, easy_margin, validate_labels):
-        cfg = engine.StepConfig(float(s), float(m), bool(easy_margin), 0, weight.shape[0])
-        return engine._EagerCE.forward(ctx, x, weight, label, ops, None, cfg, validate_labels)
-
-    @staticmethod
-    def backward(ctx, grad_loss, _grad_argmax):
-        return engine._EagerCE.backward(ctx, grad_loss, _grad_argmax)[:7]
+ArcFaceCEFunction = engine.ArcFaceCEFunction   # the autograd.Function behind `loss` (engine.run_step applies it)
 
 
 class FusedLogits:

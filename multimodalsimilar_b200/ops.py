@@ -190,6 +190,14 @@ def finalize_rows_packed(allp, label):
     B = nbytes // STATS_BYTES_PER_ROW
     if B % 2 != 0:
         raise ValueError("packed statistics need an even batch size")
+    # `allp` may be a [R, n] view of a wider receive buffer (p2p.PeerExchange sizes its slots for the largest batch
+    # seen, a later smaller batch leaves rows `slot` bytes apart): the kernel takes the rank stride, only the bytes
+    # of one rank have to be contiguous
+    if allp.dtype != torch.uint8 or not allp.is_cuda or allp.stride(1) != 1:
+        raise RuntimeError("packed statistics must be a CUDA uint8 [R, 20 B] tensor with contiguous rows")
+    stride = allp.stride(0) if R > 1 else nbytes
+    if stride % 8 != 0 or stride < nbytes:
+        raise RuntimeError("packed statistics: rank stride %d must be a multiple of 8 and >= %d" % (stride, nbytes))
     dev = allp.device
     base = allp.data_ptr()
     lse = torch.empty(B, dtype=torch.float32, device=dev)
@@ -197,10 +205,9 @@ def finalize_rows_packed(allp, label):
     z = torch.empty(B, dtype=torch.float32, device=dev)
     omp = torch.empty(B, dtype=torch.float32, device=dev)
     loss = torch.empty((), dtype=torch.float32, device=dev)
-    _req(allp, torch.uint8, "packed statistics")
     _lib.call("arcface_b200_finalize_rows_strided", ctypes.c_void_p(base + 8 * B), ctypes.c_void_p(base + 12 * B),
               ctypes.c_void_p(base), ctypes.c_void_p(base + 16 * B), _ptr(_req(label, torch.int64, "label")), R, B,
-              5 * B, 5 * B // 2, _ptr(lse), _ptr(arg), _ptr(z), _ptr(omp), _ptr(loss), _stream())
+              stride // 4, stride // 8, _ptr(lse), _ptr(arg), _ptr(z), _ptr(omp), _ptr(loss), _stream())
     return lse, arg, z, omp, loss
 
 

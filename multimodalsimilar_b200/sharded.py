@@ -81,11 +81,31 @@ class ShardedArcMarginProduct(nn.Module):
             raise ValueError("rank %d owns no classes (C=%d, world=%d)" % (self.rank, out_feature, self.world_size))
         self.weight = Parameter(torch.empty(self.class_hi - self.class_lo, in_feature))
         bound = math.sqrt(6.0 / (out_feature + in_feature))  # xavier_uniform_ of the FULL matrix (arcface.py:25)
-        nn.init.uniform_(self.weight, -bound, bound)
+        # ranks usually share one seed: drawing the shard from the default generator would start class i and class
+        # per + i as duplicates, so every rank draws from its own stream derived from that seed
+        gen = torch.Generator().manual_seed((torch.initial_seed() + 0x9E3779B1 * (self.rank + 1)) % (2 ** 63))
+        with torch.no_grad():
+            self.weight.uniform_(-bound, bound, generator=gen)
         self.cos_m = math.cos(m)
         self.sin_m = math.sin(m)
         self.th = math.cos(math.pi - m)
         self.mm = math.sin(math.pi - m) * m
+
+    # torch.save(model) pickles the module's __dict__ (the reference checkpoints whole modules,
+    # nlp_classifier_train.py:159): the kernel provider (a Python module) and the process group cannot be pickled
+    # and are re-bound to the defaults on load
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state.pop("kernels", None)
+        state.pop("process_group", None)
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        from . import ops as kernels
+
+        self.kernels = kernels
+        self.process_group = dist.group.WORLD if dist.is_initialized() else None
 
     def update_m(self, delta):
         updated = self.m + delta

@@ -145,3 +145,48 @@ def test_graph_mode_two_heads_share_an_embedding():
         assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
         for u, v in zip(a[4:], b[4:]):
             assert float((u - v).norm() / v.norm()) <= 6e-3, "iteration %d" % it
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_bad_label_raises_one_step_late(graph):
+    """arcface.py:59 (`scatter_`) raises on a label outside [0, C).  Without validate_labels the device flag is
+    examined at the start of the NEXT call of the head -- eagerly and in CUDA-graph mode -- instead of never."""
+    B, D, C = 32, 64, 500
+    x, w, y = onp.synthetic_inputs(B, D, C, seed=3)
+    head = _head(w, 64.0, 0.4, graph)
+    for _ in range(4):      # graph mode: the capture happens on the third call
+        _step(head, x, y)
+    torch.cuda.synchronize()
+    bad = y.copy()
+    bad[5] = C + 7
+    _step(head, x, bad)     # trains on silently ...
+    torch.cuda.synchronize()
+    with pytest.raises(IndexError):
+        _step(head, x, y)   # ... and is reported here
+    torch.cuda.synchronize()
+    _step(head, x, y)       # the report is not sticky
+    strict = _head(w, 64.0, 0.4, graph)
+    strict.validate_labels = True
+    with pytest.raises(IndexError):
+        _step(strict, x, bad)
+
+
+def test_autograd_function_is_the_modules_path():
+    """`ArcFaceCEFunction` (north_star: "drop-in torch.nn.Module / autograd.Function") applied by hand equals the
+    module that applies it through engine.run_step."""
+    import multimodalsimilar_b200 as mm
+    from multimodalsimilar_b200 import engine, ops
+
+    B, D, C = 48, 128, 1000
+    x, w, y = onp.synthetic_inputs(B, D, C, seed=4)
+    head = _head(w, 64.0, 0.4, False)
+    ref = _step(head, x, y)
+    xt = torch.from_numpy(x).to(dev()).requires_grad_(True)
+    wt = torch.from_numpy(w).to(dev()).requires_grad_(True)
+    cfg = engine.StepConfig(64.0, 0.4, False, 0, C)
+    assert mm.ArcFaceCEFunction is engine.ArcFaceCEFunction
+    loss, pred = mm.ArcFaceCEFunction.apply(xt, wt, torch.from_numpy(y).to(dev()), ops, None, cfg, False)
+    loss.backward()
+    assert torch.equal(loss.detach(), ref[0]) and torch.equal(pred, ref[1])
+    torch.testing.assert_close(xt.grad, ref[2], rtol=1e-4, atol=1e-7)
+    assert torch.equal(wt.grad, ref[3])

@@ -46,7 +46,11 @@ def _worker(rank, world, port, case, out_dir):
     b_loc = B // world
     ok = True
     msg = ""
-    for it in range(5):   # graph mode: two eager calls, the capture, two replays
+    B_full = B
+    for it in range(8):   # graph mode: two eager calls, the capture, two replays; then a SMALLER batch (last partial
+        # batch / eval batch of a training loop: the peer-memory slots stay sized for the first one)
+        B = B_full if it < 5 else B_full // 2
+        b_loc = B // world
         x, _, y = onp.synthetic_inputs(B, D, C, seed=30 + it, trained_like=(it % 2 == 1))
         xl = torch.from_numpy(x[rank * b_loc:(rank + 1) * b_loc]).to(dev).requires_grad_(True)
         yl = torch.from_numpy(y[rank * b_loc:(rank + 1) * b_loc]).to(dev)
@@ -77,6 +81,8 @@ def _worker(rank, world, port, case, out_dir):
                 except AssertionError as e:
                     ok = False
                     msg += "iteration %d rank %d: %s\n" % (it, r, str(e)[:300])
+    B = B_full
+    b_loc = B // world
     # global top-k over the class shards (fused top-k per rank + all-gather + device merge) against the dense head
     x, _, _ = onp.synthetic_inputs(B, D, C, seed=77, trained_like=True)
     xl = torch.from_numpy(x[rank * b_loc:(rank + 1) * b_loc]).to(dev)

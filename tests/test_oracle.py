@@ -138,3 +138,40 @@ def test_oracle_backward_is_the_gradient_of_the_oracle_loss(easy):
         wp[c, d] += h
         wm[c, d] -= h
         assert abs((loss(x, wp) - loss(x, wm)) / (2 * h) - dw[c, d]) <= 1e-6 * max(1.0, abs(dw[c, d]))
+
+
+@pytest.mark.parametrize("name", ["base", "easy", "fallback", "easy_neg", "tie", "label_col", "trained", "grad10", "ragged"])
+@pytest.mark.parametrize("chunk", [7, 1 << 16])
+def test_chunked_torch_oracle_matches_reference(golden, name, chunk):
+    """oracle/arcface_torch_chunked.py (the full-size checker of bench.py / the -m gpu tests) against the goldens
+    minted from the unmodified reference, with the classes cut into ragged chunks and in one piece."""
+    from oracle import arcface_torch_chunked as och
+
+    x, w, y, s, m, easy, grad = _case(golden, name)
+    C = w.shape[0]
+    lo, hi = C // 3, C - 1
+    r = och.head_step_chunked(torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(y), s, m, easy,
+                              grad_loss=grad, chunk=chunk, dw_range=(lo, hi))
+    gl = float(golden[name + "/loss"])
+    assert abs(float(r["loss"]) - gl) <= 2e-6 * max(1.0, abs(gl))
+    np.testing.assert_array_equal(r["argmax"].numpy(), golden[name + "/argmax"])
+    z = golden[name + "/logits"]
+    top = -np.sort(-z, axis=1)
+    np.testing.assert_allclose(r["top2_gap"].numpy(), top[:, 0] - top[:, 1], rtol=0, atol=3e-5 * s)
+    np.testing.assert_allclose(r["z_label"].numpy(), z[np.arange(len(y)), y.reshape(-1)], rtol=0, atol=2e-5 * s)
+    gx, gw = golden[name + "/dx"], golden[name + "/dw"]
+    np.testing.assert_allclose(r["dx"].numpy(), gx, rtol=1e-4, atol=5e-6 * max(1.0, np.abs(gx).max()))
+    np.testing.assert_allclose(r["dw"].numpy(), gw[lo:hi], rtol=1e-4, atol=5e-6 * max(1.0, np.abs(gw).max()))
+
+
+def test_chunked_torch_oracle_matches_dense_port():
+    from oracle import arcface_torch_chunked as och
+
+    x, w, y = onp.synthetic_inputs(48, 96, 1500, seed=5, trained_like=True)
+    xt, wt, yt = torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(y)
+    loss, pred, dx, dw = otc.head_step(xt, wt, yt, 64.0, 0.4, False)
+    r = och.head_step_chunked(xt, wt, yt, 64.0, 0.4, False, chunk=256)
+    assert abs(float(r["loss"]) - float(loss)) <= 1e-5 * max(1.0, float(loss))
+    assert torch.equal(r["argmax"], pred)
+    torch.testing.assert_close(r["dx"], dx, rtol=1e-4, atol=2e-6 * max(1.0, float(dx.abs().max())))
+    torch.testing.assert_close(r["dw"], dw, rtol=1e-4, atol=2e-6 * max(1.0, float(dw.abs().max())))

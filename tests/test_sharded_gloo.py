@@ -27,6 +27,7 @@ def _worker(rank, world, port, case, out_dir):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    torch.manual_seed(1234)   # the usual same-seed-on-all-ranks setup
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from multimodalsimilar_b200 import ShardedArcMarginProduct
@@ -36,8 +37,21 @@ def _worker(rank, world, port, case, out_dir):
         B, D, C, s, m, easy, trained, grad = case
         x, w, y = onp.synthetic_inputs(B, D, C, seed=7, trained_like=trained)
         head = ShardedArcMarginProduct(D, C, s=s, m=m, easy_margin=easy, kernels=_cpu_kernels)
+        # fresh shards of ranks that share a seed must not start as copies of each other
+        peers = [torch.empty_like(head.weight) for _ in range(world)] if (C % world == 0) else None
+        if peers is not None:
+            dist.all_gather(peers, head.weight.detach())
+            assert not torch.equal(peers[0], peers[1])
         head.load_full_weight(torch.from_numpy(w))
         assert torch.equal(head.gather_weight(), torch.from_numpy(w))
+        # torch.save(model) must keep working (the reference checkpoints whole modules, nlp_classifier_train.py:159)
+        import io
+
+        buf = io.BytesIO()
+        torch.save(head, buf)
+        buf.seek(0)
+        again = torch.load(buf, weights_only=False)
+        assert torch.equal(again.weight, head.weight) and again.class_lo == head.class_lo
         b_loc = B // world
         xl = torch.from_numpy(x[rank * b_loc:(rank + 1) * b_loc]).clone().requires_grad_(True)
         yl = torch.from_numpy(y[rank * b_loc:(rank + 1) * b_loc])
