@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libarcface_b200.so")
 # Diagnostic build (make DIAG=1): the same kernels plus the ARCFACE_B200_* environment knobs and the in-kernel wait
 # profiler.  Only tools/ ask for it; tests, bench.py and the product load the release library.
 if os.environ.get("ARCFACE_B200_DIAG") == "1":
-    LIB_PATH = os.path.join(_HERE, "libarcface_b200_diag.so")
+    LIB_PATH = os.environ.get("ARCFACE_B200_DIAG_LIB") or os.path.join(_HERE, "libarcface_b200_diag.so")
 
 OK = 0
 ERROR_NAMES = {-1: "E_ARCH", -2: "E_SHAPE", -3: "E_LAYOUT", -4: "E_WORKSPACE", -5: "E_CUDA", -6: "E_ARG"}

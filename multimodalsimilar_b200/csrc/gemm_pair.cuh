@@ -14,6 +14,11 @@
 //   resident : 128 rows x K of the reused operand (rows res * 256 + r * 128 ...), loaded once
 //   streamed : 128 rows x 64 per stage of the per-tile operand (rows s_row0 + i * 256 + r * 128 ...)
 //   TMEM     : two accumulator buffers of 256 fp32 columns; the CTA's 128 lanes are its 128 rows of the tile
+// K > 512 (Core::stream_both): the reused operand no longer fits beside the pipeline (128 rows x 1024 bf16 are
+// 256 KB), so BOTH operands stream -- a stage holds the k-block of the per-tile operand (16 KB) and the k-block of
+// the reused one (16 KB, re-fetched from L2 for every tile; B x D bf16 is a few MB and stays there).  Per SM that is
+// 64 B/clk of TMA writes + 64 B/clk of MMA reads, still a third less shared-memory traffic than the one-CTA
+// streaming tile (192 B/clk) the wide shapes -- D = 1024 / 1792 / 2816, B = 1024 -- used before.
 // P::RES_A == false: the streamed operand is A (its rows are the accumulator rows), the resident one is B.
 // P::RES_A == true : the resident operand is A, the streamed one is B (accumulator columns).
 // Roles (384 threads): warp 0 TMA producer (both CTAs), warp 1 MMA issuer (leader CTA only), warp 2 TMEM
@@ -39,10 +44,13 @@ constexpr int EPI_WARPS = 8;
 constexpr int THREADS = (4 + EPI_WARPS) * 32;
 constexpr int TILE_BYTES = ROWS * BK * 2;  // 16 KB
 constexpr int STAGING_PER_WARP = 4096;
-constexpr int MAX_KBLOCKS = 8;
+constexpr int MAX_KBLOCKS = 8;   // resident mode: k-blocks of the parked operand
+constexpr int MAX_STAGES = 8;    // barrier slots carved for the pipeline (Core::stages <= MAX_STAGES)
 
 struct Core {
-    int kblocks;         // ceil(K / 64) <= MAX_KBLOCKS
+    int kblocks;         // ceil(K / 64); <= MAX_KBLOCKS unless stream_both
+    int stream_both = 0; // 1: no resident operand, every stage carries a k-block of both operands
+    int stages = 0;      // pipeline stages in use (set by the launcher: P::STAGES, or what fits when streaming)
     int s_blocks;        // 256-row blocks of the streamed operand handled by this launch
     int s_row0;          // TMA row coordinate of block 0 in the streamed tensor map
     int n_res;           // 256-row slices of the resident operand; the number of pairs is a multiple of it
@@ -79,11 +87,34 @@ struct EpiCtx {
     unsigned long long* prof;  // measurements only: this CTA's counters [8..15] for warp 4, else null
 };
 
+// bytes of everything but the operand tiles
 template <class P>
-constexpr size_t smem_bytes(int kblocks, size_t extra_bytes) {
+constexpr size_t smem_fixed_bytes(size_t extra_bytes) {
+    return (P::STAGING ? EPI_WARPS * STAGING_PER_WARP : 0) + ((extra_bytes + 15) / 16) * 16 +
+           (2 * MAX_STAGES + 2 * ACC_BUFS + 1) * 8 + 16;
+}
+template <class P>
+constexpr size_t smem_bytes(int kblocks, size_t extra_bytes) {  // resident mode
     // no alignment slack: the kernels declare their dynamic shared memory __align__(1024) and trap if it is not
-    return static_cast<size_t>(kblocks + P::STAGES) * TILE_BYTES + (P::STAGING ? EPI_WARPS * STAGING_PER_WARP : 0) +
-           ((extra_bytes + 15) / 16) * 16 + (2 * P::STAGES + 2 * ACC_BUFS + 1) * 8 + 16;
+    return static_cast<size_t>(kblocks + P::STAGES) * TILE_BYTES + smem_fixed_bytes<P>(extra_bytes);
+}
+// pipeline stages a streaming launch gets out of `budget` bytes of shared memory
+template <class P>
+constexpr int stream_stages(size_t extra_bytes, size_t budget = 227 * 1024) {
+    int n = static_cast<int>((budget - smem_fixed_bytes<P>(extra_bytes)) / (2 * TILE_BYTES));
+    return n > MAX_STAGES ? MAX_STAGES : n;
+}
+template <class P>
+constexpr size_t smem_bytes(const Core& co, size_t extra_bytes) {
+    return co.stream_both ? static_cast<size_t>(co.stages) * 2 * TILE_BYTES + smem_fixed_bytes<P>(extra_bytes)
+                          : static_cast<size_t>(co.kblocks + co.stages) * TILE_BYTES + smem_fixed_bytes<P>(extra_bytes);
+}
+// fills Core::kblocks / stream_both / stages for a contraction of depth K
+template <class P>
+inline void core_set_k(Core& co, int K, size_t extra_bytes) {
+    co.kblocks = (K + BK - 1) / BK;
+    co.stream_both = co.kblocks > MAX_KBLOCKS ? 1 : 0;
+    co.stages = co.stream_both ? stream_stages<P>(extra_bytes) : P::STAGES;
 }
 
 // One 4 KB staging buffer per epilogue warp (32 rows x 128 B, TMA SWIZZLE_128B layout); see gemm_rs.cuh.
@@ -192,16 +223,18 @@ template <class P>
 __device__ __forceinline__ void pair_gemm_body(const CUtensorMap& tmS, const CUtensorMap& tmR, const CUtensorMap& tmC,
                                                const typename P::Params& prm, const int extra_bytes, uint8_t* smem,
                                                const int pair, const int npairs) {
-    constexpr int STAGES = P::STAGES;
     const Core& co = prm.core;
     const int kblocks = co.kblocks;
+    const bool stream = co.stream_both != 0;
+    const int STAGES = co.stages;
+    const int STAGE_BYTES = stream ? 2 * TILE_BYTES : TILE_BYTES;
     uint8_t* sRes = smem;
-    uint8_t* sStage = sRes + kblocks * TILE_BYTES;
-    uint8_t* sStaging = sStage + STAGES * TILE_BYTES;
+    uint8_t* sStage = sRes + (stream ? 0 : kblocks * TILE_BYTES);
+    uint8_t* sStaging = sStage + STAGES * STAGE_BYTES;
     uint8_t* sExtra = sStaging + (P::STAGING ? EPI_WARPS * STAGING_PER_WARP : 0);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(sExtra + ((extra_bytes + 15) / 16) * 16);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* empty_bar = full_bar + MAX_STAGES;
+    uint64_t* tfull_bar = empty_bar + MAX_STAGES;
     uint64_t* tempty_bar = tfull_bar + ACC_BUFS;
     uint64_t* res_bar = tempty_bar + ACC_BUFS;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
@@ -231,7 +264,7 @@ __device__ __forceinline__ void pair_gemm_body(const CUtensorMap& tmS, const CUt
         if (P::STAGING) tma_prefetch_desc(&tmC);
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < STAGES; ++i) {
+        for (int i = 0; i < MAX_STAGES; ++i) {
             mbar_init(&full_bar[i], 2);   // one arrive.expect_tx per CTA of the pair (used in the leader only)
             mbar_init(&empty_bar[i], 1);  // multicast tcgen05.commit
         }
@@ -266,10 +299,11 @@ __device__ __forceinline__ void pair_gemm_body(const CUtensorMap& tmS, const CUt
     if (warp == 0) {
         // ---------------- TMA producer (both CTAs): whole warp walks the schedule, one elected lane issues
         const uint32_t res_bar_leader = mapa_u32(smem_u32(res_bar), 0);
-        if (elect_one()) {
+        const int res_row = res * 2 * ROWS + rank * ROWS;
+        if (!stream && elect_one()) {
             mbar_expect_tx_cluster(res_bar_leader, kblocks * TILE_BYTES);
             for (int kb = 0; kb < kblocks; ++kb)
-                tma_load_2d_pair(sRes + kb * TILE_BYTES, &tmR, res_bar_leader, kb * BK, res * 2 * ROWS + rank * ROWS);
+                tma_load_2d_pair(sRes + kb * TILE_BYTES, &tmR, res_bar_leader, kb * BK, res_row);
         }
         __syncwarp();
         int stage = 0;
@@ -288,8 +322,9 @@ __device__ __forceinline__ void pair_gemm_body(const CUtensorMap& tmS, const CUt
                 wp_b.end();
                 if (elect_one()) {
                     const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
-                    mbar_expect_tx_cluster(full_leader, TILE_BYTES);
-                    tma_load_2d_pair(sStage + stage * TILE_BYTES, &tmS, full_leader, kb * BK, row);
+                    mbar_expect_tx_cluster(full_leader, STAGE_BYTES);
+                    tma_load_2d_pair(sStage + stage * STAGE_BYTES, &tmS, full_leader, kb * BK, row);
+                    if (stream) tma_load_2d_pair(sStage + stage * STAGE_BYTES + TILE_BYTES, &tmR, full_leader, kb * BK, res_row);
                     // the n_res pairs that stream the same block share the L2 prefetch work
                     if (pf && (kb % co.n_res) == res)
                         tma_prefetch_2d(&tmS, kb * BK, P::stream_row(prm, ip) + rank * ROWS);
@@ -305,8 +340,10 @@ __device__ __forceinline__ void pair_gemm_body(const CUtensorMap& tmS, const CUt
             constexpr uint32_t idesc = make_idesc_bf16(2 * ROWS, ACC_COLS, false, false);
             const uint32_t sStage_u32 = smem_u32(sStage);
             const uint64_t res_desc0 = make_smem_desc(smem_u32(sRes), 16, 1024);
-            mbar_wait_cluster(res_bar, 0);
-            tc_fence_after();
+            if (!stream) {
+                mbar_wait_cluster(res_bar, 0);
+                tc_fence_after();
+            }
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -323,8 +360,9 @@ __device__ __forceinline__ void pair_gemm_body(const CUtensorMap& tmS, const CUt
                     mbar_wait_cluster(&full_bar[stage], phase);
                     wp_f.end();
                     tc_fence_after();
-                    const uint64_t s_desc = make_smem_desc(sStage_u32 + stage * TILE_BYTES, 16, 1024);
-                    const uint64_t r_desc = res_desc0 + static_cast<uint64_t>(kb * (TILE_BYTES >> 4));
+                    const uint64_t s_desc = make_smem_desc(sStage_u32 + stage * STAGE_BYTES, 16, 1024);
+                    const uint64_t r_desc = stream ? s_desc + static_cast<uint64_t>(TILE_BYTES >> 4)
+                                                   : res_desc0 + static_cast<uint64_t>(kb * (TILE_BYTES >> 4));
                     const uint64_t a_desc = P::RES_A ? r_desc : s_desc;
                     const uint64_t b_desc = P::RES_A ? s_desc : r_desc;
                     if (elect_one()) {
@@ -418,9 +456,11 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
 template <class P>
 static int32_t launch_pair(const CUtensorMap& tmS, const CUtensorMap& tmR, const CUtensorMap& tmC,
                            const typename P::Params& prm, int groups, int extra_bytes, cudaStream_t st) {
-    const size_t smem = smem_bytes<P>(prm.core.kblocks, extra_bytes);
-    AB_REQUIRE(prm.core.kblocks >= 1 && prm.core.kblocks <= MAX_KBLOCKS && smem <= 227 * 1024, ARCFACE_B200_E_SHAPE,
-               "CTA-pair kernel: %d k-blocks / %zu bytes of shared memory do not fit", prm.core.kblocks, smem);
+    const size_t smem = smem_bytes<P>(prm.core, extra_bytes);
+    AB_REQUIRE(prm.core.kblocks >= 1 && (prm.core.stream_both || prm.core.kblocks <= MAX_KBLOCKS) &&
+                   prm.core.stages >= 2 && prm.core.stages <= MAX_STAGES && smem <= 227 * 1024,
+               ARCFACE_B200_E_SHAPE, "CTA-pair kernel: %d k-blocks / %d stages / %zu bytes of shared memory do not fit",
+               prm.core.kblocks, prm.core.stages, smem);
     AB_REQUIRE(groups >= 1 && prm.core.n_res >= 1, ARCFACE_B200_E_SHAPE, "empty grid");
     static bool configured[64] = {false};
     int dev = 0;

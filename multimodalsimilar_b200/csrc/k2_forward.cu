@@ -186,7 +186,10 @@ struct FwdStatsPairT : pr::PairDefaults {
     // what raises its throughput is MORE warps each holding one row pair, not a deeper pipeline per warp.
     static constexpr bool WIDE = NORM && AB_FWD_AUX_WARPS == 16;
     static constexpr int LOW_REGS = WIDE ? 40 : 0, EPI_REGS = WIDE ? 96 : 0, AUX_REGS = WIDE ? 64 : 0;
-    static constexpr int RUN = 32;  // consecutive rows a helper warp normalises between two counter updates
+#ifndef AB_FWD_RUN
+#define AB_FWD_RUN 32
+#endif
+    static constexpr int RUN = AB_FWD_RUN;  // consecutive rows a helper warp normalises between two counter updates
 
     struct Params {
         pr::Core core;
@@ -525,13 +528,17 @@ static void fwd_partition(int B, int64_t C, int nsm, int* m_tiles, int* n_tiles,
     *groups = (*n_tiles + *per - 1) / *per;  // no empty class range
 }
 
-// CTA-pair forward: usable when the 256-row Xhat slice fits in shared memory (D <= 512) and the device has
-// at least one pair of SMs.  ARCFACE_B200_FWD_IMPL=generic forces the streaming kernel (A/B measurements).
+// CTA-pair forward: whenever the device has a pair of SMs.  D <= 512 parks the 256-row Xhat slice in shared memory,
+// wider embeddings stream both operands (gemm_pair.cuh, Core::stream_both).  Diagnostic builds:
+// ARCFACE_B200_FWD_IMPL=generic forces the one-CTA streaming kernel (A/B measurements).
 static bool fwd_use_pairs(int D, int nsm) {
     const char* v = diag_env("ARCFACE_B200_FWD_IMPL");
     if (v != nullptr && strcmp(v, "generic") == 0) return false;
-    return (D + pr::BK - 1) / pr::BK <= pr::MAX_KBLOCKS && nsm >= 2;
+    (void)D;
+    return nsm >= 2;
 }
+// the in-kernel weight normaliser holds a row pair in registers: rows of up to 512 floats
+static bool fwd_norm_in_kernel(int D) { return (D + pr::BK - 1) / pr::BK <= pr::MAX_KBLOCKS; }
 static void fwd_pair_partition(int B, int64_t C, int nsm, int* n_res, int* groups, int* s_blocks) {
     *n_res = (B + FwdStatsP::NROW - 1) / FwdStatsP::NROW;
     *s_blocks = static_cast<int>((C + FwdStatsP::NROW - 1) / FwdStatsP::NROW);
@@ -564,7 +571,7 @@ static int32_t launch_fwd_pairs(const uint16_t* xhat, const uint16_t* what, cons
     fwd_pair_partition(B, C_local, sm_count(), &p.core.n_res, &groups, &p.core.s_blocks);
     AB_REQUIRE(n_parts == 2 * groups, ARCFACE_B200_E_WORKSPACE, "forward_stats: n_parts=%d, expected %d", n_parts,
                2 * groups);
-    p.core.kblocks = (D + pr::BK - 1) / pr::BK;
+    pr::core_set_k<P>(p.core, D, 0);
     p.core.s_row0 = 0;
     // NORM: the helper warps publish rows in ascending order, so the pairs walk the tiles interleaved
     // (tile t at step t / groups); otherwise every pair takes a contiguous class range
@@ -681,7 +688,7 @@ extern "C" int32_t arcface_b200_forward_stats_fused(const uint16_t* xhat, const 
                "forward_stats_fused: pointers must be 16-byte aligned");
     const char* impl = diag_env("ARCFACE_B200_FWD_IMPL");
     const bool split = impl != nullptr && strcmp(impl, "split") == 0;  // A/B: K1 and K2 as two launches
-    if (!fwd_use_pairs(D, sm_count()) || split) {
+    if (!fwd_use_pairs(D, sm_count()) || !fwd_norm_in_kernel(D) || split) {
         // shapes the in-kernel normaliser does not cover: the same two steps as separate launches
         if (int32_t rc = arcface_b200_normalize_cast(w, C_local, D, what, inv_nw, nullptr, 0, stream)) return rc;
         return arcface_b200_forward_stats(xhat, what, label_local, B, D, C_local, s, part_max, part_sum, part_arg,

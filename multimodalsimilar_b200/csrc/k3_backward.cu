@@ -1071,11 +1071,12 @@ struct BwdPlan {
 // CTA pairs of bwd_fused_kernel that can be resident at once on the current device (the roles spin on each
 // other's counters, so the whole launch has to be).  0 on failure.
 static size_t fused_smem_bytes() {
-    size_t a = pr::smem_bytes<BwdDCpT<true>>(pr::MAX_KBLOCKS, BwdDCpT<true>::EXTRA_BYTES);
-    size_t b = pr::smem_bytes<BwdDWpT<true>>(pr::MAX_KBLOCKS, BwdDWpT<true>::EXTRA_BYTES);
-    size_t c = fz::dx_smem_bytes();
-    size_t m = a > b ? a : b;
-    return m > c ? m : c;
+    // every role is sized against the whole 227 KB (resident mode: MAX_KBLOCKS + STAGES tiles; streaming mode: as
+    // many two-tile stages as fit), so the launch simply asks for all of it
+    static_assert(pr::smem_bytes<BwdDCpT<true>>(pr::MAX_KBLOCKS, BwdDCpT<true>::EXTRA_BYTES) <= 227 * 1024, "dC^T role");
+    static_assert(pr::smem_bytes<BwdDWpT<true>>(pr::MAX_KBLOCKS, BwdDWpT<true>::EXTRA_BYTES) <= 227 * 1024, "dW role");
+    static_assert(fz::dx_smem_bytes() <= 227 * 1024, "dX role");
+    return 227 * 1024;
 }
 static int fused_max_pairs(int nsm) {
     static int cached[64] = {0};
@@ -1131,9 +1132,12 @@ static BwdPlan plan_backward(int B, int D, int64_t C, int nsm) {
     pl.dc_rs = !generic && (D + 63) / 64 <= rs::MAX_KBLOCKS;
     pl.dw_rs = !generic && pl.Bp / 64 <= rs::MAX_KBLOCKS;
     pl.dx2 = !generic;
-    const bool pairs = !env_is("ARCFACE_B200_BWD_IMPL", "rs") && nsm >= 2;
-    pl.dc_pair = pl.dc_rs && pairs;
-    pl.dw_pair = pl.dw_rs && pairs;
+    // CTA pairs for every shape whose q partial sums fit the dW epilogue's eight slots (B <= 1024): the reused operand
+    // is parked in shared memory when it fits (D <= 512 for dC^T, B <= 512 for dW) and streamed otherwise
+    const bool pairs = !generic && !env_is("ARCFACE_B200_BWD_IMPL", "rs") && nsm >= 2 &&
+                       2 * ((B + BwdDCp::NCOL - 1) / BwdDCp::NCOL) <= 8;
+    pl.dc_pair = pairs;
+    pl.dw_pair = pairs;
     pl.q_slots = pl.dc_pair ? 2 * ((B + BwdDCp::NCOL - 1) / BwdDCp::NCOL) : pl.dc_rs ? 2 * ((B + rs::BN - 1) / rs::BN) : 1;
     // ---- single-launch backward: every role needs its resident operand to fit (D, B <= 512) and the launch
     // needs enough co-resident CTA pairs to give each role a few
@@ -1282,9 +1286,9 @@ extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* x
 
     CUtensorMap tm_w_k, tm_x_k, tm_dct_k, tm_xt_k, tm_dct_mn, tm_w_mn, tm_dct_out, tm_dw_out, tm_dx_out;
     if (int32_t rc = make_tmap_kmajor(&tm_w_k, what, D, C_local, D, BLOCK_M)) return rc;
-    if (int32_t rc = make_tmap_kmajor(&tm_x_k, xhat, D, B, D, pl.dc_rs ? rs::BN : BwdDC::BLOCK_N)) return rc;
+    if (int32_t rc = make_tmap_kmajor(&tm_x_k, xhat, D, B, D, (pl.dc_rs || pl.dc_pair) ? rs::BN : BwdDC::BLOCK_N)) return rc;
     if (int32_t rc = make_tmap_kmajor(&tm_dct_k, dct, B, pl.chunk_classes, pl.Bp, BLOCK_M)) return rc;
-    if (int32_t rc = make_tmap_kmajor(&tm_xt_k, xhat_t, B, D, ld_t, pl.dw_rs ? rs::BN : BwdDW::BLOCK_N)) return rc;
+    if (int32_t rc = make_tmap_kmajor(&tm_xt_k, xhat_t, B, D, ld_t, (pl.dw_rs || pl.dw_pair) ? rs::BN : BwdDW::BLOCK_N)) return rc;
     if (int32_t rc = make_tmap_mnmajor(&tm_dct_mn, dct, B, pl.chunk_classes, pl.Bp)) return rc;
     if (int32_t rc = make_tmap_mnmajor(&tm_w_mn, what, D, C_local, D)) return rc;
     if (int32_t rc = make_tmap_store(&tm_dct_out, dct, 2, pl.Bp, pl.chunk_classes, pl.Bp)) return rc;
@@ -1329,7 +1333,7 @@ extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* x
         }
         {
             BwdDCpT<true>::Params& p = fp.dc;
-            p.core.kblocks = (D + pr::BK - 1) / pr::BK;
+            pr::core_set_k<BwdDCpT<true>>(p.core, D, BwdDCpT<true>::EXTRA_BYTES);
             p.core.s_blocks = pl.n_blocks;
             p.core.s_row0 = 0;
             p.core.n_res = n_res_dc;
@@ -1343,7 +1347,7 @@ extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* x
         }
         {
             BwdDWpT<true>::Params& p = fp.dw;
-            p.core.kblocks = pl.Bp / pr::BK;
+            pr::core_set_k<BwdDWpT<true>>(p.core, pl.Bp, BwdDWpT<true>::EXTRA_BYTES);
             p.core.s_blocks = pl.n_blocks;
             p.core.s_row0 = 0;
             p.core.n_res = n_res_dw;
@@ -1438,7 +1442,7 @@ extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* x
         // ---- dC^T (and q) for this chunk
         if (pl.dc_pair) {
             BwdDCp::Params p;
-            p.core.kblocks = (D + pr::BK - 1) / pr::BK;
+            pr::core_set_k<BwdDCp>(p.core, D, BwdDCp::EXTRA_BYTES);
             p.core.s_blocks = (cn + BwdDCp::NCOL - 1) / BwdDCp::NCOL;
             p.core.s_row0 = static_cast<int>(c0);
             p.core.n_res = (B + BwdDCp::NCOL - 1) / BwdDCp::NCOL;
@@ -1483,7 +1487,7 @@ extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* x
         // ---- dW rows of this chunk
         if (pl.dw_pair) {
             BwdDWp::Params p;
-            p.core.kblocks = pl.Bp / pr::BK;
+            pr::core_set_k<BwdDWp>(p.core, pl.Bp, BwdDWp::EXTRA_BYTES);
             p.core.s_blocks = (cn + BwdDWp::NCOL - 1) / BwdDWp::NCOL;
             p.core.s_row0 = 0;  // the scratch is chunk-relative
             p.core.n_res = (D + BwdDWp::NCOL - 1) / BwdDWp::NCOL;

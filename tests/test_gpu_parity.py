@@ -170,7 +170,8 @@ def test_golden_forward_backward(golden, name):
 
 # ----------------------------------------------------------------------------- fused statistics vs own logits
 @pytest.mark.parametrize("B,D,C,s", [(64, 512, 1000, 30.0), (200, 64, 30000, 64.0), (512, 128, 70001, 64.0),
-                                     (1000, 64, 5000, 64.0), (3, 8, 2, 10.0)])
+                                     (1000, 64, 5000, 64.0), (3, 8, 2, 10.0), (100, 1000, 3001, 64.0),
+                                     (512, 1024, 20000, 64.0), (300, 1792, 777, 64.0)])
 def test_fused_statistics_match_materialised_logits(B, D, C, s):
     from multimodalsimilar_b200 import ops
 
@@ -237,6 +238,13 @@ def test_fused_forward_equals_split_forward(B, D, C, s):
     (100, 72, 777, 64.0, 0.2, True, False),
     (300, 256, 2049, 64.0, 0.4, False, True),
     (64, 512, 40000, 64.0, 0.5, False, False),   # long K range in the dX GEMM (many 64-class slices per CTA)
+    # CTA-pair kernels with BOTH operands streamed (gemm_pair.cuh, Core::stream_both): D > 512 for the forward and
+    # the dC^T role, B > 512 for the dW role; ragged k-blocks (D, B not multiples of 64), ragged class tiles
+    (70, 520, 700, 64.0, 0.4, False, False),
+    (130, 1000, 1500, 64.0, 0.4, False, True),
+    (600, 64, 900, 64.0, 0.5, False, False),
+    (1000, 1032, 300, 30.0, 0.3, True, False),
+    (96, 2816, 2000, 64.0, 0.5, False, True),
 ])
 def test_backward_matches_oracle(B, D, C, s, m, easy, trained):
     x, w, y = onp.synthetic_inputs(B, D, C, seed=11, trained_like=trained)
@@ -295,7 +303,7 @@ def torch_oracle(x, w, y, s, m, easy, grad=1.0, dtype=torch.float32):
 @pytest.mark.parametrize("B,D,C,s,m,trained", [
     (256, 1792, 100000, 64.0, 0.2, False),   # BASELINE config 2 (EfficientNet-B4 head)
     (256, 1792, 100000, 64.0, 0.2, True),
-    (512, 512, 1000000, 64.0, 0.5, False),   # north-star shape: 18 backward chunks
+    (512, 512, 1000000, 64.0, 0.5, False),   # north-star shape: single-launch backward
     (512, 512, 1000000, 64.0, 0.5, True),
     (128, 64, 600000, 64.0, 0.4, True),      # small B: chunks of > 200k classes
     (1024, 512, 300000, 64.0, 0.5, False),   # BASELINE config 5 batch (B = 1024)
