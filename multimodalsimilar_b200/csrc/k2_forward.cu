@@ -187,7 +187,7 @@ struct FwdStatsPairT : pr::PairDefaults {
     static constexpr bool WIDE = NORM && AB_FWD_AUX_WARPS == 16;
     static constexpr int LOW_REGS = WIDE ? 40 : 0, EPI_REGS = WIDE ? 96 : 0, AUX_REGS = WIDE ? 64 : 0;
 #ifndef AB_FWD_RUN
-#define AB_FWD_RUN 32
+#define AB_FWD_RUN 8
 #endif
     static constexpr int RUN = AB_FWD_RUN;  // consecutive rows a helper warp normalises between two counter updates
 

@@ -793,10 +793,14 @@ template <bool FUSED>
 struct BwdDWpT : pr::PairDefaults {
     static constexpr int STAGES = 4;
     // The dW rows leave through one 4 KB staging buffer per warp and TMA stores of {32 columns x 32 rows}.
-    // Measured alternatives (ARCFACE_B200_BWD_PROF): two 2 KB buffers with 16-column boxes double the number of
-    // proxy fences (~640 cycles per box: the fence waits for st.shared traffic that competes with the tensor
-    // pipe's operand reads for shared-memory bandwidth); 128-bit global stores straight from registers (thread =
-    // class row) are 4x slower still (32 half-sectors per warp instruction).
+    // Measured alternatives (ARCFACE_B200_BWD_PROF, cycles per tile in the store part of this epilogue; this path:
+    // ~4.2k): two 2 KB buffers with 16-column boxes double the number of proxy fences (~640 cycles per box: the
+    // fence waits for st.shared traffic that competes with the tensor pipe's operand reads for shared-memory
+    // bandwidth); 128-bit global stores straight from registers (thread = class row) are 4x slower still (32
+    // half-sectors per warp instruction); round 2: re-reading the staging buffer with eight lanes per row and
+    // storing full 128-byte lines with st.global.v4 (no proxy fence, no TMA) ~7.8k; 256-bit stores straight from
+    // registers (STG.E.ENL2.256, one full sector per lane) ~8.8k -- a store instruction that touches 32 different
+    // lines costs ~550 cycles here.  The TMA store stays.
     static constexpr bool STAGING = true;
     static constexpr bool RES_A = false;
     static constexpr int NCOL = 2 * pr::ROWS;
@@ -1152,11 +1156,31 @@ static BwdPlan plan_backward(int B, int D, int64_t C, int nsm) {
         int a = 0, b = 0, c = 0;
         if (const char* v = diag_env("ARCFACE_B200_BWD_SPLIT")) sscanf(v, "%d,%d,%d", &a, &b, &c);
         if (a <= 0 || b <= 0 || c <= 0 || a + b + c > pairs) {
-            // default shares, from the per-tile cycle counts of the roles (ARCFACE_B200_BWD_PROF): the dW role is
-            // the slowest per tile (fp32 output staged through shared memory), the dX role the fastest
-            c = static_cast<int>(pairs * 0.25) / dx_unit * dx_unit;
-            a = static_cast<int>(pairs * 0.33) / n_res_dc * n_res_dc;
-            b = (pairs - a - c) / n_res_dw * n_res_dw;
+            // Role shares from a cost model in pair-cycles per 256-class block, fitted to the wait profiler
+            // (ARCFACE_B200_BWD_PROF) at the north-star shape and checked against role-split sweeps at the BASELINE
+            // shapes (profiles/README.md):
+            //   dC^T: one 256 x 256 x D tile per 256 batch rows -- 8 D MMA cycles, but never below the ~6.6k cycles its
+            //         exp2 / pack / TMA-store epilogue takes;
+            //   dW  : one 256 x 256 x B tile per 256 embedding columns -- 8 B MMA cycles, never below the ~9k cycles of
+            //         its fp32 store epilogue (the role that small batches starve);
+            //   dX  : ~5.05k cycles per block and 256 x 256 output tile on ONE CTA.
+            // A role that streams both operands (K > 512) reaches ~70 % of its MMA rate.  The split minimises the
+            // slowest role's time per block over the admissible pair counts.
+            a = b = c = 0;
+            const double mma_dc = 8.0 * (((D + 63) / 64) * 64) / ((D + 63) / 64 > pr::MAX_KBLOCKS ? 0.7 : 1.0);
+            const double mma_dw = 8.0 * pl.Bp / (pl.Bp / 64 > pr::MAX_KBLOCKS ? 0.7 : 1.0);
+            const double cost_dc = n_res_dc * (mma_dc > 6650.0 ? mma_dc : 6650.0);
+            const double cost_dw = n_res_dw * (mma_dw > 8950.0 ? mma_dw : 8950.0);
+            const double cost_dx = tiles * 5053.0 / 2.0;
+            double best = 1e300;
+            for (int aa = n_res_dc; aa <= pairs; aa += n_res_dc)
+                for (int bb = n_res_dw; aa + bb <= pairs; bb += n_res_dw) {
+                    const int cc = (pairs - aa - bb) / dx_unit * dx_unit;
+                    if (cc < dx_unit) break;
+                    const double ta = cost_dc / aa, tb = cost_dw / bb, tc = cost_dx / cc;
+                    const double t = ta > tb ? (ta > tc ? ta : tc) : (tb > tc ? tb : tc);
+                    if (t < best) { best = t; a = aa; b = bb; c = cc; }
+                }
         }
         a = a / n_res_dc * n_res_dc;
         b = b / n_res_dw * n_res_dw;

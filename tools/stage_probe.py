@@ -1,6 +1,6 @@
 """Forward / backward kernel times per shape and per kernel-selection knob (diagnostic library: ARCFACE_B200_DIAG=1).
 
-    ARCFACE_B200_DIAG=1 python tools/stage_probe.py 512,1024,125000 256,1792,100000 [--splits 24,32,16;30,28,16] [--prof]
+    python tools/stage_probe.py 512,1024,125000 "256,1792,100000@11,49,12;9,49,16" [--splits "24,32,16;30,28,16"] [--prof]
 
 For every shape: the fused forward (K1(w)+K2) with the CTA-pair kernels and with the one-CTA streaming kernel, and the
 backward as the single launch (default role split, then every --splits entry), as three CTA-pair launches, and as the
@@ -49,6 +49,10 @@ def setenv(**kw):
 
 
 for spec in args:
+    shape_splits = list(splits)
+    if "@" in spec:   # B,D,C@a,b,c;a,b,c : role splits tried for this shape only
+        spec, sp = spec.split("@")
+        shape_splits += sp.split(";")
     B, D, C = (int(v) for v in spec.split(","))
     g = torch.Generator(device=dev).manual_seed(0)
     bound = math.sqrt(6.0 / (C + D))
@@ -71,7 +75,7 @@ for spec in args:
     def bwd():
         ops.backward(xhat, xhat_t, what, inv_nw, lse, omp, lm.dphi, lm.label_local, 64.0, 1.0 / B, dw_out=dw)
 
-    variants = [("fused default", {})] + [("fused " + sp, {"BWD_SPLIT": sp}) for sp in splits] + \
+    variants = [("fused default", {})] + [("fused " + sp, {"BWD_SPLIT": sp}) for sp in shape_splits] + \
                [("3 pair launches", {"BWD_IMPL": "split"}), ("generic", {"BWD_IMPL": "generic"})]
     for name, env in variants:
         setenv(**env)
