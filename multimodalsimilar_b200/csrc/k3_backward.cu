@@ -799,8 +799,12 @@ struct BwdDWpT : pr::PairDefaults {
     // bandwidth); 128-bit global stores straight from registers (thread = class row) are 4x slower still (32
     // half-sectors per warp instruction); round 2: re-reading the staging buffer with eight lanes per row and
     // storing full 128-byte lines with st.global.v4 (no proxy fence, no TMA) ~7.8k; 256-bit stores straight from
-    // registers (STG.E.ENL2.256, one full sector per lane) ~8.8k -- a store instruction that touches 32 different
-    // lines costs ~550 cycles here.  The TMA store stays.
+    // registers (STG.E.ENL2.256, one full sector per lane) ~8.8k; sixteen epilogue warps (four per lane quadrant, 2 KB
+    // boxes of 16 columns, registers traded with setmaxnreg) ~9.8k per tile in total.  Every variant lands at
+    // 13-16 bytes per clock and SM: the fp32 gradient leaves an SM no faster than that whatever issues the stores
+    // (a device-wide copy kernel writes ~11.5 B/clk/SM at the measured HBM peak), i.e. a dW tile (128 KB per CTA) costs
+    // >= 8.2k cycles against 4.1k of MMA.  The dW role is bound by the store path of its SMs, which is why the role
+    // split gives it the largest share; the epilogue's form is not the lever.
     static constexpr bool STAGING = true;
     static constexpr bool RES_A = false;
     static constexpr int NCOL = 2 * pr::ROWS;
