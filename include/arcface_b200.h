@@ -45,6 +45,14 @@ extern "C" {
 #define ARCFACE_B200_E_CUDA (-5)      /* a CUDA runtime / driver call failed */
 #define ARCFACE_B200_E_ARG (-6)       /* null pointer or invalid scalar */
 
+/* Precision modes of the cosine contraction (the `precision` keyword of the module).
+ *   BF16   : bf16 operands, fp32 accumulation -- the throughput mode (logits within ~2e-2 * s / 30 of fp32).
+ *   BF16X3 : every normalised value is a bf16 pair hi + lo and the contraction keeps hi.hi + hi.lo + lo.hi
+ *            (three tensor-core products in one fp32 accumulator): cosines within 1e-5 of fp32, i.e. better than
+ *            the "1e-4 under a TF32 mode" of the north star, on the same tcgen05 kind::f16 kernels. */
+#define ARCFACE_B200_PREC_BF16 0
+#define ARCFACE_B200_PREC_BF16X3 1
+
 #define ARCFACE_B200_MAX_BATCH 2048
 
 int32_t arcface_b200_version(int32_t* major, int32_t* minor);
@@ -57,6 +65,13 @@ int32_t arcface_b200_device_ok(void);
  * dst_t (nullable) additionally receives the transpose, dst_t[d * ld_t + r], for the dW GEMM. */
 int32_t arcface_b200_normalize_cast(const float* src, int64_t rows, int32_t D, uint16_t* dst, float* inv_norm,
                                     uint16_t* dst_t, int64_t ld_t, void* stream);
+
+/* K1 of the ARCFACE_B200_PREC_BF16X3 mode: each normalised value v as the bf16 pair hi = bf16(v), lo = bf16(v - hi),
+ * the row written three times along the contraction dimension -- dst3 [rows][3 D]: order 0 (embeddings) [hi|hi|lo],
+ * order 1 (class weights) [hi|lo|hi] -- so that the bf16 GEMMs over 3 D columns (arcface_b200_forward_stats /
+ * _logits / _cosine_topk with D := 3 D) accumulate hi.hi + hi.lo + lo.hi in fp32.  dst_t (nullable): transposed hi. */
+int32_t arcface_b200_normalize_cast3(const float* src, int64_t rows, int32_t D, int32_t order, uint16_t* dst3,
+                                     float* inv_norm, uint16_t* dst_t, int64_t ld_t, void* stream);
 
 /* Label column in fp32 + margin (arcface.py:49-55 restricted to the label column, the only place the
  * reference's one-hot blend at :58-60 uses phi).  For every row b whose label falls in this shard:
@@ -177,6 +192,25 @@ int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* xhat_t, int6
                               const int32_t* label_local, int32_t B, int32_t D, int64_t C_local, float s,
                               float grad_scale, const float* grad_loss_dev, float* dxhat, float* dw,
                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* arcface_b200_backward with a precision mode.  prec = ARCFACE_B200_PREC_BF16X3: `xhat` [B][3 D] and `what`
+ * [C_local][3 D] are the rows written by arcface_b200_normalize_cast3 (orders 0 and 1), `xhat_t` the transposed hi part;
+ * the probabilities are recomputed from the three-term product, the gradient GEMMs run on bf16 dC and the hi parts. */
+int32_t arcface_b200_backward_prec(const uint16_t* xhat, const uint16_t* xhat_t, int64_t ld_t, const uint16_t* what,
+                                   const float* inv_nw, const float* lse, const float* one_minus_p, const float* dphi,
+                                   const int32_t* label_local, int32_t B, int32_t D, int64_t C_local, float s,
+                                   float grad_scale, const float* grad_loss_dev, float* dxhat, float* dw,
+                                   void* workspace, size_t workspace_bytes, int32_t prec, void* stream);
+
+/* The step before the head in the two-stream model (multimodal_classifier.py:50-56):
+ *   out = cat(F.normalize(a), F.normalize(b), dim = 1),  a [B][D1], b [B][D2], out [B][D1 + D2] fp32
+ * in one pass; inv1 / inv2 [B] receive 1 / max(||.||, 1e-12).  D1, D2 multiples of 4. */
+int32_t arcface_b200_two_stream_concat(const float* a, const float* b, int32_t B, int32_t D1, int32_t D2, float* out,
+                                       float* inv1, float* inv2, void* stream);
+/* Its backward: da = (g_a - e_a (e_a . g_a)) * inv1, db likewise, with e = the halves of `emb` (the forward's output)
+ * and g = the halves of `grad` [B][D1 + D2]. */
+int32_t arcface_b200_two_stream_concat_bwd(const float* emb, const float* inv1, const float* inv2, const float* grad,
+                                           int32_t B, int32_t D1, int32_t D2, float* da, float* db, void* stream);
 
 /* Normalise backward for the embeddings: dx[b] = (dxhat[b] - (xhat[b] . dxhat[b]) xhat[b]) * inv_nx[b]
  * with xhat = x * inv_nx in fp32. */

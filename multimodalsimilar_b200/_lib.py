@@ -28,6 +28,7 @@ SIGNATURES = {
     "arcface_b200_last_error": (c_char_p, []),
     "arcface_b200_device_ok": (c_int32, []),
     "arcface_b200_normalize_cast": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "arcface_b200_normalize_cast3": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "arcface_b200_label_margin": (
         c_int32,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64, c_int64, c_int64,
@@ -68,6 +69,15 @@ SIGNATURES = {
         [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
          c_int64, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
     ),
+    "arcface_b200_backward_prec": (
+        c_int32,
+        [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+         c_int64, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int32, c_void_p],
+    ),
+    "arcface_b200_two_stream_concat": (
+        c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "arcface_b200_two_stream_concat_bwd": (
+        c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "arcface_b200_normalize_bwd_x": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "arcface_b200_scale_grads": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "arcface_b200_adamw_normalize": (

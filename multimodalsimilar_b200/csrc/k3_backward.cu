@@ -200,6 +200,7 @@ struct BwdDW {
         int q_slots;
         const float* inv_nw;
         const __nv_bfloat16* what;
+        int64_t ldw;  // row stride of what (D; 3 D in the bf16x3 mode, whose rows start with the hi part)
     };
 
     __device__ static void prologue(const Params&, uint8_t*, int) {}
@@ -248,7 +249,7 @@ struct BwdDW {
             if (cvalid)
                 for (int sl = 0; sl < p.q_slots; ++sl) qc += p.q[static_cast<int64_t>(sl) * p.C + c];
             const float inw = cvalid ? p.inv_nw[c] : 0.f;
-            const __nv_bfloat16* wrow = p.what + static_cast<int64_t>(cvalid ? c : 0) * p.D;
+            const __nv_bfloat16* wrow = p.what + static_cast<int64_t>(cvalid ? c : 0) * p.ldw;
             uint4 wcur[4], wnext[4];
             load_w(wrow, cvalid, t.n0, wcur);
 #pragma unroll 1
@@ -481,6 +482,7 @@ struct BwdDWr {
         int q_slots;
         const float* inv_nw;
         const __nv_bfloat16* what;
+        int64_t ldw;
     };
     static constexpr int EXTRA_BYTES = 0;
 
@@ -501,7 +503,7 @@ struct BwdDWr {
         __device__ __forceinline__ void prefetch(int i) {
             const int c = p.c_begin + i * rs::BM + quad * 32 + lane;
             const bool cvalid = c < p.C;
-            const __nv_bfloat16* wrow = p.what + static_cast<int64_t>(cvalid ? c : 0) * p.D;
+            const __nv_bfloat16* wrow = p.what + static_cast<int64_t>(cvalid ? c : 0) * p.ldw;
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
                 const int d = d0 + g * 8;
@@ -817,6 +819,7 @@ struct BwdDWpT : pr::PairDefaults {
         int q_slots;  // <= 8
         const float* inv_nw;
         const __nv_bfloat16* what;
+        int64_t ldw;
         float* dw;  // out [C][D] fp32
         Ring ring;  // FUSED only
         int evict_first;  // 1: dW is stored with an L2 evict-first policy (it is never read back by this kernel)
@@ -877,7 +880,7 @@ struct BwdDWpT : pr::PairDefaults {
         __device__ __forceinline__ void fetch_w(int i, int grp, uint4 (&w)[4]) const {
             const int c = class_of(i);
             const bool cvalid = c < p.C;
-            const __nv_bfloat16* wrow = p.what + static_cast<int64_t>(cvalid ? c : 0) * p.D;
+            const __nv_bfloat16* wrow = p.what + static_cast<int64_t>(cvalid ? c : 0) * p.ldw;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 const int d = d0 + grp * 32 + g * 8;
@@ -1132,12 +1135,14 @@ static bool env_is(const char* name, const char* value) {  // diagnostic builds 
 //   ARCFACE_B200_BWD_SPLIT=a,b,c    CTA pairs given to the dC^T / dW / dX roles of the single-launch backward
 //   ARCFACE_B200_BWD_RING=<n>       ring slots of the single-launch backward
 //   ARCFACE_B200_BWD_CHUNK_MB=<n>   cap of the dC^T scratch in MiB
-static BwdPlan plan_backward(int B, int D, int64_t C, int nsm) {
+// Ds = depth of the S^T recompute (D; 3 D in the bf16x3 mode): only the role split depends on it.
+static BwdPlan plan_backward(int B, int D, int64_t C, int nsm, int Ds = 0) {
+    if (Ds <= 0) Ds = D;
     BwdPlan pl;
     pl.Bp = ((B + 63) / 64) * 64;
     if (nsm < 1) nsm = 148;
     const bool generic = env_is("ARCFACE_B200_BWD_IMPL", "generic");
-    pl.dc_rs = !generic && (D + 63) / 64 <= rs::MAX_KBLOCKS;
+    pl.dc_rs = !generic && (Ds + 63) / 64 <= rs::MAX_KBLOCKS;
     pl.dw_rs = !generic && pl.Bp / 64 <= rs::MAX_KBLOCKS;
     pl.dx2 = !generic;
     // CTA pairs for every shape whose q partial sums fit the dW epilogue's eight slots (B <= 1024): the reused operand
@@ -1171,7 +1176,7 @@ static BwdPlan plan_backward(int B, int D, int64_t C, int nsm) {
             // A role that streams both operands (K > 512) reaches ~70 % of its MMA rate.  The split minimises the
             // slowest role's time per block over the admissible pair counts.
             a = b = c = 0;
-            const double mma_dc = 8.0 * (((D + 63) / 64) * 64) / ((D + 63) / 64 > pr::MAX_KBLOCKS ? 0.7 : 1.0);
+            const double mma_dc = 8.0 * (((Ds + 63) / 64) * 64) / ((Ds + 63) / 64 > pr::MAX_KBLOCKS ? 0.7 : 1.0);
             const double mma_dw = 8.0 * pl.Bp / (pl.Bp / 64 > pr::MAX_KBLOCKS ? 0.7 : 1.0);
             const double cost_dc = n_res_dc * (mma_dc > 6650.0 ? mma_dc : 6650.0);
             const double cost_dw = n_res_dw * (mma_dw > 8950.0 ? mma_dw : 8950.0);
@@ -1286,12 +1291,47 @@ extern "C" int32_t arcface_b200_backward_launches(int32_t B, int32_t D, int64_t 
     return ARCFACE_B200_OK;
 }
 
+static int32_t backward_impl(const uint16_t* xhat, const uint16_t* xhat_t, int64_t ld_t,
+                             const uint16_t* what, const float* inv_nw, const float* lse,
+                             const float* one_minus_p, const float* dphi, const int32_t* label_local,
+                             int32_t B, int32_t D, int64_t C_local, float s, float grad_scale,
+                             const float* grad_loss_dev, float* dxhat, float* dw, void* workspace,
+                             size_t workspace_bytes, int32_t prec, void* stream);
+
 extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* xhat_t, int64_t ld_t,
                                          const uint16_t* what, const float* inv_nw, const float* lse,
                                          const float* one_minus_p, const float* dphi, const int32_t* label_local,
                                          int32_t B, int32_t D, int64_t C_local, float s, float grad_scale,
                                          const float* grad_loss_dev, float* dxhat, float* dw, void* workspace,
                                          size_t workspace_bytes, void* stream) {
+    return backward_impl(xhat, xhat_t, ld_t, what, inv_nw, lse, one_minus_p, dphi, label_local, B, D, C_local, s,
+                         grad_scale, grad_loss_dev, dxhat, dw, workspace, workspace_bytes, ARCFACE_B200_PREC_BF16, stream);
+}
+
+extern "C" int32_t arcface_b200_backward_prec(const uint16_t* xhat, const uint16_t* xhat_t, int64_t ld_t,
+                                              const uint16_t* what, const float* inv_nw, const float* lse,
+                                              const float* one_minus_p, const float* dphi, const int32_t* label_local,
+                                              int32_t B, int32_t D, int64_t C_local, float s, float grad_scale,
+                                              const float* grad_loss_dev, float* dxhat, float* dw, void* workspace,
+                                              size_t workspace_bytes, int32_t prec, void* stream) {
+    AB_REQUIRE(prec == ARCFACE_B200_PREC_BF16 || prec == ARCFACE_B200_PREC_BF16X3, ARCFACE_B200_E_ARG,
+               "backward: unknown precision mode %d", prec);
+    return backward_impl(xhat, xhat_t, ld_t, what, inv_nw, lse, one_minus_p, dphi, label_local, B, D, C_local, s,
+                         grad_scale, grad_loss_dev, dxhat, dw, workspace, workspace_bytes, prec, stream);
+}
+
+// prec = ARCFACE_B200_PREC_BF16X3: `xhat` / `what` are the 3 D wide rows of arcface_b200_normalize_cast3 ([hi|hi|lo] /
+// [hi|lo|hi]).  The probabilities are recomputed from the three-term product (contraction depth 3 D, the same
+// operands the forward used), so dC carries no bf16 logit noise; the two gradient GEMMs run on dC (bf16) and the hi
+// parts (xhat_t, the first D columns of `what`).
+static int32_t backward_impl(const uint16_t* xhat, const uint16_t* xhat_t, int64_t ld_t,
+                             const uint16_t* what, const float* inv_nw, const float* lse,
+                             const float* one_minus_p, const float* dphi, const int32_t* label_local,
+                             int32_t B, int32_t D, int64_t C_local, float s, float grad_scale,
+                             const float* grad_loss_dev, float* dxhat, float* dw, void* workspace,
+                             size_t workspace_bytes, int32_t prec, void* stream) {
+    const int Ds = prec == ARCFACE_B200_PREC_BF16X3 ? 3 * D : D;   // depth of the S^T recompute
+    const int64_t ldw = Ds;                                         // row stride of xhat / what
     if (int32_t rc = check_arch()) return rc;
     AB_REQUIRE(xhat && xhat_t && what && inv_nw && lse && one_minus_p && dphi && label_local && dxhat && dw && workspace,
                ARCFACE_B200_E_ARG, "backward: null pointer");
@@ -1301,7 +1341,7 @@ extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* x
                "backward: pointers must be 16-byte aligned");
     AB_REQUIRE(s > 0.f, ARCFACE_B200_E_ARG, "backward: scale s must be positive");
     const int nsm = sm_count();
-    const BwdPlan pl = plan_backward(B, D, C_local, nsm);
+    const BwdPlan pl = plan_backward(B, D, C_local, nsm, Ds);
     AB_REQUIRE(workspace_bytes >= pl.total, ARCFACE_B200_E_WORKSPACE, "backward: workspace %zu < required %zu",
                workspace_bytes, pl.total);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1313,12 +1353,12 @@ extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* x
     AB_CHECK_CUDA(cudaMemsetAsync(dxhat, 0, static_cast<size_t>(B) * D * sizeof(float), st));
 
     CUtensorMap tm_w_k, tm_x_k, tm_dct_k, tm_xt_k, tm_dct_mn, tm_w_mn, tm_dct_out, tm_dw_out, tm_dx_out;
-    if (int32_t rc = make_tmap_kmajor(&tm_w_k, what, D, C_local, D, BLOCK_M)) return rc;
-    if (int32_t rc = make_tmap_kmajor(&tm_x_k, xhat, D, B, D, (pl.dc_rs || pl.dc_pair) ? rs::BN : BwdDC::BLOCK_N)) return rc;
+    if (int32_t rc = make_tmap_kmajor(&tm_w_k, what, Ds, C_local, ldw, BLOCK_M)) return rc;
+    if (int32_t rc = make_tmap_kmajor(&tm_x_k, xhat, Ds, B, ldw, (pl.dc_rs || pl.dc_pair) ? rs::BN : BwdDC::BLOCK_N)) return rc;
     if (int32_t rc = make_tmap_kmajor(&tm_dct_k, dct, B, pl.chunk_classes, pl.Bp, BLOCK_M)) return rc;
     if (int32_t rc = make_tmap_kmajor(&tm_xt_k, xhat_t, B, D, ld_t, (pl.dw_rs || pl.dw_pair) ? rs::BN : BwdDW::BLOCK_N)) return rc;
     if (int32_t rc = make_tmap_mnmajor(&tm_dct_mn, dct, B, pl.chunk_classes, pl.Bp)) return rc;
-    if (int32_t rc = make_tmap_mnmajor(&tm_w_mn, what, D, C_local, D)) return rc;
+    if (int32_t rc = make_tmap_mnmajor(&tm_w_mn, what, D, C_local, ldw)) return rc;
     if (int32_t rc = make_tmap_store(&tm_dct_out, dct, 2, pl.Bp, pl.chunk_classes, pl.Bp)) return rc;
     if (int32_t rc = make_tmap_store(&tm_dw_out, dw, 4, D, C_local, D)) return rc;
     if (int32_t rc = make_tmap_store(&tm_dx_out, dxhat, 4, D, B, D)) return rc;
@@ -1361,7 +1401,7 @@ extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* x
         }
         {
             BwdDCpT<true>::Params& p = fp.dc;
-            pr::core_set_k<BwdDCpT<true>>(p.core, D, BwdDCpT<true>::EXTRA_BYTES);
+            pr::core_set_k<BwdDCpT<true>>(p.core, Ds, BwdDCpT<true>::EXTRA_BYTES);
             p.core.s_blocks = pl.n_blocks;
             p.core.s_row0 = 0;
             p.core.n_res = n_res_dc;
@@ -1384,6 +1424,7 @@ extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* x
             p.C = C; p.D = D; p.c_begin = 0;
             p.q = q; p.q_slots = pl.q_slots; p.inv_nw = inv_nw;
             p.what = reinterpret_cast<const __nv_bfloat16*>(what);
+            p.ldw = ldw;
             p.dw = dw;
             p.evict_first = env_is("ARCFACE_B200_BWD_EVICT", "1") ? 1 : 0;
             p.ring = ring;
@@ -1470,7 +1511,7 @@ extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* x
         // ---- dC^T (and q) for this chunk
         if (pl.dc_pair) {
             BwdDCp::Params p;
-            pr::core_set_k<BwdDCp>(p.core, D, BwdDCp::EXTRA_BYTES);
+            pr::core_set_k<BwdDCp>(p.core, Ds, BwdDCp::EXTRA_BYTES);
             p.core.s_blocks = (cn + BwdDCp::NCOL - 1) / BwdDCp::NCOL;
             p.core.s_row0 = static_cast<int>(c0);
             p.core.n_res = (B + BwdDCp::NCOL - 1) / BwdDCp::NCOL;
@@ -1487,7 +1528,7 @@ extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* x
                 return rc;
         } else if (pl.dc_rs) {
             BwdDCr::Params p;
-            p.core.kblocks = (D + rs::BK - 1) / rs::BK;
+            p.core.kblocks = (Ds + rs::BK - 1) / rs::BK;
             p.core.m_blocks = c_blocks;
             p.core.s_row0 = static_cast<int>(c0);
             p.core.n_res = (B + rs::BN - 1) / rs::BN;
@@ -1503,7 +1544,7 @@ extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* x
                 return rc;
         } else {
             BwdDC::Params p;
-            p.B = B; p.D = D; p.C = C; p.Bp = pl.Bp;
+            p.B = B; p.D = Ds; p.C = C; p.Bp = pl.Bp;
             p.c_begin = static_cast<int>(c0); p.c_blocks = c_blocks; p.n_tiles = n_tiles;
             p.s_log2e = s * LOG2E_B; p.coef = s * grad_scale; p.grad_dev = grad_loss_dev;
             p.lse = lse; p.one_minus_p = one_minus_p; p.dphi = dphi; p.label_local = label_local;
@@ -1524,6 +1565,7 @@ extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* x
             p.C = C; p.D = D; p.c_begin = static_cast<int>(c0);
             p.q = q; p.q_slots = pl.q_slots; p.inv_nw = inv_nw;
             p.what = reinterpret_cast<const __nv_bfloat16*>(what);
+            p.ldw = ldw;
             p.dw = dw;
             p.evict_first = env_is("ARCFACE_B200_BWD_EVICT", "1") ? 1 : 0;
             int groups = (nsm / 2) / p.core.n_res;
@@ -1541,6 +1583,7 @@ extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* x
             p.C = C; p.D = D; p.c_begin = static_cast<int>(c0);
             p.q = q; p.q_slots = pl.q_slots; p.inv_nw = inv_nw;
             p.what = reinterpret_cast<const __nv_bfloat16*>(what);
+            p.ldw = ldw;
             int groups = nsm / p.core.n_res;
             if (groups < 1) groups = 1;
             if (groups > c_blocks) groups = c_blocks;
@@ -1551,6 +1594,7 @@ extern "C" int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* x
             p.B = B; p.D = D; p.C = C;
             p.c_begin = static_cast<int>(c0); p.c_blocks = c_blocks; p.dn_tiles = dn_tiles;
             p.q = q; p.q_slots = pl.q_slots; p.inv_nw = inv_nw; p.what = reinterpret_cast<const __nv_bfloat16*>(what);
+            p.ldw = ldw;
             const int total = c_blocks * dn_tiles;
             const int grid = total < nsm ? total : nsm;
             if (int32_t rc = launch_gemm<BwdDW>(tm_dct_k, tm_xt_k, tm_dw_out, p, grid, 0, st)) return rc;

@@ -107,6 +107,132 @@ __global__ void __launch_bounds__(256) normalize_cast_generic_kernel(const float
     }
 }
 
+// K1 for the high-precision mode (precision = 'bf16x3'): every normalised value v is kept as a pair of bf16,
+// hi = bf16(v) and lo = bf16(v - hi), and the row is written THREE times along the contraction dimension so that the
+// unchanged bf16 tensor-core GEMM over 3 D columns computes  x_hi.w_hi + x_hi.w_lo + x_lo.w_hi  (everything but the
+// 2^-18 lo.lo term) in its fp32 accumulator:
+//   order 0 (embeddings)   : [hi | hi | lo]
+//   order 1 (class weights): [hi | lo | hi]
+// Optional transpose of the hi part ([D][ld_t], the dW GEMM's operand).  One warp per row, two passes (the second
+// served by L1/L2); a parity mode, not a throughput path.
+__global__ void __launch_bounds__(256) normalize_cast3_kernel(const float* __restrict__ src, int64_t rows, int D,
+                                                              int order, __nv_bfloat16* __restrict__ dst,
+                                                              float* __restrict__ inv_norm,
+                                                              __nv_bfloat16* __restrict__ dst_t, int64_t ld_t) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* rp = src + row * D;
+    float ss = 0.f;
+    for (int d = lane * 4; d < D; d += 128) {
+        const float4 a = *reinterpret_cast<const float4*>(rp + d);
+        ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+    }
+    ss = warp_sum(ss);
+    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    if (lane == 0) inv_norm[row] = inv;
+    __nv_bfloat16* op = dst + row * 3 * static_cast<int64_t>(D);
+    const int off_hi2 = order == 0 ? D : 2 * D;   // second copy of hi
+    const int off_lo = order == 0 ? 2 * D : D;
+    for (int d = lane * 4; d < D; d += 128) {
+        const float4 a = *reinterpret_cast<const float4*>(rp + d);
+        const float f[4] = {a.x * inv, a.y * inv, a.z * inv, a.w * inv};
+        float h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            h[j] = __bfloat162float(__float2bfloat16_rn(f[j]));
+            l[j] = f[j] - h[j];
+        }
+        uint2 hi, lo;
+        hi.x = pack_bf16x2(h[0], h[1]);
+        hi.y = pack_bf16x2(h[2], h[3]);
+        lo.x = pack_bf16x2(l[0], l[1]);
+        lo.y = pack_bf16x2(l[2], l[3]);
+        *reinterpret_cast<uint2*>(op + d) = hi;
+        *reinterpret_cast<uint2*>(op + off_hi2 + d) = hi;
+        *reinterpret_cast<uint2*>(op + off_lo + d) = lo;
+        if (dst_t != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst_t[static_cast<int64_t>(d + j) * ld_t + row] = __float2bfloat16_rn(h[j]);
+        }
+    }
+}
+
+// The step before the head in the two-stream model (multimodal_classifier.py:50-56):
+//   emb = cat(F.normalize(img_emb), F.normalize(title_emb), dim = 1)
+// as ONE pass: one warp per row, both halves normalised and written side by side (the reference runs two norm
+// reductions, two divisions and a concat: five launches, each a B x D round trip).  inv1 / inv2 keep 1 / max(||.||, eps)
+// for the backward below.
+__global__ void __launch_bounds__(256)
+two_stream_concat_kernel(const float* __restrict__ a, const float* __restrict__ b, int B, int D1, int D2,
+                         float* __restrict__ out, float* __restrict__ inv1, float* __restrict__ inv2) {
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= B) return;
+    const float* ap = a + static_cast<int64_t>(r) * D1;
+    const float* bp = b + static_cast<int64_t>(r) * D2;
+    float sa = 0.f, sb = 0.f;
+    for (int d = lane * 4; d < D1; d += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(ap + d);
+        sa += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    for (int d = lane * 4; d < D2; d += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(bp + d);
+        sb += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    sa = warp_sum(sa);
+    sb = warp_sum(sb);
+    const float ia = 1.0f / fmaxf(sqrtf(sa), 1e-12f), ib = 1.0f / fmaxf(sqrtf(sb), 1e-12f);
+    if (lane == 0) { inv1[r] = ia; inv2[r] = ib; }
+    float* op = out + static_cast<int64_t>(r) * (D1 + D2);
+    for (int d = lane * 4; d < D1; d += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(ap + d);
+        *reinterpret_cast<float4*>(op + d) = make_float4(v.x * ia, v.y * ia, v.z * ia, v.w * ia);
+    }
+    for (int d = lane * 4; d < D2; d += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(bp + d);
+        *reinterpret_cast<float4*>(op + D1 + d) = make_float4(v.x * ib, v.y * ib, v.z * ib, v.w * ib);
+    }
+}
+
+// Backward of the above: with e = a normalised half of `emb` and g the matching half of the incoming gradient,
+// d(input) = (g - e (e . g)) * inv  (F.normalize's backward), for both halves in one pass.
+__global__ void __launch_bounds__(256)
+two_stream_concat_bwd_kernel(const float* __restrict__ emb, const float* __restrict__ inv1, const float* __restrict__ inv2,
+                             const float* __restrict__ grad, int B, int D1, int D2, float* __restrict__ da,
+                             float* __restrict__ db) {
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= B) return;
+    const int D = D1 + D2;
+    const float* ep = emb + static_cast<int64_t>(r) * D;
+    const float* gp = grad + static_cast<int64_t>(r) * D;
+    float ra = 0.f, rb = 0.f;
+    for (int d = lane * 4; d < D1; d += 128) {
+        const float4 e = *reinterpret_cast<const float4*>(ep + d), g = *reinterpret_cast<const float4*>(gp + d);
+        ra += e.x * g.x + e.y * g.y + e.z * g.z + e.w * g.w;
+    }
+    for (int d = lane * 4; d < D2; d += 128) {
+        const float4 e = *reinterpret_cast<const float4*>(ep + D1 + d), g = *reinterpret_cast<const float4*>(gp + D1 + d);
+        rb += e.x * g.x + e.y * g.y + e.z * g.z + e.w * g.w;
+    }
+    ra = warp_sum(ra);
+    rb = warp_sum(rb);
+    const float ia = inv1[r], ib = inv2[r];
+    float* ap = da + static_cast<int64_t>(r) * D1;
+    float* bp = db + static_cast<int64_t>(r) * D2;
+    for (int d = lane * 4; d < D1; d += 128) {
+        const float4 e = *reinterpret_cast<const float4*>(ep + d), g = *reinterpret_cast<const float4*>(gp + d);
+        *reinterpret_cast<float4*>(ap + d) = make_float4((g.x - e.x * ra) * ia, (g.y - e.y * ra) * ia,
+                                                         (g.z - e.z * ra) * ia, (g.w - e.w * ra) * ia);
+    }
+    for (int d = lane * 4; d < D2; d += 128) {
+        const float4 e = *reinterpret_cast<const float4*>(ep + D1 + d), g = *reinterpret_cast<const float4*>(gp + D1 + d);
+        *reinterpret_cast<float4*>(bp + d) = make_float4((g.x - e.x * rb) * ib, (g.y - e.y * rb) * ib,
+                                                         (g.z - e.z * rb) * ib, (g.w - e.w * rb) * ib);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 label_margin_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ inv_nx,
                     const float* __restrict__ inv_nw, const int64_t* __restrict__ label, int B, int D, int64_t C_local,
@@ -430,6 +556,54 @@ extern "C" int32_t arcface_b200_normalize_cast(const float* src, int64_t rows, i
     else if (nch <= 8) normalize_cast_kernel<8><<<grid, block, 0, st>>>(src, rows, D, d, inv_norm, dt, ld_t);
     else if (nch <= 12) normalize_cast_kernel<12><<<grid, block, 0, st>>>(src, rows, D, d, inv_norm, dt, ld_t);
     else normalize_cast_generic_kernel<<<grid, block, 0, st>>>(src, rows, D, d, inv_norm, dt, ld_t);
+    AB_CHECK_CUDA(cudaGetLastError());
+    return ARCFACE_B200_OK;
+}
+
+extern "C" int32_t arcface_b200_normalize_cast3(const float* src, int64_t rows, int32_t D, int32_t order, uint16_t* dst3,
+                                                float* inv_norm, uint16_t* dst_t, int64_t ld_t, void* stream) {
+    if (int32_t rc = check_arch()) return rc;
+    AB_REQUIRE(src && dst3 && inv_norm, ARCFACE_B200_E_ARG, "normalize_cast3: null pointer");
+    AB_REQUIRE(rows >= 0 && D >= 8 && D % 8 == 0, ARCFACE_B200_E_SHAPE, "normalize_cast3: D=%d must be a positive multiple of 8", D);
+    AB_REQUIRE(order == 0 || order == 1, ARCFACE_B200_E_ARG, "normalize_cast3: order must be 0 (hi|hi|lo) or 1 (hi|lo|hi)");
+    AB_REQUIRE(aligned16(src) && aligned16(dst3), ARCFACE_B200_E_LAYOUT, "normalize_cast3: pointers must be 16-byte aligned");
+    AB_REQUIRE(dst_t == nullptr || ld_t >= rows, ARCFACE_B200_E_LAYOUT, "normalize_cast3: ld_t < rows");
+    if (rows == 0) return ARCFACE_B200_OK;
+    const int wpb = 8;
+    const int64_t nblk = (rows + wpb - 1) / wpb;
+    AB_REQUIRE(nblk < (1ll << 31), ARCFACE_B200_E_SHAPE, "normalize_cast3: too many rows");
+    normalize_cast3_kernel<<<static_cast<unsigned>(nblk), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        src, rows, D, order, reinterpret_cast<__nv_bfloat16*>(dst3), inv_norm, reinterpret_cast<__nv_bfloat16*>(dst_t), ld_t);
+    AB_CHECK_CUDA(cudaGetLastError());
+    return ARCFACE_B200_OK;
+}
+
+extern "C" int32_t arcface_b200_two_stream_concat(const float* a, const float* b, int32_t B, int32_t D1, int32_t D2,
+                                                  float* out, float* inv1, float* inv2, void* stream) {
+    if (int32_t rc = check_arch()) return rc;
+    AB_REQUIRE(a && b && out && inv1 && inv2, ARCFACE_B200_E_ARG, "two_stream_concat: null pointer");
+    AB_REQUIRE(B >= 0 && D1 >= 4 && D2 >= 4 && D1 % 4 == 0 && D2 % 4 == 0, ARCFACE_B200_E_SHAPE,
+               "two_stream_concat: widths %d / %d must be positive multiples of 4", D1, D2);
+    AB_REQUIRE(aligned16(a) && aligned16(b) && aligned16(out), ARCFACE_B200_E_LAYOUT,
+               "two_stream_concat: pointers must be 16-byte aligned");
+    if (B == 0) return ARCFACE_B200_OK;
+    two_stream_concat_kernel<<<(B + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, B, D1, D2, out, inv1, inv2);
+    AB_CHECK_CUDA(cudaGetLastError());
+    return ARCFACE_B200_OK;
+}
+
+extern "C" int32_t arcface_b200_two_stream_concat_bwd(const float* emb, const float* inv1, const float* inv2,
+                                                      const float* grad, int32_t B, int32_t D1, int32_t D2, float* da,
+                                                      float* db, void* stream) {
+    if (int32_t rc = check_arch()) return rc;
+    AB_REQUIRE(emb && inv1 && inv2 && grad && da && db, ARCFACE_B200_E_ARG, "two_stream_concat_bwd: null pointer");
+    AB_REQUIRE(B >= 0 && D1 >= 4 && D2 >= 4 && D1 % 4 == 0 && D2 % 4 == 0, ARCFACE_B200_E_SHAPE,
+               "two_stream_concat_bwd: widths %d / %d must be positive multiples of 4", D1, D2);
+    AB_REQUIRE(aligned16(emb) && aligned16(grad) && aligned16(da) && aligned16(db), ARCFACE_B200_E_LAYOUT,
+               "two_stream_concat_bwd: pointers must be 16-byte aligned");
+    if (B == 0) return ARCFACE_B200_OK;
+    two_stream_concat_bwd_kernel<<<(B + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(emb, inv1, inv2, grad, B, D1,
+                                                                                            D2, da, db);
     AB_CHECK_CUDA(cudaGetLastError());
     return ARCFACE_B200_OK;
 }

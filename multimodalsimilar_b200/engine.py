@@ -33,6 +33,17 @@ class StepConfig:
     easy_margin: bool
     class_lo: int     # first global class id of the local weight rows
     c_total: int      # classes over all ranks
+    prec: int = 0     # PRECISIONS[...]: 0 = bf16 operands, 1 = bf16x3 (hi/lo pairs, three products per cosine)
+
+
+PRECISIONS = {"bf16": 0, "bf16x3": 1}   # the `precision` keyword of the modules -> ARCFACE_B200_PREC_*
+
+
+def precision_code(name) -> int:
+    try:
+        return PRECISIONS[name]
+    except KeyError:
+        raise ValueError("precision must be one of %s, got %r" % (sorted(PRECISIONS), name)) from None
 
 
 @dataclass
@@ -153,6 +164,9 @@ def _rows(K, xhat, w, label_local, cfg, w_cache, out=None):
     """(what, inv_nw, max, sum, arg): K1 (w) fused into K2, or K2 alone on the rows a fused optimiser step left
     behind (`w_cache` = (what, inv_nw), optim.FusedHeadAdamW)."""
     kw = {} if out is None else {"out": out}
+    if cfg.prec:   # bf16x3: K1 writes the three-part rows, K2 contracts over 3 D
+        what, inv_nw, _ = K.normalize_cast3(w, 1)
+        return (what, inv_nw) + tuple(K.forward_rows(xhat, what, label_local, cfg.s, cfg.class_lo, **kw))
     if w_cache is not None:
         what, inv_nw = w_cache
         return (what, inv_nw) + tuple(K.forward_rows(xhat, what, label_local, cfg.s, cfg.class_lo, **kw))
@@ -166,7 +180,10 @@ def forward_eager(K, group, x_local, w, y_local, cfg: StepConfig, packed_xy=None
     b_loc = x_local.shape[0]
     x_all, y_all = gather_batch(x_local, y_local, group, packed_xy, peer)
     B = x_all.shape[0]
-    xhat, inv_nx, xhat_t = K.normalize_cast(x_all, want_transpose=True)
+    if cfg.prec:
+        xhat, inv_nx, xhat_t = K.normalize_cast3(x_all, 0, want_transpose=True)
+    else:
+        xhat, inv_nx, xhat_t = K.normalize_cast(x_all, want_transpose=True)
     if R > 1 and B % 2 == 0 and hasattr(K, "finalize_rows_packed"):
         # the kernels fill one packed buffer, the exchange is one all-gather, the merge reads it in place
         buf, v_max, v_sum, v_z, v_arg = K.packed_stats(B, x_all.device)
@@ -194,8 +211,9 @@ def backward_eager(K, group, x_local, st: FwdState, grad_loss, cfg: StepConfig, 
     R, rank = _world(group), _rank(group)
     b_loc = x_local.shape[0]
     g = grad_loss.to(torch.float32).contiguous()
+    kw = {"prec": cfg.prec} if cfg.prec else {}
     dxhat_part, dw = K.backward(st.xhat, st.xhat_t, st.what, st.inv_nw, st.lse, st.omp, st.dphi, st.label_local,
-                                cfg.s, 1.0 / st.B, grad_loss_dev=g)
+                                cfg.s, 1.0 / st.B, grad_loss_dev=g, **kw)
     dx = None
     if need_dx:
         inv_loc = st.inv_nx if R == 1 else st.inv_nx[rank * b_loc:(rank + 1) * b_loc].contiguous()
@@ -389,7 +407,7 @@ def run_step(head, K, group, x, w, label, cfg: StepConfig, validate_labels: bool
     # normalised rows left behind by a fused optimiser step: valid while the weight has not been touched since
     w_cache = None
     cache = _W_CACHE.get(head)
-    if cache is not None and x.is_cuda and cache[2] == w._version and cache[3] == w.data_ptr():
+    if cache is not None and x.is_cuda and cache[2] == w._version and cache[3] == w.data_ptr() and not cfg.prec:
         w_cache = (cache[0], cache[1])
     peer = _peer_for(head, group, x) if (group is not None and x.is_cuda and getattr(head, "use_p2p", False)) else None
     guard = None

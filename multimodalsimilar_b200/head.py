@@ -141,9 +141,10 @@ class ArcMarginProduct(nn.Module):
     # has only the reference's attributes in its __dict__
     validate_labels = False
     use_cuda_graph = True
+    precision = "bf16"
 
     def __init__(self, in_feature=128, out_feature=10575, s=64.0, m=0.40, easy_margin=False, *,
-                 in_features=None, out_features=None, validate_labels=False, use_cuda_graph=True):
+                 in_features=None, out_features=None, validate_labels=False, use_cuda_graph=True, precision="bf16"):
         super().__init__()
         if in_features is not None:
             in_feature = in_features
@@ -158,6 +159,10 @@ class ArcMarginProduct(nn.Module):
         self.easy_margin = easy_margin
         self.validate_labels = validate_labels
         self.use_cuda_graph = use_cuda_graph
+        # 'bf16' (throughput: bf16 operands, fp32 accumulation) or 'bf16x3' (parity: hi/lo bf16 pairs, three
+        # tensor-core products per cosine -- cosines within 1e-5 of the reference's fp32 head, ~3x the GEMM work)
+        engine.precision_code(precision)
+        self.precision = precision
         self.cos_m, self.sin_m, self.th, self.mm = ops.margin_constants(m)
 
     def update_m(self, delta):
@@ -183,11 +188,23 @@ class ArcMarginProduct(nn.Module):
         """Fused head + mean softmax cross-entropy.  Returns (loss [], argmax int64 [B])."""
         x, label = self._prep(x, label)
         w = self.weight if self.weight.is_contiguous() else self.weight.contiguous()
-        cfg = engine.StepConfig(float(self.s), float(self.m), bool(self.easy_margin), 0, w.shape[0])
+        cfg = engine.StepConfig(float(self.s), float(self.m), bool(self.easy_margin), 0, w.shape[0],
+                                engine.precision_code(self.precision))
         return engine.run_step(self, ops, None, x, w, label, cfg, bool(self.validate_labels))
 
     def forward(self, x, label):
         return FusedLogits(self, x, label)
+
+    def _operands(self, x):
+        """(xhat, inv_nx, what, inv_nw) in the head's precision mode: bf16 [., D], or the 3 D wide hi/lo rows."""
+        w = self.weight.detach().contiguous()
+        if engine.precision_code(self.precision):
+            xhat, inv_nx, _ = ops.normalize_cast3(x, 0)
+            what, inv_nw, _ = ops.normalize_cast3(w, 1)
+        else:
+            xhat, inv_nx, _ = ops.normalize_cast(x)
+            what, inv_nw, _ = ops.normalize_cast(w)
+        return xhat, inv_nx, what, inv_nw
 
     @torch.no_grad()
     def logits(self, x, label=None):
@@ -197,8 +214,7 @@ class ArcMarginProduct(nn.Module):
         else:
             x, label = self._prep(x, label)
         w = self.weight.detach().contiguous()
-        xhat, inv_nx, _ = ops.normalize_cast(x)
-        what, inv_nw, _ = ops.normalize_cast(w)
+        xhat, inv_nx, what, inv_nw = self._operands(x)
         if label is None:
             return ops.logits(xhat, what, None, None, float(self.s))
         lm = ops.label_margin(x, w, inv_nx, inv_nw, label, 0, w.shape[0], float(self.s), float(self.m),
@@ -210,8 +226,7 @@ class ArcMarginProduct(nn.Module):
     def forward_test(self, x):
         """arcface.py:65-67: bare cosines [B, C] (no margin, no scale), materialised like the reference."""
         x = x.to(torch.float32).contiguous()
-        xhat, _, _ = ops.normalize_cast(x)
-        what, _, _ = ops.normalize_cast(self.weight.detach().contiguous())
+        xhat, _, what, _ = self._operands(x)
         return ops.logits(xhat, what, None, None, 1.0)
 
     @torch.no_grad()
@@ -219,8 +234,7 @@ class ArcMarginProduct(nn.Module):
         """argmax_c cos[b, c] without materialising the cosines (what the eval loops do with
         forward_test's output, nlp_classifier_train.py:143-156).  Returns (argmax int64 [B], max cosine [B])."""
         x = x.to(torch.float32).contiguous()
-        xhat, _, _ = ops.normalize_cast(x)
-        what, _, _ = ops.normalize_cast(self.weight.detach().contiguous())
+        xhat, _, what, _ = self._operands(x)
         rmax, _, rarg = ops.forward_rows(xhat, what, None, 1.0, 0)
         return rarg, rmax
 
@@ -229,8 +243,7 @@ class ArcMarginProduct(nn.Module):
         """The k best classes per row by cosine, descending, without the B x C matrix: (cosines fp32 [B, k],
         class ids int64 [B, k]).  What top-k over `forward_test(x)` returns (arcface.py:65-67)."""
         x = x.to(torch.float32).contiguous()
-        xhat, _, _ = ops.normalize_cast(x)
-        what, _, _ = ops.normalize_cast(self.weight.detach().contiguous())
+        xhat, _, what, _ = self._operands(x)
         return ops.cosine_topk(xhat, what, k)
 
     def extra_repr(self):

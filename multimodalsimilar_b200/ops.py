@@ -64,6 +64,26 @@ def normalize_cast(src: torch.Tensor, want_transpose: bool = False):
     return dst, inv, dst_t
 
 
+PREC = {"bf16": 0, "bf16x3": 1}   # ARCFACE_B200_PREC_* (include/arcface_b200.h)
+
+
+def normalize_cast3(src: torch.Tensor, order: int, want_transpose: bool = False):
+    """K1 of the bf16x3 mode.  src [R, D] fp32 -> (bf16 [R, 3 D] laid out [hi|hi|lo] (order 0, embeddings) or
+    [hi|lo|hi] (order 1, class weights), inv_norm fp32 [R], optional transposed hi part bf16 [D, ld_t])."""
+    _req(src, torch.float32, "src")
+    R, D = src.shape
+    dst = torch.empty((R, 3 * D), dtype=torch.bfloat16, device=src.device)
+    inv = torch.empty((R,), dtype=torch.float32, device=src.device)
+    dst_t = None
+    ld_t = 0
+    if want_transpose:
+        ld_t = round_up(R, 64)
+        dst_t = torch.empty((D, ld_t), dtype=torch.bfloat16, device=src.device)
+    _lib.call("arcface_b200_normalize_cast3", _ptr(src), R, D, int(order), _ptr(dst), _ptr(inv), _ptr(dst_t), ld_t,
+              _stream())
+    return dst, inv, dst_t
+
+
 @dataclass
 class LabelMargin:
     t_label: torch.Tensor      # fp32 [B] exact label cosine (0 where the label is on another rank)
@@ -273,22 +293,54 @@ def backward_launches(B: int, D: int, c_local: int) -> int:
 
 
 def backward(xhat, xhat_t, what, inv_nw, lse, one_minus_p, dphi, label_local, s: float, grad_scale: float,
-             grad_loss_dev=None, dw_out=None):
-    """K3.  Returns (dxhat fp32 [B, D] partial over this shard's classes, dW fp32 [C_local, D])."""
+             grad_loss_dev=None, dw_out=None, prec: int = 0, dxhat_out=None):
+    """K3.  Returns (dxhat fp32 [B, D] partial over this shard's classes, dW fp32 [C_local, D]).
+    prec = PREC['bf16x3']: xhat / what are the 3 D wide rows of `normalize_cast3`."""
     B, D = xhat.shape
+    if prec:
+        D //= 3
     C = what.shape[0]
     dev = xhat.device
-    dxhat = torch.empty((B, D), dtype=torch.float32, device=dev)
+    dxhat = dxhat_out if dxhat_out is not None else torch.empty((B, D), dtype=torch.float32, device=dev)
+    _req(dxhat, torch.float32, "dxhat")
     dw = dw_out if dw_out is not None else torch.empty((C, D), dtype=torch.float32, device=dev)
     _req(dw, torch.float32, "dw")
     nbytes = backward_workspace_bytes(B, D, C)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     if grad_loss_dev is not None:
         grad_loss_dev = _req(grad_loss_dev.reshape(1), torch.float32, "grad_loss")
-    _lib.call("arcface_b200_backward", _ptr(xhat), _ptr(xhat_t), xhat_t.shape[1], _ptr(what), _ptr(inv_nw), _ptr(lse),
-              _ptr(one_minus_p), _ptr(dphi), _ptr(label_local), B, D, C, s, grad_scale, _ptr(grad_loss_dev), _ptr(dxhat),
-              _ptr(dw), _ptr(ws), nbytes, _stream())
+    _lib.call("arcface_b200_backward_prec", _ptr(xhat), _ptr(xhat_t), xhat_t.shape[1], _ptr(what), _ptr(inv_nw),
+              _ptr(lse), _ptr(one_minus_p), _ptr(dphi), _ptr(label_local), B, D, C, s, grad_scale, _ptr(grad_loss_dev),
+              _ptr(dxhat), _ptr(dw), _ptr(ws), nbytes, int(prec), _stream())
     return dxhat, dw
+
+
+def two_stream_concat(a, b):
+    """cat(F.normalize(a), F.normalize(b), dim=1) in one kernel -> (emb fp32 [B, D1 + D2], inv1 [B], inv2 [B])."""
+    _req(a, torch.float32, "a")
+    _req(b, torch.float32, "b")
+    B, D1 = a.shape
+    D2 = b.shape[1]
+    if b.shape[0] != B:
+        raise ValueError("both streams need the same batch size")
+    out = torch.empty((B, D1 + D2), dtype=torch.float32, device=a.device)
+    inv1 = torch.empty(B, dtype=torch.float32, device=a.device)
+    inv2 = torch.empty(B, dtype=torch.float32, device=a.device)
+    _lib.call("arcface_b200_two_stream_concat", _ptr(a), _ptr(b), B, D1, D2, _ptr(out), _ptr(inv1), _ptr(inv2), _stream())
+    return out, inv1, inv2
+
+
+def two_stream_concat_bwd(emb, inv1, inv2, grad, D1: int):
+    """Backward of `two_stream_concat`: (d a [B, D1], d b [B, D2])."""
+    _req(emb, torch.float32, "emb")
+    _req(grad, torch.float32, "grad")
+    B, D = emb.shape
+    D2 = D - D1
+    da = torch.empty((B, D1), dtype=torch.float32, device=emb.device)
+    db = torch.empty((B, D2), dtype=torch.float32, device=emb.device)
+    _lib.call("arcface_b200_two_stream_concat_bwd", _ptr(emb), _ptr(inv1), _ptr(inv2), _ptr(grad), B, D1, D2, _ptr(da),
+              _ptr(db), _stream())
+    return da, db
 
 
 def normalize_bwd_x(x, inv_nx, dxhat) -> torch.Tensor:

@@ -55,7 +55,8 @@ class ShardedArcMarginProduct(nn.Module):
     """
 
     def __init__(self, in_feature=128, out_feature=10575, s=64.0, m=0.40, easy_margin=False, *, in_features=None,
-                 out_features=None, process_group=None, kernels=None, use_cuda_graph=True, use_p2p=True):
+                 out_features=None, process_group=None, kernels=None, use_cuda_graph=True, use_p2p=True,
+                 precision="bf16"):
         super().__init__()
         if in_features is not None:
             in_feature = in_features
@@ -66,6 +67,8 @@ class ShardedArcMarginProduct(nn.Module):
         self.kernels = kernels
         self.use_cuda_graph = use_cuda_graph
         self.use_p2p = use_p2p      # exchanges through peer-mapped memory (p2p.py) instead of NCCL when available
+        engine.precision_code(precision)
+        self.precision = precision  # 'bf16' | 'bf16x3' (see ArcMarginProduct)
         self.process_group = process_group if process_group is not None else dist.group.WORLD
         self.world_size = dist.get_world_size(self.process_group)
         self.rank = dist.get_rank(self.process_group)
@@ -119,7 +122,8 @@ class ShardedArcMarginProduct(nn.Module):
     def loss(self, x, label):
         x = x.to(torch.float32).contiguous()
         label = label.reshape(-1).to(device=x.device, dtype=torch.int64).contiguous()
-        cfg = engine.StepConfig(float(self.s), float(self.m), bool(self.easy_margin), self.class_lo, self.out_feature)
+        cfg = engine.StepConfig(float(self.s), float(self.m), bool(self.easy_margin), self.class_lo, self.out_feature,
+                                engine.precision_code(getattr(self, "precision", "bf16")))
         w = self.weight if self.weight.is_contiguous() else self.weight.contiguous()
         return engine.run_step(self, self.kernels, self.process_group, x, w, label, cfg, False)
 
