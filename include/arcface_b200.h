@@ -243,6 +243,16 @@ int32_t arcface_b200_adamw_normalize(float* w, const float* grad, float* exp_avg
 int32_t arcface_b200_p2p_exchange(const void* src, size_t bytes_per_peer, size_t src_stride, const uint64_t* peer_bufs,
                                   const uint64_t* peer_flags, int32_t rank, int32_t world, size_t slot_stride,
                                   int32_t channel, uint32_t* sync_dev, void* stream);
+
+/* The all-gather form of arcface_b200_p2p_exchange (src_stride = 0) with a split receive layout: the first `split` bytes
+ * of every rank's message land contiguously in rank order at the start of each receive buffer ([world][split]), the
+ * remaining bytes contiguously behind them ([world][bytes_per_peer - split]).  The class-sharded head gathers the
+ * byte-packed (x | labels) of every rank this way and reads one [B][D] matrix and one [B] label vector straight out
+ * of the receive buffer.  split = 0: plain slots, as arcface_b200_p2p_exchange. */
+int32_t arcface_b200_p2p_gather_split(const void* src, size_t bytes_per_peer, size_t src_stride, size_t split,
+                                      const uint64_t* peer_bufs, const uint64_t* peer_flags, int32_t rank,
+                                      int32_t world, size_t slot_stride, int32_t channel, uint32_t* sync_dev,
+                                      void* stream);
 /* normalize_bwd_x over the SUM of n_parts partial dxhat buffers ([n_parts][B][D], part_stride floats apart), summed in
  * index order: the reduce half of the reduce-scatter, fused. */
 int32_t arcface_b200_normalize_bwd_x_sum(const float* x, const float* inv_nx, const float* parts, int32_t n_parts,

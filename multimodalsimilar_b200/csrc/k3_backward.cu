@@ -1267,7 +1267,10 @@ extern "C" int32_t arcface_b200_backward_workspace_bytes(int32_t B, int32_t D, i
     if (int32_t rc = check_arch()) return rc;
     AB_REQUIRE(bytes, ARCFACE_B200_E_ARG, "backward_workspace_bytes: null pointer");
     if (int32_t rc = check_bwd_shape("backward_workspace_bytes", B, D, C_local)) return rc;
-    *bytes = plan_backward(B, D, C_local, sm_count()).total;
+    // enough for either precision mode (the role split, and with it the ring size, depends on the recompute depth)
+    const size_t a = plan_backward(B, D, C_local, sm_count()).total;
+    const size_t b = plan_backward(B, D, C_local, sm_count(), 3 * D).total;
+    *bytes = a > b ? a : b;
     return ARCFACE_B200_OK;
 }
 

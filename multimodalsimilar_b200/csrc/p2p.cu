@@ -31,6 +31,10 @@ struct P2PParams {
     unsigned long long bytes_per_peer;   // multiple of 16
     unsigned long long src_stride;       // 0: the same bytes go to every peer (all-gather); else peer r gets src + r * stride
     unsigned long long slot_stride;
+    unsigned long long split;            // all-gather only, 0 = off: the first `split` bytes of every rank's message land
+                                         // contiguously in rank order ([world][split]), the remaining bytes likewise
+                                         // behind them -- the gathered (x | labels) arrive as one x matrix and one
+                                         // label vector, no unpacking copies
     int rank, world, channel;
     unsigned* sync;                      // this channel's [call number, arrival counter]
 };
@@ -56,7 +60,13 @@ __global__ void __launch_bounds__(256) p2p_exchange_kernel(const P2PParams p) {
         const int peer = static_cast<int>(i / chunks);
         const unsigned long long c = i - static_cast<unsigned long long>(peer) * chunks;
         const uint4 v = *reinterpret_cast<const uint4*>(p.src + static_cast<unsigned long long>(peer) * p.src_stride + (c << 4));
-        *reinterpret_cast<uint4*>(p.bufs[peer] + static_cast<unsigned long long>(p.rank) * p.slot_stride + (c << 4)) = v;
+        const unsigned long long o = c << 4;
+        unsigned long long dst = static_cast<unsigned long long>(p.rank) * p.slot_stride + o;
+        if (p.split != 0ull)
+            dst = o < p.split ? static_cast<unsigned long long>(p.rank) * p.split + o
+                              : static_cast<unsigned long long>(p.world) * p.split +
+                                    static_cast<unsigned long long>(p.rank) * (p.bytes_per_peer - p.split) + (o - p.split);
+        *reinterpret_cast<uint4*>(p.bufs[peer] + dst) = v;
     }
     __threadfence_system();  // this thread's peer stores are performed before anything it does next
     __syncthreads();
@@ -129,7 +139,17 @@ extern "C" int32_t arcface_b200_p2p_exchange(const void* src, size_t bytes_per_p
                                              const uint64_t* peer_bufs, const uint64_t* peer_flags, int32_t rank,
                                              int32_t world, size_t slot_stride, int32_t channel, uint32_t* sync_dev,
                                              void* stream) {
+    return arcface_b200_p2p_gather_split(src, bytes_per_peer, src_stride, 0, peer_bufs, peer_flags, rank, world,
+                                         slot_stride, channel, sync_dev, stream);
+}
+
+extern "C" int32_t arcface_b200_p2p_gather_split(const void* src, size_t bytes_per_peer, size_t src_stride, size_t split,
+                                                 const uint64_t* peer_bufs, const uint64_t* peer_flags, int32_t rank,
+                                                 int32_t world, size_t slot_stride, int32_t channel, uint32_t* sync_dev,
+                                                 void* stream) {
     if (int32_t rc = check_arch()) return rc;
+    AB_REQUIRE(split % 16 == 0 && split <= bytes_per_peer && (split == 0 || src_stride == 0), ARCFACE_B200_E_LAYOUT,
+               "p2p_gather_split: split must be a multiple of 16 bytes inside an all-gather message");
     AB_REQUIRE(src && peer_bufs && peer_flags && sync_dev, ARCFACE_B200_E_ARG, "p2p_exchange: null pointer");
     AB_REQUIRE(world >= 1 && world <= P2P_MAX_RANKS && rank >= 0 && rank < world && channel >= 0 && channel < 8,
                ARCFACE_B200_E_ARG, "p2p_exchange: bad rank / world / channel");
@@ -147,6 +167,7 @@ extern "C" int32_t arcface_b200_p2p_exchange(const void* src, size_t bytes_per_p
     p.bytes_per_peer = bytes_per_peer;
     p.src_stride = src_stride;
     p.slot_stride = slot_stride;
+    p.split = split;
     p.rank = rank; p.world = world; p.channel = channel;
     p.sync = sync_dev + 2 * channel;
     const unsigned long long total16 = (bytes_per_peer >> 4) * static_cast<unsigned long long>(world);

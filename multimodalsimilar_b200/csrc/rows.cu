@@ -243,7 +243,9 @@ label_margin_kernel(const float* __restrict__ x, const float* __restrict__ w, co
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (b >= B) return;
     const int64_t y = label[b];
-    if ((y < 0 || y >= C_total) && lane == 0 && bad_flag != nullptr) atomicExch(bad_flag, 1);
+    // plain store (every writer stores the same value): `bad_flag` may be mapped pinned HOST memory, so that the
+    // flag reaches the host without a copy node in the step (engine.LabelGuard)
+    if ((y < 0 || y >= C_total) && lane == 0 && bad_flag != nullptr) *reinterpret_cast<volatile int*>(bad_flag) = 1;
     const int64_t loc = y - class_offset;
     if (loc < 0 || loc >= C_local) {
         if (lane == 0) {

@@ -69,18 +69,15 @@ class LabelGuard:
 
     The reference raises from `one_hot.scatter_` (arcface.py:59) when a label is outside [0, C).  Here
     `label_margin` raises a device flag instead; reading it synchronously would stall every step (and is impossible
-    inside a replayed CUDA graph), so the flag is copied to pinned host memory as part of the step and examined at
-    the START of the next call of the same head: a bad label raises IndexError one step late instead of training on
-    silently.  `validate_labels=True` keeps the synchronous check (eager launches, one sync per step)."""
+    inside a replayed CUDA graph), so the label kernel raises the flag directly in pinned host memory (device-visible
+    under unified addressing: no copy node, no fill) and the host examines it at the START of the next call of the
+    same head: a bad label raises IndexError one step late instead of training on silently.
+    `validate_labels=True` keeps the synchronous check (eager launches, a device flag, one sync per step)."""
 
     def __init__(self):
         self.host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.event = torch.cuda.Event()
         self.armed = False
-
-    def post(self, bad_flag: torch.Tensor) -> None:
-        """Queue (or, under stream capture, record into the graph) the flag's copy to the host."""
-        self.host.copy_(bad_flag, non_blocking=True)
 
     def mark(self) -> None:
         self.event.record()
@@ -121,10 +118,13 @@ def gather_batch(x_local: torch.Tensor, y_local: torch.Tensor, group, packed=Non
     xb = b * D * 4
     if packed is None:
         packed = torch.cat([x_local.reshape(-1).view(torch.uint8), y_local.view(torch.uint8)])
-    if peer is not None and packed.numel() % 16 == 0:
-        allp = peer.all_gather_bytes(0, packed)     # stores over NVLink + flags (csrc/p2p.cu)
-    else:
-        allp = _all_gather_bytes(packed, group)
+    if peer is not None and packed.numel() % 16 == 0 and xb % 16 == 0:
+        # stores over NVLink + flags (csrc/p2p.cu); x rows and labels land as two contiguous rank-ordered regions
+        xa, ya = peer.all_gather_split(0, packed, xb)
+        # x is consumed (K1, label margin) before this rank raises its flag of the NEXT exchange, so no peer can be
+        # overwriting it (csrc/p2p.cu); the labels are read again after that exchange (finalize), hence their copy
+        return xa.view(torch.float32).view(R * b, D), ya.view(torch.int64).clone()
+    allp = _all_gather_bytes(packed, group)
     x_all = allp[:, :xb].contiguous().view(torch.float32).reshape(R * b, D)
     y_all = allp[:, xb:].contiguous().view(torch.int64).reshape(R * b)
     return x_all, y_all
@@ -173,13 +173,15 @@ def _rows(K, xhat, w, label_local, cfg, w_cache, out=None):
     return K.forward_rows_fused(xhat, w, label_local, cfg.s, cfg.class_lo, **kw)
 
 
-def forward_eager(K, group, x_local, w, y_local, cfg: StepConfig, packed_xy=None, w_cache=None, peer=None) -> FwdState:
+def forward_eager(K, group, x_local, w, y_local, cfg: StepConfig, packed_xy=None, w_cache=None, peer=None,
+                  guard=None) -> FwdState:
     """K1 (x) -> label margin -> K1 (w) + K2 -> combine -> [exchange] -> finalize.  arcface.py:45-63 + the mean
     CrossEntropyLoss + argmax of the call sites, for the global batch against the local class rows."""
     R, rank = _world(group), _rank(group)
     b_loc = x_local.shape[0]
     x_all, y_all = gather_batch(x_local, y_local, group, packed_xy, peer)
     B = x_all.shape[0]
+    gk = {"bad_flag_out": guard.host} if guard is not None else {}   # the label kernel raises the guard's host flag
     if cfg.prec:
         xhat, inv_nx, xhat_t = K.normalize_cast3(x_all, 0, want_transpose=True)
     else:
@@ -188,7 +190,7 @@ def forward_eager(K, group, x_local, w, y_local, cfg: StepConfig, packed_xy=None
         # the kernels fill one packed buffer, the exchange is one all-gather, the merge reads it in place
         buf, v_max, v_sum, v_z, v_arg = K.packed_stats(B, x_all.device)
         lm = K.label_margin(x_all, w, inv_nx, None, y_all, cfg.class_lo, cfg.c_total, cfg.s, cfg.m, cfg.easy_margin,
-                            z_out=v_z)
+                            z_out=v_z, **gk)
         what, inv_nw, _, _, _ = _rows(K, xhat, w, lm.label_local, cfg, w_cache, out=(v_max, v_sum, v_arg))
         if peer is not None and buf.numel() % 16 == 0:
             allp = peer.all_gather_bytes(1, buf)
@@ -196,7 +198,7 @@ def forward_eager(K, group, x_local, w, y_local, cfg: StepConfig, packed_xy=None
             allp = _all_gather_bytes(buf, group)
         lse, argmax, _z, omp, loss = K.finalize_rows_packed(allp, y_all)
     else:
-        lm = K.label_margin(x_all, w, inv_nx, None, y_all, cfg.class_lo, cfg.c_total, cfg.s, cfg.m, cfg.easy_margin)
+        lm = K.label_margin(x_all, w, inv_nx, None, y_all, cfg.class_lo, cfg.c_total, cfg.s, cfg.m, cfg.easy_margin, **gk)
         what, inv_nw, rmax, rsum, rarg = _rows(K, xhat, w, lm.label_local, cfg, w_cache)
         rows_max, rows_sum, rows_z, rows_arg = exchange_rows(rmax, rsum, lm.z_label, rarg, group)
         lse, argmax, _z, omp, loss = K.finalize_rows(rows_max, rows_sum, rows_arg, rows_z, y_all)
@@ -256,7 +258,7 @@ class GraphedStep:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(self.WARMUP):  # lazy initialisation (NCCL communicators, kernel attributes) outside capture
-                st = forward_eager(K, group, self.x, w, self.y, cfg, self.xy, w_cache, peer)
+                st = forward_eager(K, group, self.x, w, self.y, cfg, self.xy, w_cache, peer, guard)
                 if with_backward:
                     backward_eager(K, group, self.x, st, self.one, cfg, True, peer)
             del st
@@ -265,9 +267,7 @@ class GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         self.dx = self.dw = None
         with torch.cuda.graph(self.graph):
-            self.st = forward_eager(K, group, self.x, w, self.y, cfg, self.xy, w_cache, peer)
-            if guard is not None:
-                guard.post(self.st.bad_flag)   # a memcpy node of the graph: the flag reaches the host with every replay
+            self.st = forward_eager(K, group, self.x, w, self.y, cfg, self.xy, w_cache, peer, guard)
             if with_backward:
                 self.dx, self.dw = backward_eager(K, group, self.x, self.st, self.one, cfg, True, peer)
 
@@ -326,12 +326,11 @@ class ArcFaceCEFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, label, K, group, cfg, validate_labels, w_cache=None, peer=None, guard=None):
-        st = forward_eager(K, group, x, w, label, cfg, None, w_cache, peer)
+        st = forward_eager(K, group, x, w, label, cfg, None, w_cache, peer, None if validate_labels else guard)
         if validate_labels:
             if int(st.bad_flag.item()) != 0:
                 raise IndexError("ArcMarginProduct: a label is outside [0, %d)" % cfg.c_total)
         elif guard is not None:
-            guard.post(st.bad_flag)
             guard.mark()
         ctx.save_for_backward(x, st.inv_nx, st.xhat, st.xhat_t, st.what, st.inv_nw, st.lse, st.omp, st.dphi,
                               st.label_local)

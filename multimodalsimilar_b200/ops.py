@@ -93,7 +93,10 @@ class LabelMargin:
     bad_flag: torch.Tensor     # int32 [1] set when a label is outside [0, C_total)
 
 
-def label_margin(x, w, inv_nx, inv_nw, label, class_offset, c_total, s, m, easy_margin, z_out=None) -> LabelMargin:
+def label_margin(x, w, inv_nx, inv_nw, label, class_offset, c_total, s, m, easy_margin, z_out=None,
+                 bad_flag_out=None) -> LabelMargin:
+    """bad_flag_out: optional int32 [1] tensor the kernel raises on an out-of-range label instead of a fresh device
+    flag -- may be PINNED HOST memory (device-visible under unified addressing): nothing resets it but its owner."""
     _req(x, torch.float32, "x")
     _req(w, torch.float32, "weight")
     _req(label, torch.int64, "label")
@@ -104,7 +107,7 @@ def label_margin(x, w, inv_nx, inv_nw, label, class_offset, c_total, s, m, easy_
         z_out if z_out is not None else torch.empty(B, dtype=torch.float32, device=dev),
         torch.empty(B, dtype=torch.float32, device=dev),
         torch.empty(B, dtype=torch.int32, device=dev),
-        torch.zeros(1, dtype=torch.int32, device=dev),
+        bad_flag_out if bad_flag_out is not None else torch.zeros(1, dtype=torch.int32, device=dev),
     )
     cos_m, sin_m, th, mm = margin_constants(m)
     _lib.call("arcface_b200_label_margin", _ptr(x), _ptr(w), _ptr(inv_nx), _ptr(inv_nw), _ptr(label), B, D,

@@ -67,6 +67,20 @@ class PeerExchange:
         lo = self.off[channel]
         return self.buf[lo: lo + self.slot[channel] * self.world].view(self.world, self.slot[channel])
 
+    def all_gather_split(self, channel: int, packed: torch.Tensor, split: int):
+        """All-gather of `packed` uint8 [n] whose first `split` bytes and last n - split bytes arrive as two contiguous
+        rank-ordered regions: returns (uint8 [R * split], uint8 [R * (n - split)]) views of the receive buffer."""
+        n = packed.numel()
+        if n % 16 != 0 or split % 16 != 0 or not (0 < split < n) or n > self.slot[channel]:
+            raise ValueError("message of %d bytes (split at %d) does not fit channel %d" % (n, split, channel))
+        _lib.call("arcface_b200_p2p_gather_split", ctypes.c_void_p(packed.data_ptr()), n, 0, split, self._bufs[channel],
+                  self._flags, self.rank, self.world, self.slot[channel], channel, ctypes.c_void_p(self.sync.data_ptr()),
+                  torch.cuda.current_stream().cuda_stream)
+        self.last_channel = channel
+        lo = self.off[channel]
+        R = self.world
+        return self.buf[lo: lo + R * split], self.buf[lo + R * split: lo + R * n]
+
     def all_gather_bytes(self, channel: int, packed: torch.Tensor) -> torch.Tensor:
         """packed uint8 [n] (n a multiple of 16, <= the channel's slot) -> uint8 [R, n] view of the receive buffer."""
         n = packed.numel()

@@ -205,7 +205,8 @@ def test_fused_statistics_match_materialised_logits(B, D, C, s):
 # ----------------------------------------------------------------------------- K1(w) fused into K2
 @pytest.mark.parametrize("B,D,C,s", [(64, 512, 1000, 30.0), (512, 512, 40000, 64.0), (200, 64, 30000, 64.0),
                                      (300, 256, 70001, 64.0), (512, 128, 129, 64.0), (3, 8, 2, 10.0),
-                                     (256, 1792, 3000, 64.0)])
+                                     (256, 1792, 3000, 64.0), (130, 1024, 2000, 64.0), (64, 2816, 700, 64.0),
+                                     (96, 3072, 500, 30.0), (64, 3328, 300, 64.0), (512, 776, 5000, 64.0)])
 def test_fused_forward_equals_split_forward(B, D, C, s):
     """arcface_b200_forward_stats_fused (weight normalise + cast inside the GEMM kernel, rows handed to the TMA
     producer through per-block counters) must produce bit-identical what / inv_nw / statistics to the two
@@ -565,5 +566,6 @@ def test_bf16x3_full_size(B, D, C, trained):
     sep = r["top2_gap"] > X3_ARGMAX_GAP
     assert torch.equal(pred[sep], r["argmax"][sep])
     for got, ref in ((xt.grad, r["dx"]), (head.weight.grad, r["dw"])):
-        assert float((got - ref).norm() / ref.norm()) <= 4e-3
-        assert float((got - ref).abs().max()) <= 1e-2 * float(ref.abs().max())
+        # (trained-like inputs drive every p_label to 1: the gradients themselves are ~1e-12 there, hence the floors)
+        assert float((got - ref).norm()) <= 4e-3 * float(ref.norm()) + 1e-9
+        assert float((got - ref).abs().max()) <= 1e-2 * float(ref.abs().max()) + 1e-9
