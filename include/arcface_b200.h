@@ -223,6 +223,16 @@ int32_t arcface_b200_normalize_bwd_x(const float* x, const float* inv_nx, const 
  * apply it.  When *scale_dev == 1.0f -- loss.backward() on the head's own loss -- the kernel returns immediately. */
 int32_t arcface_b200_scale_grads(float* a, int64_t na, float* b, int64_t nb, const float* scale_dev, void* stream);
 
+/* dst[0..n) = src[0..n) * *scale_dev (always written), b[0..nb) *= *scale_dev unless the factor is exactly 1
+ * (n, nb multiples of 4).  The graph-replay path hands `dst` (a fresh dX) to autograd and keeps `src` as its static
+ * buffer: one launch instead of arcface_b200_scale_grads + a device copy. */
+int32_t arcface_b200_scale_copy(const float* src, float* dst, int64_t n, float* b, int64_t nb, const float* scale_dev,
+                                void* stream);
+
+/* dst = [x (b x D fp32) | y (b int64)]: the step's inputs into the packed static buffer of a captured graph (the
+ * layout the class-sharded head's gather sends as is) in one launch. */
+int32_t arcface_b200_pack_xy(const float* x, const int64_t* y, int32_t b, int32_t D, void* dst, void* stream);
+
 /* Fused head optimiser: one torch.optim.AdamW step (decoupled weight decay, bias correction for step number `step`
  * >= 1) on the fp32 class-weight rows, in place on w / exp_avg / exp_avg_sq, and -- when what / inv_nw are given --
  * the NEXT forward's K1 in the same pass: what = bf16(w_new / max(||w_new||, 1e-12)), inv_nw = 1 / max(||w_new||, 1e-12).

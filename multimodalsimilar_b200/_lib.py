@@ -80,6 +80,8 @@ SIGNATURES = {
         c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "arcface_b200_normalize_bwd_x": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "arcface_b200_scale_grads": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "arcface_b200_scale_copy": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "arcface_b200_pack_xy": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "arcface_b200_adamw_normalize": (
         c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_double, c_double, c_double, c_double,
                   c_double, c_int64, c_void_p, c_void_p, c_void_p]),

@@ -300,87 +300,8 @@ struct FwdStatsPairT : pr::PairDefaults {
     // update that ends every run, not by the loads in flight.)
     static constexpr int PPR = RUN / 2;  // pairs per run
 
-    // Rows wider than 512 floats (D = 768 ... 3072: the RoBERTa, EfficientNet-B4 and two-stream heads) do not fit a
-    // register row pair: one row at a time, two passes.  Pass 1 streams the row from HBM and sums the squares, four
-    // 8-float chunks per lane in flight; pass 2 re-reads it (an L2 hit: the line was fetched a microsecond ago),
-    // scales, packs and stores.  The summation order is normalize_cast_kernel's (chunks lane, lane + 32, ... in
-    // order, then the xor butterfly), so what / inv_nw stay bit-identical to the stand-alone K1.
-    __device__ static void aux_wide(const Params& p, int u, int nu, int lane) {
-        const int64_t n_runs = (static_cast<int64_t>(p.C) + RUN - 1) / RUN;
-        for (int64_t run = u; run < n_runs; run += nu) {
-            const int64_t r0 = run * RUN;
-            int rows = 0;
-#pragma unroll 1
-            for (int k = 0; k < RUN; ++k) {
-                const int64_t row = r0 + k;
-                if (row >= p.C) break;
-                ++rows;
-                const float* src = p.w + row * p.D;
-                float ss = 0.f;
-#pragma unroll 1
-                for (int d0 = 0; d0 < p.D; d0 += 1024) {
-                    float4 v[4][2];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int d = d0 + (lane + 32 * c) * 8;
-                        if (d < p.D) {
-                            v[c][0] = ldg_stream4(src + d);
-                            v[c][1] = ldg_stream4(src + d + 4);
-                        }
-                    }
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int d = d0 + (lane + 32 * c) * 8;
-                        if (d < p.D) {
-                            const float4 x = v[c][0], y = v[c][1];
-                            ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
-                            ss += y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-                const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
-                if (lane == 0) p.inv_nw[row] = inv;
-                __nv_bfloat16* dst = p.what + row * p.D;
-#pragma unroll 1
-                for (int d0 = 0; d0 < p.D; d0 += 512) {
-                    float4 v[2][2];
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const int d = d0 + (lane + 32 * c) * 8;
-                        if (d < p.D) {
-                            v[c][0] = *reinterpret_cast<const float4*>(src + d);
-                            v[c][1] = *reinterpret_cast<const float4*>(src + d + 4);
-                        }
-                    }
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const int d = d0 + (lane + 32 * c) * 8;
-                        if (d < p.D) {
-                            const float4 x = v[c][0], y = v[c][1];
-                            uint4 o;
-                            o.x = pack_bf16x2(x.x * inv, x.y * inv);
-                            o.y = pack_bf16x2(x.z * inv, x.w * inv);
-                            o.z = pack_bf16x2(y.x * inv, y.y * inv);
-                            o.w = pack_bf16x2(y.z * inv, y.w * inv);
-                            *reinterpret_cast<uint4*>(dst + d) = o;
-                        }
-                    }
-                }
-            }
-            __threadfence();
-            __syncwarp();
-            if (lane == 0 && rows > 0) red_relaxed_gpu_add(p.ready + (r0 / pr::ROWS), rows);
-        }
-    }
-
     __device__ static void aux(const Params& p, int u, int nu, int lane) {
         if constexpr (NORM) {
-            if (p.D > 512) {
-                aux_wide(p, u, nu, lane);
-                return;
-            }
             const int64_t n_runs = (static_cast<int64_t>(p.C) + RUN - 1) / RUN;
             if (u >= n_runs) return;
             const int64_t n_pairs = ((n_runs - u + nu - 1) / nu) * PPR;  // of this warp (even)
@@ -617,9 +538,11 @@ static bool fwd_use_pairs(int D, int nsm) {
     (void)D;
     return nsm >= 2;
 }
-// the in-kernel weight normaliser: a register row pair up to 512 floats, one row in two passes up to 3072 (beyond
-// that the stand-alone K1 switches to a different summation order and the two would no longer be bit-identical)
-static bool fwd_norm_in_kernel(int D) { return D <= 3072; }
+// The in-kernel weight normaliser holds a row pair in registers: rows of up to 512 floats.  Wider rows run K1 as its
+// own launch: a one-row-at-a-time, two-pass helper (second pass from L2) was measured at 0.52 / 0.35 / 0.80 ms for
+// the forward of BASELINE configs 2 / 3-shard / 4 against 0.27 / 0.22 / 0.52 ms for K1 + K2 as two launches -- sixteen
+// helper warps with one row in flight each do not keep enough bytes in flight.
+static bool fwd_norm_in_kernel(int D) { return (D + pr::BK - 1) / pr::BK <= pr::MAX_KBLOCKS; }
 static void fwd_pair_partition(int B, int64_t C, int nsm, int* n_res, int* groups, int* s_blocks) {
     *n_res = (B + FwdStatsP::NROW - 1) / FwdStatsP::NROW;
     *s_blocks = static_cast<int>((C + FwdStatsP::NROW - 1) / FwdStatsP::NROW);

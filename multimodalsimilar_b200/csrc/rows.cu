@@ -428,6 +428,38 @@ scale_grads_kernel(float* __restrict__ a, int64_t na4, float* __restrict__ b, in
     }
 }
 
+// dst = src * (*g) (always written: the caller hands `dst` to autograd and keeps `src` as a static buffer), and
+// b *= (*g) in place unless the factor is exactly 1.  One launch for what used to be scale_grads + a device copy.
+__global__ void __launch_bounds__(256)
+scale_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n4, float* __restrict__ b, int64_t nb4,
+                  const float* __restrict__ g) {
+    const float f = *g;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    const int64_t total = f == 1.0f ? n4 : n4 + nb4;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+        if (i < n4) {
+            float4 v = reinterpret_cast<const float4*>(src)[i];
+            v.x *= f; v.y *= f; v.z *= f; v.w *= f;
+            reinterpret_cast<float4*>(dst)[i] = v;
+        } else {
+            float4* p = reinterpret_cast<float4*>(b) + (i - n4);
+            float4 v = *p;
+            v.x *= f; v.y *= f; v.z *= f; v.w *= f;
+            *p = v;
+        }
+    }
+}
+
+// The step's inputs into the packed static buffer of a captured graph: dst = [x (b x D fp32) | labels (b int64)].
+__global__ void __launch_bounds__(256)
+pack_xy_kernel(const float* __restrict__ x, const int64_t* __restrict__ y, int64_t nx4, int64_t ny, unsigned char* __restrict__ dst) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nx4 + ny; i += stride) {
+        if (i < nx4) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(x)[i];
+        else reinterpret_cast<int64_t*>(dst + nx4 * 16)[i - nx4] = y[i - nx4];
+    }
+}
+
 // Fused head optimiser: one AdamW step on the class-weight rows AND the next step's K1
 // in the same pass.  Reference: `AdamW(model.classifier.parameters(), lr=1e-2)` + optimizer.step()
 // (nlp_classifier_train.py:94-97, 131-133) followed, one forward later, by F.normalize(self.weight) (arcface.py:47).
@@ -532,6 +564,38 @@ extern "C" int32_t arcface_b200_scale_grads(float* a, int64_t na, float* b, int6
     const int64_t want = (n4 + 255) / 256;
     const int grid = static_cast<int>(want < 8 * 148 ? want : 8 * 148);
     scale_grads_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, na / 4, b, nb / 4, scale_dev);
+    AB_CHECK_CUDA(cudaGetLastError());
+    return ARCFACE_B200_OK;
+}
+
+extern "C" int32_t arcface_b200_scale_copy(const float* src, float* dst, int64_t n, float* b, int64_t nb,
+                                           const float* scale_dev, void* stream) {
+    if (int32_t rc = check_arch()) return rc;
+    AB_REQUIRE(scale_dev && (n == 0 || (src && dst)) && (b || nb == 0), ARCFACE_B200_E_ARG, "scale_copy: null pointer");
+    AB_REQUIRE(n >= 0 && nb >= 0 && n % 4 == 0 && nb % 4 == 0, ARCFACE_B200_E_SHAPE,
+               "scale_copy: element counts must be non-negative multiples of 4");
+    AB_REQUIRE(aligned16(src) && aligned16(dst) && aligned16(b), ARCFACE_B200_E_LAYOUT,
+               "scale_copy: pointers must be 16-byte aligned");
+    if (n + nb == 0) return ARCFACE_B200_OK;
+    const int64_t n4 = (n + nb) / 4;
+    const int64_t want = (n4 + 255) / 256;
+    const int grid = static_cast<int>(want < 8 * 148 ? want : 8 * 148);
+    scale_copy_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, n / 4, b, nb / 4, scale_dev);
+    AB_CHECK_CUDA(cudaGetLastError());
+    return ARCFACE_B200_OK;
+}
+
+extern "C" int32_t arcface_b200_pack_xy(const float* x, const int64_t* y, int32_t b, int32_t D, void* dst, void* stream) {
+    if (int32_t rc = check_arch()) return rc;
+    AB_REQUIRE(x && y && dst, ARCFACE_B200_E_ARG, "pack_xy: null pointer");
+    AB_REQUIRE(b >= 0 && D >= 4 && D % 4 == 0, ARCFACE_B200_E_SHAPE, "pack_xy: bad shape");
+    AB_REQUIRE(aligned16(x) && aligned16(dst) && (reinterpret_cast<uintptr_t>(y) & 7u) == 0, ARCFACE_B200_E_LAYOUT,
+               "pack_xy: x / dst must be 16-byte aligned, y 8-byte aligned");
+    if (b == 0) return ARCFACE_B200_OK;
+    const int64_t nx4 = static_cast<int64_t>(b) * D / 4;
+    const int64_t want = (nx4 + b + 255) / 256;
+    const int grid = static_cast<int>(want < 2 * 148 ? want : 2 * 148);
+    pack_xy_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, nx4, b, static_cast<unsigned char*>(dst));
     AB_CHECK_CUDA(cudaGetLastError());
     return ARCFACE_B200_OK;
 }

@@ -62,6 +62,7 @@ class FwdState:
     omp: torch.Tensor
     dphi: torch.Tensor
     label_local: torch.Tensor
+    argmax_all: Any = None   # argmax of every row of the global batch (argmax_local is a view of it)
 
 
 class LabelGuard:
@@ -202,9 +203,11 @@ def forward_eager(K, group, x_local, w, y_local, cfg: StepConfig, packed_xy=None
         what, inv_nw, rmax, rsum, rarg = _rows(K, xhat, w, lm.label_local, cfg, w_cache)
         rows_max, rows_sum, rows_z, rows_arg = exchange_rows(rmax, rsum, lm.z_label, rarg, group)
         lse, argmax, _z, omp, loss = K.finalize_rows(rows_max, rows_sum, rows_arg, rows_z, y_all)
-    argmax_local = argmax if R == 1 else argmax[rank * b_loc:(rank + 1) * b_loc].contiguous()
-    return FwdState(loss, argmax_local, lm.bad_flag, B, inv_nx, xhat, xhat_t, what, inv_nw, lse, omp, lm.dphi,
-                    lm.label_local)
+    argmax_local = argmax if R == 1 else argmax[rank * b_loc:(rank + 1) * b_loc]
+    st = FwdState(loss, argmax_local, lm.bad_flag, B, inv_nx, xhat, xhat_t, what, inv_nw, lse, omp, lm.dphi,
+                  lm.label_local)
+    st.argmax_all = argmax   # (with `loss`: one packed buffer, ops.packed_outputs)
+    return st
 
 
 def backward_eager(K, group, x_local, st: FwdState, grad_loss, cfg: StepConfig, need_dx: bool = True, peer=None):
@@ -271,13 +274,29 @@ class GraphedStep:
             if with_backward:
                 self.dx, self.dw = backward_eager(K, group, self.x, self.st, self.one, cfg, True, peer)
 
+    def outputs(self):
+        """(loss, argmax of the local rows) copied out of the graph's static storage: one device copy."""
+        st = self.st
+        full = st.argmax_all if st.argmax_all is not None else st.argmax_local
+        if hasattr(self.K, "clone_outputs"):
+            arg, loss = self.K.clone_outputs(full, st.loss)
+        else:
+            arg, loss = full.clone(), st.loss.clone()
+        if arg.numel() != st.argmax_local.numel():
+            lo = st.argmax_local.storage_offset() - full.storage_offset()
+            arg = arg[lo: lo + st.argmax_local.numel()]
+        return loss, arg
+
     def run(self, x_local, y_local, param=None):
         if self.with_backward and param is not None and param.grad is not None and \
                 param.grad.untyped_storage().data_ptr() == self.dw.untyped_storage().data_ptr():
             # the caller accumulates gradients and .grad still aliases the buffer this replay overwrites
             param.grad = param.grad.clone()
-        self.x.copy_(x_local)
-        self.y.copy_(y_local)
+        if hasattr(self.K, "pack_xy") and x_local.is_contiguous() and y_local.is_contiguous():
+            self.K.pack_xy(x_local, y_local, self.xy)   # both inputs into the static buffer: one launch
+        else:
+            self.x.copy_(x_local)
+            self.y.copy_(y_local)
         self.graph.replay()
         if self.guard is not None:
             self.guard.mark()
@@ -292,8 +311,7 @@ class _GraphedCE(torch.autograd.Function):
     def forward(ctx, x, w, label, plan: GraphedStep, param_ref):
         ctx.version = plan.run(x, label, param_ref() if param_ref is not None else None)
         ctx.plan = plan
-        loss = plan.st.loss.clone()
-        argmax = plan.st.argmax_local.clone()
+        loss, argmax = plan.outputs()
         ctx.mark_non_differentiable(argmax)
         return loss, argmax
 
@@ -306,8 +324,12 @@ class _GraphedCE(torch.autograd.Function):
                                "forwards in flight")
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         g = grad_loss.to(torch.float32).reshape(1).contiguous()
-        plan.K.scale_grads(plan.dx if need_dx else None, plan.dw if need_dw else None, g)
-        dx = plan.dx.clone() if need_dx else None
+        if need_dx and hasattr(plan.K, "scale_copy"):
+            # dx leaves the static buffer scaled, dW is scaled in place (no-op for a factor of 1): one launch
+            dx = plan.K.scale_copy(plan.dx, plan.dw if need_dw else None, g)
+        else:
+            plan.K.scale_grads(plan.dx if need_dx else None, plan.dw if need_dw else None, g)
+            dx = plan.dx.clone() if need_dx else None
         dw = plan.dw.detach() if need_dw else None  # alias: autograd adopts it without a copy
         ctx.version = -1  # the factor has been applied in place: a second backward would apply it twice
         return dx, dw, None, None, None
@@ -439,7 +461,7 @@ def run_step(head, K, group, x, w, label, cfg: StepConfig, validate_labels: bool
     plan: GraphedStep = state["plan"]
     if not with_bwd:
         plan.run(x, label)
-        return plan.st.loss.clone(), plan.st.argmax_local.clone()
+        return plan.outputs()
     param = getattr(head, "weight", None)
     return _GraphedCE.apply(x, w, label, plan, weakref.ref(param) if isinstance(param, torch.nn.Parameter) else None)
 

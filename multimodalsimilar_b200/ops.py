@@ -185,15 +185,33 @@ def finalize_rows(rows_max, rows_sum, rows_arg, rows_z, label):
     R, B = rows_max.shape
     dev = rows_max.device
     lse = torch.empty(B, dtype=torch.float32, device=dev)
-    arg = torch.empty(B, dtype=torch.int64, device=dev)
+    arg, loss = packed_outputs(B, dev)
     z = torch.empty(B, dtype=torch.float32, device=dev)
     omp = torch.empty(B, dtype=torch.float32, device=dev)
-    loss = torch.empty((), dtype=torch.float32, device=dev)
     _lib.call("arcface_b200_finalize_rows", _ptr(_req(rows_max, torch.float32, "rows_max")),
               _ptr(_req(rows_sum, torch.float32, "rows_sum")), _ptr(_req(rows_arg, torch.int64, "rows_arg")),
               _ptr(_req(rows_z, torch.float32, "rows_z")), _ptr(_req(label, torch.int64, "label")), R, B, _ptr(lse),
               _ptr(arg), _ptr(z), _ptr(omp), _ptr(loss), _stream())
     return lse, arg, z, omp, loss
+
+
+def packed_outputs(B: int, device):
+    """(argmax int64 [B], loss fp32 []) as views of ONE buffer, [argmax | loss], so that a caller that must copy the
+    step's results out of static storage (graph replay) needs a single copy: `clone_outputs(argmax, loss)`."""
+    buf = torch.empty(8 * B + 16, dtype=torch.uint8, device=device)
+    arg = buf[: 8 * B].view(torch.int64)
+    arg._pack = buf   # Python-side note for clone_outputs; views made from `arg` do not carry it
+    return arg, buf[8 * B: 8 * B + 4].view(torch.float32).reshape(())
+
+
+def clone_outputs(arg: torch.Tensor, loss: torch.Tensor):
+    """(argmax, loss) copied out of the buffer behind `packed_outputs` with one device copy."""
+    buf = getattr(arg, "_pack", None)
+    if buf is None:
+        return arg.clone(), loss.clone()
+    B = arg.numel()
+    raw = buf.clone()
+    return raw[: 8 * B].view(torch.int64), raw[8 * B: 8 * B + 4].view(torch.float32).reshape(())
 
 
 STATS_BYTES_PER_ROW = 20  # packed per-rank statistics: [arg int64 x B | max fp32 x B | sum fp32 x B | z_label fp32 x B]
@@ -224,10 +242,9 @@ def finalize_rows_packed(allp, label):
     dev = allp.device
     base = allp.data_ptr()
     lse = torch.empty(B, dtype=torch.float32, device=dev)
-    arg = torch.empty(B, dtype=torch.int64, device=dev)
+    arg, loss = packed_outputs(B, dev)
     z = torch.empty(B, dtype=torch.float32, device=dev)
     omp = torch.empty(B, dtype=torch.float32, device=dev)
-    loss = torch.empty((), dtype=torch.float32, device=dev)
     _lib.call("arcface_b200_finalize_rows_strided", ctypes.c_void_p(base + 8 * B), ctypes.c_void_p(base + 12 * B),
               ctypes.c_void_p(base), ctypes.c_void_p(base + 16 * B), _ptr(_req(label, torch.int64, "label")), R, B,
               stride // 4, stride // 8, _ptr(lse), _ptr(arg), _ptr(z), _ptr(omp), _ptr(loss), _stream())
@@ -373,6 +390,25 @@ def scale_grads(a, b, scale_dev) -> None:
     nb = 0 if b is None else _req(b, torch.float32, "b").numel()
     _lib.call("arcface_b200_scale_grads", _ptr(a), na, _ptr(b), nb, _ptr(_req(scale_dev, torch.float32, "scale")),
               _stream())
+
+
+def scale_copy(src, b, scale_dev) -> torch.Tensor:
+    """Returns a fresh tensor src * scale (DEVICE scalar) and scales `b` (fp32 tensor or None) in place unless the
+    factor is exactly 1: one launch."""
+    _req(src, torch.float32, "src")
+    dst = torch.empty_like(src)
+    nb = 0 if b is None else _req(b, torch.float32, "b").numel()
+    _lib.call("arcface_b200_scale_copy", _ptr(src), _ptr(dst), src.numel(), _ptr(b), nb,
+              _ptr(_req(scale_dev, torch.float32, "scale")), _stream())
+    return dst
+
+
+def pack_xy(x, y, dst) -> None:
+    """dst uint8 [b * D * 4 + b * 8] <- (x fp32 [b, D] | y int64 [b]) in one launch."""
+    _req(x, torch.float32, "x")
+    _req(y, torch.int64, "y")
+    b, D = x.shape
+    _lib.call("arcface_b200_pack_xy", _ptr(x), _ptr(y), b, D, _ptr(dst), _stream())
 
 
 def adamw_normalize(w, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, what=None, inv_nw=None):
