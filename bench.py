@@ -124,7 +124,7 @@ class ClockSampler(threading.Thread):
                     self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
                 except Exception:
                     pass
-                time.sleep(0.004)
+                time.sleep(0.001)
         except Exception as e:  # pragma: no cover
             self.error = repr(e)
 
@@ -276,6 +276,12 @@ class Job:
         if sample_clocks:
             sampler = ClockSampler(self.dev.index or 0)
             sampler.start()
+            t_wait = time.perf_counter()   # NVML initialisation takes tens of ms: short timed regions would see no sample
+            while not sampler.sm and sampler.error is None and time.perf_counter() - t_wait < 2.0:
+                time.sleep(0.002)
+            sampler.sm.clear()
+            sampler.power.clear()
+            sampler.mask = 0
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         self.barrier()
         evs[0].record()
@@ -545,10 +551,11 @@ def dominant_kernel_roofline(job, ops, peaks, stages, regime, traffic_ok):
 
 
 def launches_per_step(job, ops):
-    """Our kernels per step (memset / copy / NCCL nodes not counted): K1(x), label, K1(w)+K2, combine, finalize, K3,
-    bwd-x, scale_grads -- replayed from one CUDA graph -- plus the three peer-memory exchange kernels when used."""
+    """Our kernels per step (memset / copy / NCCL nodes not counted): pack_xy, then -- replayed from one CUDA graph --
+    K1(x), label, K1(w)+K2, combine, finalize, K3, bwd-x, then scale_copy; plus the three peer-memory exchange kernels
+    when used."""
     cfg = job.cfg
-    n = 1 + 1 + 1 + 1 + 1 + ops.backward_launches(cfg["B"], cfg["D"], job.c_hi - job.c_lo) + 1 + 1
+    n = 1 + 1 + 1 + 1 + 1 + 1 + ops.backward_launches(cfg["B"], cfg["D"], job.c_hi - job.c_lo) + 1 + 1
     if cfg["D"] > 512:
         n += 1   # K1 of the class weights is its own launch when the in-kernel normaliser does not cover D
     if job.exchange() == "p2p":

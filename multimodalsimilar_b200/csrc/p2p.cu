@@ -189,8 +189,11 @@ extern "C" int32_t arcface_b200_normalize_bwd_x_sum(const float* x, const float*
     AB_REQUIRE(aligned16(x) && aligned16(parts) && aligned16(dx), ARCFACE_B200_E_LAYOUT,
                "normalize_bwd_x_sum: pointers must be 16-byte aligned");
     if (B == 0) return ARCFACE_B200_OK;
-    normalize_bwd_x_sum_kernel<<<(B + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, inv_nx, parts, n_parts,
-                                                                                          part_stride, B, D, dx);
+    // one warp per row; small local batches (64 rows per rank at 8 GPUs) get two-warp CTAs so that the rows spread
+    // over 32 SMs instead of 8
+    const int wpb = B <= 256 ? 2 : 8;
+    normalize_bwd_x_sum_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, inv_nx, parts, n_parts, part_stride, B, D, dx);
     AB_CHECK_CUDA(cudaGetLastError());
     return ARCFACE_B200_OK;
 }

@@ -333,27 +333,46 @@ combine_partials_kernel(const float* __restrict__ pm, const float* __restrict__ 
 // out of the streamed sum makes 1 - p_label = S_rest / (S_rest + e_label) free of cancellation, which
 // matters once the head is trained (p_label -> 1) -- the reference's fp32 softmax - one_hot loses those
 // digits.
-__global__ void __launch_bounds__(256)
+// One CTA (the mean loss is a fixed-order tree sum: deterministic), up to 1024 threads so that a 512- or 1024-row batch
+// is one row per thread; the per-rank values of a row are loaded eight ranks at a time before the merge runs over
+// them (the loads are independent, the merge is not): at 8 ranks this kernel sits on the critical path between the
+// statistics exchange and the backward.
+__global__ void __launch_bounds__(1024)
 finalize_rows_kernel(const float* __restrict__ rm, const float* __restrict__ rs, const int64_t* __restrict__ ra,
                      const float* __restrict__ rz, const int64_t* __restrict__ label, int n_ranks, int B,
                      int64_t fstride, int64_t astride, float* __restrict__ lse, int64_t* __restrict__ argmax, float* __restrict__ z_out,
                      float* __restrict__ one_minus_p, float* __restrict__ loss) {
-    __shared__ float red[256];
+    __shared__ float red[1024];
     float acc = 0.f;
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
         float Mx = -INFINITY, Sx = 0.f, Z = 0.f;
         int64_t Ax = 0;
-        for (int r = 0; r < n_ranks; ++r) {
-            const float m = rm[r * fstride + b];
-            const float s = rs[r * fstride + b];
-            if (m > Mx) {  // strict: the lower rank (lower class range) keeps ties
-                Sx = Sx * expf(Mx - m) + s;
-                Mx = m;
-                Ax = ra[r * astride + b];
-            } else if (m > -INFINITY) {
-                Sx += s * expf(m - Mx);
+        for (int r0 = 0; r0 < n_ranks; r0 += 8) {
+            float mv[8], sv[8], zv[8];
+            int64_t av[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int r = r0 + k;
+                const bool ok = r < n_ranks;
+                mv[k] = ok ? rm[r * fstride + b] : -INFINITY;
+                sv[k] = ok ? rs[r * fstride + b] : 0.f;
+                zv[k] = ok ? rz[r * fstride + b] : 0.f;
+                av[k] = ok ? ra[r * astride + b] : 0;
             }
-            Z += rz[r * fstride + b];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (r0 + k >= n_ranks) break;
+                const float m = mv[k];
+                const float s = sv[k];
+                if (m > Mx) {  // strict: the lower rank (lower class range) keeps ties
+                    Sx = Sx * expf(Mx - m) + s;
+                    Mx = m;
+                    Ax = av[k];
+                } else if (m > -INFINITY) {
+                    Sx += s * expf(m - Mx);
+                }
+                Z += zv[k];
+            }
         }
         const int64_t y = label[b];
         float l, omp, ce;
@@ -377,7 +396,7 @@ finalize_rows_kernel(const float* __restrict__ rm, const float* __restrict__ rs,
     }
     red[threadIdx.x] = acc;
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
+    for (int o = static_cast<int>(blockDim.x) >> 1; o > 0; o >>= 1) {
         if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
         __syncthreads();
     }
@@ -719,7 +738,8 @@ extern "C" int32_t arcface_b200_finalize_rows_strided(const float* rows_max, con
                ARCFACE_B200_E_ARG, "finalize_rows: null pointer");
     AB_REQUIRE(n_ranks >= 1 && B >= 1, ARCFACE_B200_E_SHAPE, "finalize_rows: bad shape");
     AB_REQUIRE(rank_stride_f32 >= B && rank_stride_i64 >= B, ARCFACE_B200_E_LAYOUT, "finalize_rows: rank stride < B");
-    finalize_rows_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(rows_max, rows_sum, rows_arg, rows_z_label,
+    const int threads = B <= 256 ? 256 : (B <= 512 ? 512 : 1024);   // a power of two (tree sum)
+    finalize_rows_kernel<<<1, threads, 0, static_cast<cudaStream_t>(stream)>>>(rows_max, rows_sum, rows_arg, rows_z_label,
                                                                           label, n_ranks, B, rank_stride_f32,
                                                                           rank_stride_i64, lse, argmax, z_label_out,
                                                                           one_minus_p, loss);
