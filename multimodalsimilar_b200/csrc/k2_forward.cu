@@ -300,8 +300,73 @@ struct FwdStatsPairT : pr::PairDefaults {
     // update that ends every run, not by the loads in flight.)
     static constexpr int PPR = RUN / 2;  // pairs per run
 
+    // 512 < D <= 1024 (the RoBERTa-large head): the same 32 registers hold ONE row of up to 1024 floats -- lane l owns
+    // the 8-float chunks l, l + 32, l + 64, l + 96 -- so the bytes a warp keeps in flight (4 KB) and the summation
+    // order (normalize_cast_kernel<4>'s) are those of the row-pair loop below.
+    __device__ static void aux_row1024(const Params& p, int u, int nu, int lane) {
+        const int64_t n_runs = (static_cast<int64_t>(p.C) + RUN - 1) / RUN;
+        for (int64_t run = u; run < n_runs; run += nu) {
+            const int64_t r0 = run * RUN;
+            int rows = 0;
+#pragma unroll 1
+            for (int k = 0; k < RUN; ++k) {
+                const int64_t row = r0 + k;
+                if (row >= p.C) break;
+                ++rows;
+                const float* src = p.w + row * p.D;
+                float4 v[4][2];
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    const int d = (lane + 32 * ch) * 8;
+                    if (d < p.D) {
+                        v[ch][0] = ldg_stream4(src + d);
+                        v[ch][1] = ldg_stream4(src + d + 4);
+                    } else {
+                        v[ch][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[ch][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                float ss = 0.f;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    const int d = (lane + 32 * ch) * 8;
+                    if (d < p.D) {   // same guard as normalize_cast_kernel: bit-identical sums
+                        const float4 x = v[ch][0], y = v[ch][1];
+                        ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+                        ss += y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w;
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+                if (lane == 0) p.inv_nw[row] = inv;
+                __nv_bfloat16* dst = p.what + row * p.D;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    const int d = (lane + 32 * ch) * 8;
+                    if (d < p.D) {
+                        const float4 x = v[ch][0], y = v[ch][1];
+                        uint4 o;
+                        o.x = pack_bf16x2(x.x * inv, x.y * inv);
+                        o.y = pack_bf16x2(x.z * inv, x.w * inv);
+                        o.z = pack_bf16x2(y.x * inv, y.y * inv);
+                        o.w = pack_bf16x2(y.z * inv, y.w * inv);
+                        *reinterpret_cast<uint4*>(dst + d) = o;
+                    }
+                }
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0 && rows > 0) red_relaxed_gpu_add(p.ready + (r0 / pr::ROWS), rows);
+        }
+    }
+
     __device__ static void aux(const Params& p, int u, int nu, int lane) {
         if constexpr (NORM) {
+            if (p.D > 512) {
+                aux_row1024(p, u, nu, lane);
+                return;
+            }
             const int64_t n_runs = (static_cast<int64_t>(p.C) + RUN - 1) / RUN;
             if (u >= n_runs) return;
             const int64_t n_pairs = ((n_runs - u + nu - 1) / nu) * PPR;  // of this warp (even)
@@ -538,11 +603,18 @@ static bool fwd_use_pairs(int D, int nsm) {
     (void)D;
     return nsm >= 2;
 }
-// The in-kernel weight normaliser holds a row pair in registers: rows of up to 512 floats.  Wider rows run K1 as its
-// own launch: a one-row-at-a-time, two-pass helper (second pass from L2) was measured at 0.52 / 0.35 / 0.80 ms for
+// The in-kernel weight normaliser holds a row pair (D <= 512) or one row (D <= 1024) in registers.  Wider rows run K1
+// as its own launch: a one-row-at-a-time, two-pass helper (second pass from L2) was measured at 0.52 / 0.35 / 0.80 ms for
 // the forward of BASELINE configs 2 / 3-shard / 4 against 0.27 / 0.22 / 0.52 ms for K1 + K2 as two launches -- sixteen
 // helper warps with one row in flight each do not keep enough bytes in flight.
-static bool fwd_norm_in_kernel(int D) { return (D + pr::BK - 1) / pr::BK <= pr::MAX_KBLOCKS; }
+static bool fwd_norm_in_kernel(int D) {
+    if (const char* v = diag_env("ARCFACE_B200_FWD_NORM_MAXD")) return D <= atoi(v);
+    // A register row pair covers D <= 512.  The one-register-row variant for D <= 1024 (aux_row1024) is correct and
+    // bit-identical but measured SLOWER than K1 + K2 as two launches (0.237 vs 0.214 ms for one rank's shard of the
+    // RoBERTa-large head, 0.183 vs 0.166 ms at D = 768): with both GEMM operands streaming, the helper warps' loads
+    // and the TMA traffic get in each other's way.  It stays reachable through the diagnostic knob only.
+    return D <= 512;
+}
 static void fwd_pair_partition(int B, int64_t C, int nsm, int* n_res, int* groups, int* s_blocks) {
     *n_res = (B + FwdStatsP::NROW - 1) / FwdStatsP::NROW;
     *s_blocks = static_cast<int>((C + FwdStatsP::NROW - 1) / FwdStatsP::NROW);
