@@ -60,8 +60,8 @@ CONFIGS = {
 EXTRA_CONFIGS = ["c2", "c3", "c4", "c5_100k", "c5_1m", "c5_10m"]
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of the north-star
 # workload on one B200; only meaningful for the single-GPU north-star shape.
-NCU_TRAFFIC = {"fwd": 2.543024e9 + 0.999243e9, "k3": 1.399593e9 + 2.114164e9,
-               "source": "profiles/r1_v9_fwd_bwd_full_raw.csv (ncu --set full, per launch)"}
+NCU_TRAFFIC = {"fwd": 2.300311e9 + 0.995569e9, "k3": 1.401256e9 + 2.114588e9,
+               "source": "profiles/r2_fwd_bwd_full_raw.csv (ncu --set full, per launch)"}
 METRIC = "arcface_head_fwd_bwd_samples_per_sec_1M_classes"
 WEIGHT_SEED = 1234
 WEIGHT_BLOCK = 65536
