@@ -83,6 +83,8 @@ def load_reference_head(head, source, name: Optional[str] = None) -> None:
     else:
         with torch.no_grad():
             head.weight.copy_(weight.to(head.weight.device, head.weight.dtype))
+        if hasattr(head, "invalidate_weight_cache"):
+            head.invalidate_weight_cache()
 
 
 def reference_state_dict(head, prefix: str = "classifier.") -> Dict[str, torch.Tensor]:

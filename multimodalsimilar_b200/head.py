@@ -246,5 +246,12 @@ class ArcMarginProduct(nn.Module):
         xhat, _, what, _ = self._operands(x)
         return ops.cosine_topk(xhat, what, k)
 
+    def invalidate_weight_cache(self) -> None:
+        """Forget everything derived from `weight`: the normalised rows a fused optimiser step left behind and the
+        captured CUDA graph.  Needed only after writes that bypass autograd's version counter (`weight.data.copy_`,
+        raw-pointer writes): ordinary in-place ops, optimiser steps and `load_state_dict` are noticed by themselves."""
+        engine._W_CACHE.pop(self, None)
+        engine.drop_plan(self)
+
     def extra_repr(self):
         return ""

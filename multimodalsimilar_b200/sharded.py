@@ -172,3 +172,9 @@ class ShardedArcMarginProduct(nn.Module):
         if tuple(weight.shape) != (self.out_feature, self.in_feature):
             raise ValueError("expected weight of shape %s" % ((self.out_feature, self.in_feature),))
         self.weight.copy_(weight[self.class_lo:self.class_hi].to(self.weight.device, self.weight.dtype))
+        self.invalidate_weight_cache()
+
+    def invalidate_weight_cache(self) -> None:
+        """See ArcMarginProduct.invalidate_weight_cache."""
+        engine._W_CACHE.pop(self, None)
+        engine.drop_plan(self)

@@ -116,8 +116,30 @@ def test_cosine_index_is_a_flat_ip_index():
     assert float((D_[:, 0] - 1.0).abs().max()) <= 1e-2                        # cos(x, x) = 1 up to bf16 rounding
     rv, ri = onp.cosine_topk(arr[:64], arr, k)
     np.testing.assert_allclose(D_[:64].cpu().numpy(), rv, rtol=0, atol=1e-2)
-    with pytest.raises(ValueError):
-        index.search(arr[:4], 200)
+    # k beyond the fused kernel's lists (daodian_infer.py:230 searches with k = len(slice)): materialising path
+    D2, I2 = index.search(arr[:8], 200)
+    rv2, _ = onp.cosine_topk(arr[:8], arr, 200)
+    np.testing.assert_allclose(D2.cpu().numpy(), rv2, rtol=0, atol=1e-2)
+    assert bool((I2[:, 0] == torch.arange(8, device=I2.device)).all())
+
+
+def test_cosine_index_any_width_and_high_precision():
+    """The reference's fastText retrieval builds IndexFlat(100) (daodian_infer.py:227): widths that are not multiples of
+    8 are zero-padded; precision='bf16x3' brings the scores within 1e-5 of fp32 cosines (they are compared against
+    tuned thresholds downstream)."""
+    import multimodalsimilar_b200 as mm
+
+    n, d, k = 3000, 100, 26
+    rng = np.random.RandomState(1)
+    arr = rng.standard_normal((n, d)).astype(np.float32)
+    rv, ri = onp.cosine_topk(arr[:50], arr, k)
+    for prec, tol in (("bf16", 1e-2), ("bf16x3", 2e-5)):
+        index = mm.CosineIndex(d, precision=prec)
+        index.add(arr)
+        D_, I_ = index.search(arr[:50], k)
+        np.testing.assert_allclose(D_.cpu().numpy(), rv, rtol=0, atol=tol)
+        if prec == "bf16x3":
+            np.testing.assert_array_equal(I_.cpu().numpy(), ri)
 
 
 def test_topk_merge_of_shard_lists():

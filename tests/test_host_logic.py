@@ -116,16 +116,19 @@ def test_fused_optimizer_rejects_what_it_cannot_update():
 def test_cosine_index_argument_checks():
     import multimodalsimilar_b200 as mm
 
+    assert mm.CosineIndex(100, device="cpu").dp == 104   # any width: rows are zero-padded to a multiple of 8
     with pytest.raises(ValueError):
-        mm.CosineIndex(12)            # d must be a multiple of 8
+        mm.CosineIndex(0)
+    with pytest.raises(ValueError):
+        mm.CosineIndex(16, precision="fp64")
     index = mm.CosineIndex(16, device="cpu")
     assert index.ntotal == 0
     with pytest.raises(ValueError):
         index.search(torch.zeros(2, 16), 0)
-    with pytest.raises(ValueError):
-        index.search(torch.zeros(2, 16), 129)
     with pytest.raises(RuntimeError, match="empty"):
         index.search(torch.zeros(2, 16), 5)
+    with pytest.raises(RuntimeError, match="empty"):
+        index.search(torch.zeros(2, 16), 500)   # k > 128 is served (materialising path), not rejected
     with pytest.raises(RuntimeError, match="CUDA"):
         index.add(torch.zeros(4, 16))   # there is no CPU path
 
