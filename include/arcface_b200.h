@@ -248,11 +248,14 @@ int32_t arcface_b200_adamw_normalize(float* w, const float* grad, float* exp_avg
  * returns (stream order) once every rank's flag for the same call has arrived here.  peer_bufs / peer_flags: HOST
  * arrays of `world` device addresses valid in this process (torch.distributed._symmetric_memory buffer_ptrs);
  * flags = uint32 [8][16] per rank, zeroed once; sync_dev = uint32 [16] of local device memory, zeroed once.  All ranks
- * must issue the same sequence of calls per channel.  Replaces the latency-bound NCCL all-gather / reduce-scatter of
+ * must issue the same sequence of calls per channel.  error_word (nullable; device or mapped pinned HOST memory): set
+ * to 1 + channel when a peer's flag has not arrived after a few seconds of polling -- the kernel then finishes without
+ * it (the step's results are meaningless) instead of hanging the GPU or trapping the context; the caller examines the
+ * word before its next exchange.  Replaces the latency-bound NCCL all-gather / reduce-scatter of
  * the class-sharded step (sharded.py; nn.DataParallel's gather / reduce in the reference). */
 int32_t arcface_b200_p2p_exchange(const void* src, size_t bytes_per_peer, size_t src_stride, const uint64_t* peer_bufs,
                                   const uint64_t* peer_flags, int32_t rank, int32_t world, size_t slot_stride,
-                                  int32_t channel, uint32_t* sync_dev, void* stream);
+                                  int32_t channel, uint32_t* sync_dev, uint32_t* error_word, void* stream);
 
 /* The all-gather form of arcface_b200_p2p_exchange (src_stride = 0) with a split receive layout: the first `split` bytes
  * of every rank's message land contiguously in rank order at the start of each receive buffer ([world][split]), the
@@ -261,7 +264,7 @@ int32_t arcface_b200_p2p_exchange(const void* src, size_t bytes_per_peer, size_t
  * of the receive buffer.  split = 0: plain slots, as arcface_b200_p2p_exchange. */
 int32_t arcface_b200_p2p_gather_split(const void* src, size_t bytes_per_peer, size_t src_stride, size_t split,
                                       const uint64_t* peer_bufs, const uint64_t* peer_flags, int32_t rank,
-                                      int32_t world, size_t slot_stride, int32_t channel, uint32_t* sync_dev,
+                                      int32_t world, size_t slot_stride, int32_t channel, uint32_t* sync_dev, uint32_t* error_word,
                                       void* stream);
 /* normalize_bwd_x over the SUM of n_parts partial dxhat buffers ([n_parts][B][D], part_stride floats apart), summed in
  * index order: the reduce half of the reduce-scatter, fused. */

@@ -87,10 +87,10 @@ SIGNATURES = {
                   c_double, c_int64, c_void_p, c_void_p, c_void_p]),
     "arcface_b200_p2p_exchange": (
         c_int32, [c_void_p, c_size_t, c_size_t, c_void_p, c_void_p, c_int32, c_int32, c_size_t, c_int32, c_void_p,
-                  c_void_p]),
+                  c_void_p, c_void_p]),
     "arcface_b200_p2p_gather_split": (
         c_int32, [c_void_p, c_size_t, c_size_t, c_size_t, c_void_p, c_void_p, c_int32, c_int32, c_size_t, c_int32,
-                  c_void_p, c_void_p]),
+                  c_void_p, c_void_p, c_void_p]),
     "arcface_b200_normalize_bwd_x_sum": (
         c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "arcface_b200_step_workspace_bytes": (c_int32, [c_int32, c_int32, c_int64, POINTER(c_size_t)]),

@@ -184,8 +184,14 @@ struct FwdStatsPairT : pr::PairDefaults {
     // registers with setmaxnreg (gemm_pair.cuh): producer / MMA / allocator warps 40, epilogue 96, helpers 64.
     // The helper loop is latency-bound per warp (global load -> shuffle reduction -> sqrt -> convert -> store), so
     // what raises its throughput is MORE warps each holding one row pair, not a deeper pipeline per warp.
-    static constexpr bool WIDE = NORM && AB_FWD_AUX_WARPS == 16;
-    static constexpr int LOW_REGS = WIDE ? 40 : 0, EPI_REGS = WIDE ? 96 : 0, AUX_REGS = WIDE ? 64 : 0;
+#ifndef AB_FWD_AUX_REGS
+#define AB_FWD_AUX_REGS 64
+#endif
+#ifndef AB_FWD_EPI_REGS
+#define AB_FWD_EPI_REGS 96
+#endif
+    static constexpr bool WIDE = NORM && AB_FWD_AUX_WARPS >= 16;
+    static constexpr int LOW_REGS = WIDE ? 40 : 0, EPI_REGS = WIDE ? AB_FWD_EPI_REGS : 0, AUX_REGS = WIDE ? AB_FWD_AUX_REGS : 0;
 #ifndef AB_FWD_RUN
 #define AB_FWD_RUN 8
 #endif

@@ -22,7 +22,11 @@
 namespace ab {
 
 constexpr int P2P_MAX_RANKS = 16;
-constexpr unsigned P2P_SPIN_LIMIT = 400000000u;  // ~ seconds: a lost peer traps instead of hanging the GPU forever
+// ~ seconds.  A peer that never shows up (crashed rank, mismatched call sequence) must not hang the GPU, and must not
+// kill this process's CUDA context either: the waiting thread gives up, raises the caller's error word (nullable; may
+// be mapped pinned host memory) and the kernel finishes normally.  The step's results are then meaningless; the host
+// side (p2p.PeerExchange) examines the word before its next exchange and raises.
+constexpr unsigned P2P_SPIN_LIMIT = 400000000u;
 
 struct P2PParams {
     unsigned long long bufs[P2P_MAX_RANKS];
@@ -37,6 +41,7 @@ struct P2PParams {
                                          // label vector, no unpacking copies
     int rank, world, channel;
     unsigned* sync;                      // this channel's [call number, arrival counter]
+    unsigned* error_word;                // nullable: set to 1 + channel when a peer's flag never arrives
 };
 
 __device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
@@ -84,7 +89,10 @@ __global__ void __launch_bounds__(256) p2p_exchange_kernel(const P2PParams p) {
         const unsigned* local = reinterpret_cast<const unsigned*>(p.flags[p.rank]) + p.channel * P2P_MAX_RANKS + threadIdx.x;
         unsigned spins = 0;
         while (static_cast<int>(ld_acquire_sys_u32(local) - call) < 0) {
-            if (++spins > P2P_SPIN_LIMIT) __trap();
+            if (++spins > P2P_SPIN_LIMIT) {
+                if (p.error_word != nullptr) *reinterpret_cast<volatile unsigned*>(p.error_word) = 1u + p.channel;
+                break;
+            }
             __nanosleep(64);
         }
     }
@@ -138,15 +146,15 @@ using namespace ab;
 extern "C" int32_t arcface_b200_p2p_exchange(const void* src, size_t bytes_per_peer, size_t src_stride,
                                              const uint64_t* peer_bufs, const uint64_t* peer_flags, int32_t rank,
                                              int32_t world, size_t slot_stride, int32_t channel, uint32_t* sync_dev,
-                                             void* stream) {
+                                             uint32_t* error_word, void* stream) {
     return arcface_b200_p2p_gather_split(src, bytes_per_peer, src_stride, 0, peer_bufs, peer_flags, rank, world,
-                                         slot_stride, channel, sync_dev, stream);
+                                         slot_stride, channel, sync_dev, error_word, stream);
 }
 
 extern "C" int32_t arcface_b200_p2p_gather_split(const void* src, size_t bytes_per_peer, size_t src_stride, size_t split,
                                                  const uint64_t* peer_bufs, const uint64_t* peer_flags, int32_t rank,
                                                  int32_t world, size_t slot_stride, int32_t channel, uint32_t* sync_dev,
-                                                 void* stream) {
+                                                 uint32_t* error_word, void* stream) {
     if (int32_t rc = check_arch()) return rc;
     AB_REQUIRE(split % 16 == 0 && split <= bytes_per_peer && (split == 0 || src_stride == 0), ARCFACE_B200_E_LAYOUT,
                "p2p_gather_split: split must be a multiple of 16 bytes inside an all-gather message");
@@ -170,6 +178,7 @@ extern "C" int32_t arcface_b200_p2p_gather_split(const void* src, size_t bytes_p
     p.split = split;
     p.rank = rank; p.world = world; p.channel = channel;
     p.sync = sync_dev + 2 * channel;
+    p.error_word = error_word;
     const unsigned long long total16 = (bytes_per_peer >> 4) * static_cast<unsigned long long>(world);
     unsigned long long want = (total16 + 255ull) / 256ull;   // one 16-byte chunk per thread ...
     const int grid = static_cast<int>(want < 1 ? 1 : (want > 64 ? 64 : want));  // ... up to 64 CTAs

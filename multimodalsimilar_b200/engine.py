@@ -297,6 +297,8 @@ class GraphedStep:
         else:
             self.x.copy_(x_local)
             self.y.copy_(y_local)
+        if self.peer is not None:
+            self.peer.check()   # an exchange of an earlier replay timed out waiting for a rank
         self.graph.replay()
         if self.guard is not None:
             self.guard.mark()

@@ -48,6 +48,9 @@ class PeerExchange:
         self._flags = (ctypes.c_uint64 * 16)(*(ptrs + [0] * (16 - len(ptrs))))
         self._bufs = [(ctypes.c_uint64 * 16)(*([p + off for p in ptrs] + [0] * (16 - len(ptrs)))) for off in self.off]
         self.sync = torch.zeros(16, dtype=torch.int32, device=device)   # [call number, arrival counter] per channel
+        # raised by the exchange kernel when a peer never shows up (csrc/p2p.cu); pinned host memory the device can
+        # write, examined before every exchange: a lost rank becomes a Python exception, not a dead CUDA context
+        self.err = torch.zeros(1, dtype=torch.int32).pin_memory()
         # Host-side record of the last channel ISSUED (eagerly or by a graph replay).  Channels 0 and 1 are always
         # separated by the other one, which is what makes their buffers safe to reuse (csrc/p2p.cu); two scatters in
         # a row (two backwards of one head without a forward between them) are not, so the second one is declined
@@ -59,10 +62,20 @@ class PeerExchange:
     def matches(self, b_loc: int, D: int) -> bool:
         return b_loc <= self.b_cap and D == self.D
 
+    def check(self) -> None:
+        """Raise if an earlier exchange timed out waiting for a peer (the results since then are meaningless)."""
+        code = int(self.err[0])
+        if code != 0:
+            raise RuntimeError("multimodalsimilar_b200: peer-memory exchange on channel %d timed out waiting for a rank "
+                               "(ARCFACE_B200_E_CUDA): a peer process died or the ranks issued different call sequences"
+                               % (code - 1))
+
     def _exchange(self, channel: int, src: torch.Tensor, bytes_per_peer: int, src_stride: int) -> torch.Tensor:
+        self.check()
         _lib.call("arcface_b200_p2p_exchange", ctypes.c_void_p(src.data_ptr()), bytes_per_peer, src_stride,
                   self._bufs[channel], self._flags, self.rank, self.world, self.slot[channel], channel,
-                  ctypes.c_void_p(self.sync.data_ptr()), torch.cuda.current_stream().cuda_stream)
+                  ctypes.c_void_p(self.sync.data_ptr()), ctypes.c_void_p(self.err.data_ptr()),
+                  torch.cuda.current_stream().cuda_stream)
         self.last_channel = channel
         lo = self.off[channel]
         return self.buf[lo: lo + self.slot[channel] * self.world].view(self.world, self.slot[channel])
@@ -73,9 +86,10 @@ class PeerExchange:
         n = packed.numel()
         if n % 16 != 0 or split % 16 != 0 or not (0 < split < n) or n > self.slot[channel]:
             raise ValueError("message of %d bytes (split at %d) does not fit channel %d" % (n, split, channel))
+        self.check()
         _lib.call("arcface_b200_p2p_gather_split", ctypes.c_void_p(packed.data_ptr()), n, 0, split, self._bufs[channel],
                   self._flags, self.rank, self.world, self.slot[channel], channel, ctypes.c_void_p(self.sync.data_ptr()),
-                  torch.cuda.current_stream().cuda_stream)
+                  ctypes.c_void_p(self.err.data_ptr()), torch.cuda.current_stream().cuda_stream)
         self.last_channel = channel
         lo = self.off[channel]
         R = self.world
