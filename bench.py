@@ -124,7 +124,7 @@ class ClockSampler(threading.Thread):
                     self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
                 except Exception:
                     pass
-                time.sleep(0.001)
+                time.sleep(0.003)
         except Exception as e:  # pragma: no cover
             self.error = repr(e)
 
@@ -273,7 +273,7 @@ class Job:
             self.step()
         self.barrier()
         sampler = None
-        if sample_clocks:
+        if sample_clocks and self.rank == 0:   # the line is rank 0's; NVML polling from every rank only adds host jitter
             sampler = ClockSampler(self.dev.index or 0)
             sampler.start()
             t_wait = time.perf_counter()   # NVML initialisation takes tens of ms: short timed regions would see no sample
@@ -290,7 +290,7 @@ class Job:
             loss = self.step()
             evs[i + 1].record()
         self.barrier()
-        clocks = sampler.result() if sampler is not None else None
+        clocks = sampler.result() if sampler is not None else ({"sm_mhz": None, "note": "sampled on rank 0 only"} if sample_clocks else None)
         per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(steps))
         out = {"ms_per_step": self.max_over_ranks(evs[0].elapsed_time(evs[steps]) / steps),
                "ms_per_step_median": self.max_over_ranks(per[len(per) // 2]),

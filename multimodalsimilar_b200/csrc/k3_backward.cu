@@ -803,10 +803,13 @@ struct BwdDWpT : pr::PairDefaults {
     // storing full 128-byte lines with st.global.v4 (no proxy fence, no TMA) ~7.8k; 256-bit stores straight from
     // registers (STG.E.ENL2.256, one full sector per lane) ~8.8k; sixteen epilogue warps (four per lane quadrant, 2 KB
     // boxes of 16 columns, registers traded with setmaxnreg) ~9.8k per tile in total.  Every variant lands at
-    // 13-16 bytes per clock and SM: the fp32 gradient leaves an SM no faster than that whatever issues the stores
-    // (a device-wide copy kernel writes ~11.5 B/clk/SM at the measured HBM peak), i.e. a dW tile (128 KB per CTA) costs
-    // >= 8.2k cycles against 4.1k of MMA.  The dW role is bound by the store path of its SMs, which is why the role
-    // split gives it the largest share; the epilogue's form is not the lever.
+    // 13-19 bytes per clock and SM.  tools/probes/ explains why: an SM that does nothing else stores 32 B/clk
+    // (store_probe), lane pairs writing 64 contiguous bytes per row reach that rate straight from registers
+    // (store_pattern_probe; tried here too: 9.8k cycles per tile), but the rate falls to 10-19 B/clk as soon as the same
+    // SM also pulls data in (store_load_probe) -- and this role's SMs pull in 192 KB per tile (the dC^T operand and the
+    // normalised weights of the correction term) for the 128 KB they write.  A dW tile therefore costs >= ~8k cycles
+    // against 4.1k of MMA whatever issues the stores: the role is bound by its SMs' memory port, which is why the
+    // role split gives it the largest share; the epilogue's form is not the lever.
     static constexpr bool STAGING = true;
     static constexpr bool RES_A = false;
     static constexpr int NCOL = 2 * pr::ROWS;
