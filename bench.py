@@ -31,6 +31,7 @@ over the ranks (fixed global problem: strong scaling) with three exchanges per s
 --impl reference: only that CPU path, as its own JSON line.
 """
 import argparse
+import gc
 import json
 import math
 import os
@@ -283,13 +284,19 @@ class Job:
             sampler.power.clear()
             sampler.mask = 0
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
-        self.barrier()
-        evs[0].record()
-        loss = None
-        for i in range(steps):
-            loss = self.step()
-            evs[i + 1].record()
-        self.barrier()
+        # a generational GC pause in ONE rank stalls every rank at the next exchange: collect now, not inside the region
+        gc.collect()
+        gc.disable()
+        try:
+            self.barrier()
+            evs[0].record()
+            loss = None
+            for i in range(steps):
+                loss = self.step()
+                evs[i + 1].record()
+            self.barrier()
+        finally:
+            gc.enable()
         clocks = sampler.result() if sampler is not None else ({"sm_mhz": None, "note": "sampled on rank 0 only"} if sample_clocks else None)
         per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(steps))
         out = {"ms_per_step": self.max_over_ranks(evs[0].elapsed_time(evs[steps]) / steps),
