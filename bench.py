@@ -301,7 +301,8 @@ class Job:
         per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(steps))
         out = {"ms_per_step": self.max_over_ranks(evs[0].elapsed_time(evs[steps]) / steps),
                "ms_per_step_median": self.max_over_ranks(per[len(per) // 2]),
-               "ms_per_step_best": self.max_over_ranks(per[0]), "loss": float(loss.detach())}
+               "ms_per_step_best": self.max_over_ranks(per[0]), "ms_per_step_worst": self.max_over_ranks(per[-1]),
+               "loss": float(loss.detach())}
         if clocks is not None:
             out["clocks"] = clocks
         return out
@@ -683,7 +684,8 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "ms_per_step_median": t["ms_per_step_median"],
-            "ms_per_step_best": t["ms_per_step_best"], "higher_is_better": True, "scaling": "strong",
+            "ms_per_step_best": t["ms_per_step_best"], "ms_per_step_worst": t["ms_per_step_worst"],
+            "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(head_name, cfg, world, exchange),
             "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline_step": roof_step, "loss": t["loss"],

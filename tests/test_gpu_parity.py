@@ -4,8 +4,17 @@ the golden vectors minted from the reference, or -- at sizes the oracle cannot r
 PyTorch restatement run on the same GPU (test-only checker).
 
 Tolerances (BASELINE.json north_star): label / argmax indices bit-exact (on rows whose top-2 gap exceeds
-the logit tolerance), loss within 1e-3 relative, logits and gradients within 2e-2 absolute in the bf16
-mode; the logit tolerance is taken on z at s = 30 and on z / s * 30 otherwise.
+the logit tolerance), loss within 1e-3 relative, logits and gradients within 2e-2 absolute.
+
+Two precision modes, two statements:
+  * precision='bf16x3' (the parity mode, test_bf16x3_*): the north-star gates are held UNSCALED on every golden case,
+    on BASELINE config 1 and at full size, at the reference's own s = 64 -- logits within 2e-3 (gate 2e-2), cosines
+    within 1e-4, loss within 2e-5 relative, argmax exact down to a top-2 gap of 2e-3.
+  * precision='bf16' (the throughput mode, everything else in this file): bf16 operands put ~0.45 / sqrt(D) bf16 ulps on
+    a cosine, i.e. the logit error is 2e-2 at BASELINE config 1 (s = 30, D = 512: held unscaled there) and grows with
+    s / 30 and sqrt(512 / D) -- 3.6e-2 at s = 64, D = 512 (SURVEY.md section 7-4 measured exactly that).  For those
+    shapes the tests assert the mode's error model (`logit_atol`), which is an accuracy statement about bf16, not the
+    north-star gate; the gate itself is asserted in the bf16x3 mode.
 """
 import math
 
