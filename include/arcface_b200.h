@@ -69,7 +69,8 @@ int32_t arcface_b200_normalize_cast(const float* src, int64_t rows, int32_t D, u
 /* K1 of the ARCFACE_B200_PREC_BF16X3 mode: each normalised value v as the bf16 pair hi = bf16(v), lo = bf16(v - hi),
  * the row written three times along the contraction dimension -- dst3 [rows][3 D]: order 0 (embeddings) [hi|hi|lo],
  * order 1 (class weights) [hi|lo|hi] -- so that the bf16 GEMMs over 3 D columns (arcface_b200_forward_stats /
- * _logits / _cosine_topk with D := 3 D) accumulate hi.hi + hi.lo + lo.hi in fp32.  dst_t (nullable): transposed hi. */
+ * _logits / _cosine_topk with D := 3 D) accumulate hi.hi + hi.lo + lo.hi in fp32.  dst_t (nullable, [D][3 ld_t], caller
+ * zeroes the padding): the transposed operand of the dW GEMM, [hi^T | lo^T | hi^T]. */
 int32_t arcface_b200_normalize_cast3(const float* src, int64_t rows, int32_t D, int32_t order, uint16_t* dst3,
                                      float* inv_norm, uint16_t* dst_t, int64_t ld_t, void* stream);
 
@@ -194,8 +195,12 @@ int32_t arcface_b200_backward(const uint16_t* xhat, const uint16_t* xhat_t, int6
                               void* workspace, size_t workspace_bytes, void* stream);
 
 /* arcface_b200_backward with a precision mode.  prec = ARCFACE_B200_PREC_BF16X3: `xhat` [B][3 D] and `what`
- * [C_local][3 D] are the rows written by arcface_b200_normalize_cast3 (orders 0 and 1), `xhat_t` the transposed hi part;
- * the probabilities are recomputed from the three-term product, the gradient GEMMs run on bf16 dC and the hi parts. */
+ * [C_local][3 D] are the rows written by arcface_b200_normalize_cast3 (orders 0 and 1), `xhat_t` its transposed output
+ * [D][3 ld_t] = [hi^T | lo^T | hi^T] with ld_t = B rounded up to 64 and ZERO padding columns.  The probabilities are
+ * recomputed from the three-term product; dC leaves its epilogue as a bf16 pair hi + lo ([hi | hi | lo] blocks of the
+ * scratch), the dW GEMM contracts over the three blocks, dX runs as three launches (hi.W_hi + hi.W_lo + lo.W_hi) and a
+ * row pass adds the lo part of the weight projection: gradients within ~1e-5 relative of fp32 (B <= 1024; larger
+ * batches keep bf16 dC and the hi operands). */
 int32_t arcface_b200_backward_prec(const uint16_t* xhat, const uint16_t* xhat_t, int64_t ld_t, const uint16_t* what,
                                    const float* inv_nw, const float* lse, const float* one_minus_p, const float* dphi,
                                    const int32_t* label_local, int32_t B, int32_t D, int64_t C_local, float s,

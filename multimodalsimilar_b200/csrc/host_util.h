@@ -58,6 +58,10 @@ static inline const char* diag_env(const char* name) { return getenv(name); }
 static inline const char* diag_env(const char*) { return nullptr; }
 #endif
 
+// rows.cu: dW[c] -= inv_nw[c] * (sum of q slots)[c] * what_lo[c] (bf16x3 backward, see k3_backward.cu)
+int32_t launch_dw_lo_correction(float* dw, const void* what3, const float* q, int q_slots, const float* inv_nw,
+                                int64_t C, int D, cudaStream_t st);
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace ab

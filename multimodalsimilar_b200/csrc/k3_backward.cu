@@ -574,7 +574,10 @@ struct Ring {
     int done_target;   // arrivals that free its slot
 };
 
-template <bool FUSED>
+// X3 = true (the bf16x3 precision mode, non-fused launches only): dC leaves as a bf16 pair hi + lo laid out
+// [hi | hi | lo] in three blocks of Bp columns, so that the dW GEMM over 3 Bp columns against [xhat_hi^T | xhat_lo^T |
+// xhat_hi^T] and three dX launches (hi.W_hi, hi.W_lo, lo.W_hi) keep the gradient GEMMs at ~2^-17 relative as well.
+template <bool FUSED, bool X3 = false>
 struct BwdDCpT : pr::PairDefaults {
     static constexpr int STAGES = 3;  // 3 x 16 KB: the per-column constants below take the fourth stage's room
     static constexpr bool STAGING = true;
@@ -685,7 +688,7 @@ struct BwdDCpT : pr::PairDefaults {
         // caller knows none of the CTA's 128 classes is a label of these batch columns).
         template <bool LABELS>
         __device__ __forceinline__ void eight(const uint32_t* v, int j0, float coef, int cmatch, float& qa, float& qb,
-                                              uint32_t* o) const {
+                                              uint32_t* o, uint32_t* ol) const {
             const float4 l0 = *reinterpret_cast<const float4*>(lse2 + j0);
             const float4 l1 = *reinterpret_cast<const float4*>(lse2 + j0 + 4);
             const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
@@ -702,7 +705,11 @@ struct BwdDCpT : pr::PairDefaults {
                 dc[j] = d;
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = pack_bf16x2(dc[2 * j], dc[2 * j + 1]);
+            for (int j = 0; j < 4; ++j) {
+                o[j] = pack_bf16x2(dc[2 * j], dc[2 * j + 1]);
+                if constexpr (X3)   // lo = bf16(d - hi): the two halves of the packed word are the hi values
+                    ol[j] = pack_bf16x2(dc[2 * j] - bf16_lo(o[j]), dc[2 * j + 1] - bf16_hi(o[j]));
+            }
         }
         template <bool LABELS>
         __device__ __forceinline__ void group(uint32_t taddr, int g, int row0, float coef, int cmatch, float (&q)[4]) {
@@ -713,17 +720,35 @@ struct BwdDCpT : pr::PairDefaults {
             tmem_ld_wait();
             const unsigned long long t1 = tick();
             uint32_t o[32];  // 64 columns of bf16
-#pragma unroll
-            for (int k = 0; k < 4; ++k) eight<LABELS>(v0 + 8 * k, g * 64 + 8 * k, coef, cmatch, q[0], q[1], o + 4 * k);
+            uint32_t ol[X3 ? 32 : 1];
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                eight<LABELS>(v1 + 8 * k, g * 64 + 32 + 8 * k, coef, cmatch, q[2], q[3], o + 16 + 4 * k);
+                eight<LABELS>(v0 + 8 * k, g * 64 + 8 * k, coef, cmatch, q[0], q[1], o + 4 * k, ol + (X3 ? 4 * k : 0));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                eight<LABELS>(v1 + 8 * k, g * 64 + 32 + 8 * k, coef, cmatch, q[2], q[3], o + 16 + 4 * k,
+                              ol + (X3 ? 16 + 4 * k : 0));
             const unsigned long long t2 = tick();
             stager.acquire();  // only now: the previous box has had the whole computation above to leave
             const unsigned long long t3 = tick();
 #pragma unroll
             for (int k = 0; k < 8; ++k) stager.put(k, o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
-            stager.commit(tm_out, b0 + g * 64, row0);  // rows past the chunk are clipped by the TMA
+            if constexpr (X3) {
+                // the hi box goes to column blocks 0 and 1 (one staging, two TMA stores), the lo box to block 2
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(tm_out, stager.buf, b0 + g * 64, row0);
+                    tma_store_2d(tm_out, stager.buf, p.Bp + b0 + g * 64, row0);
+                    bulk_commit();
+                }
+                stager.acquire();
+#pragma unroll
+                for (int k = 0; k < 8; ++k) stager.put(k, ol[4 * k], ol[4 * k + 1], ol[4 * k + 2], ol[4 * k + 3]);
+                stager.commit(tm_out, 2 * p.Bp + b0 + g * 64, row0);
+            } else {
+                stager.commit(tm_out, b0 + g * 64, row0);  // rows past the chunk are clipped by the TMA
+            }
             if (prof != nullptr) { pacc[2] += t1 - t0; pacc[3] += t2 - t1; pacc[4] += t3 - t2; }
         }
         __device__ void prefetch(int) {}
@@ -778,6 +803,7 @@ struct BwdDCpT : pr::PairDefaults {
     };
 };
 using BwdDCp = BwdDCpT<false>;
+using BwdDCp3 = BwdDCpT<false, true>;
 
 // ------------------------------------------------------------------ dW on a CTA pair
 // streamed = dC^T scratch rows (256 classes per tile), resident = 256 rows of Xhat^T (embedding columns of the
@@ -1080,6 +1106,7 @@ struct BwdPlan {
     size_t cnt_off, cnt_bytes;
     int q_slots;             // partial-sum slots of q per class
     size_t scratch_off, scratch_bytes, q_off, q_bytes, total;
+    int kx;                  // column blocks of the dC^T scratch: 1, or 3 = [hi | hi | lo] (bf16x3 mode on CTA pairs)
 };
 
 // CTA pairs of bwd_fused_kernel that can be resident at once on the current device (the roles spin on each
@@ -1160,7 +1187,10 @@ static BwdPlan plan_backward(int B, int D, int64_t C, int nsm, int Ds = 0) {
     pl.fused = false;
     pl.n_dc = pl.n_dw = pl.n_dx = pl.ring_slots = 0;
     pl.n_blocks = static_cast<int>((C + 255) / 256);
-    if (pl.dc_pair && pl.dw_pair && !env_is("ARCFACE_B200_BWD_IMPL", "split")) {
+    // bf16x3 mode (Ds = 3 D) on CTA pairs: hi/lo dC through a three-block scratch, three launches per chunk (the ring
+    // of the single-launch backward holds one block per slot)
+    pl.kx = (Ds > D && pl.dc_pair && pl.dw_pair) ? 3 : 1;
+    if (pl.dc_pair && pl.dw_pair && pl.kx == 1 && !env_is("ARCFACE_B200_BWD_IMPL", "split")) {
         const int n_res_dc = (B + 255) / 256, n_res_dw = (D + 255) / 256;
         const int tiles = n_res_dc * n_res_dw;         // dX output tiles (256 x 256)
         const int dx_unit = (tiles + 1) / 2;           // CTA pairs per dX split
@@ -1238,7 +1268,7 @@ static BwdPlan plan_backward(int B, int D, int64_t C, int nsm, int Ds = 0) {
         if (chunk > c_round) chunk = c_round;
     } else {
         // the scratch goes through HBM once; as few launches as the cap allows, evenly sized
-        int64_t max_chunk = static_cast<int64_t>(cap / (static_cast<size_t>(pl.Bp) * 2)) / 128 * 128;
+        int64_t max_chunk = static_cast<int64_t>(cap / (static_cast<size_t>(pl.Bp) * 2 * pl.kx)) / 128 * 128;
         if (max_chunk < 128) max_chunk = 128;
         const int64_t n = (c_round + max_chunk - 1) / max_chunk;
         chunk = ((c_round / 128 + n - 1) / n) * 128;
@@ -1246,7 +1276,7 @@ static BwdPlan plan_backward(int B, int D, int64_t C, int nsm, int Ds = 0) {
     pl.chunk_classes = static_cast<int>(chunk);
     pl.n_chunks = static_cast<int>((C + chunk - 1) / chunk);
     pl.scratch_off = 0;
-    pl.scratch_bytes = static_cast<size_t>(chunk) * pl.Bp * 2;
+    pl.scratch_bytes = static_cast<size_t>(chunk) * pl.Bp * 2 * pl.kx;
     pl.q_off = (pl.scratch_bytes + 255) / 256 * 256;
     pl.q_bytes = static_cast<size_t>(C) * 4 * pl.q_slots;
     pl.total = pl.q_off + (pl.q_bytes + 255) / 256 * 256;
@@ -1361,11 +1391,21 @@ static int32_t backward_impl(const uint16_t* xhat, const uint16_t* xhat_t, int64
     CUtensorMap tm_w_k, tm_x_k, tm_dct_k, tm_xt_k, tm_dct_mn, tm_w_mn, tm_dct_out, tm_dw_out, tm_dx_out;
     if (int32_t rc = make_tmap_kmajor(&tm_w_k, what, Ds, C_local, ldw, BLOCK_M)) return rc;
     if (int32_t rc = make_tmap_kmajor(&tm_x_k, xhat, Ds, B, ldw, (pl.dc_rs || pl.dc_pair) ? rs::BN : BwdDC::BLOCK_N)) return rc;
-    if (int32_t rc = make_tmap_kmajor(&tm_dct_k, dct, B, pl.chunk_classes, pl.Bp, BLOCK_M)) return rc;
-    if (int32_t rc = make_tmap_kmajor(&tm_xt_k, xhat_t, B, D, ld_t, (pl.dw_rs || pl.dw_pair) ? rs::BN : BwdDW::BLOCK_N)) return rc;
-    if (int32_t rc = make_tmap_mnmajor(&tm_dct_mn, dct, B, pl.chunk_classes, pl.Bp)) return rc;
+    const bool x3 = pl.kx == 3;   // hi/lo dC: every dC^T map spans three blocks of Bp columns
+    const int64_t ldc = static_cast<int64_t>(pl.Bp) * pl.kx;
+    if (x3) {
+        AB_REQUIRE(ld_t == pl.Bp, ARCFACE_B200_E_LAYOUT,
+                   "backward (bf16x3): xhat_t must be [D][3 * ld_t] with ld_t = %d (the batch rounded up to 64)", pl.Bp);
+        // the batch padding inside each block is zero on both sides (written by the dC^T epilogue / the caller)
+        if (int32_t rc = make_tmap_kmajor(&tm_dct_k, dct, 3 * pl.Bp, pl.chunk_classes, ldc, BLOCK_M)) return rc;
+        if (int32_t rc = make_tmap_kmajor(&tm_xt_k, xhat_t, 3 * pl.Bp, D, 3 * ld_t, rs::BN)) return rc;
+    } else {
+        if (int32_t rc = make_tmap_kmajor(&tm_dct_k, dct, B, pl.chunk_classes, pl.Bp, BLOCK_M)) return rc;
+        if (int32_t rc = make_tmap_kmajor(&tm_xt_k, xhat_t, B, D, ld_t, (pl.dw_rs || pl.dw_pair) ? rs::BN : BwdDW::BLOCK_N)) return rc;
+    }
+    if (int32_t rc = make_tmap_mnmajor(&tm_dct_mn, dct, B, pl.chunk_classes, ldc)) return rc;
     if (int32_t rc = make_tmap_mnmajor(&tm_w_mn, what, D, C_local, ldw)) return rc;
-    if (int32_t rc = make_tmap_store(&tm_dct_out, dct, 2, pl.Bp, pl.chunk_classes, pl.Bp)) return rc;
+    if (int32_t rc = make_tmap_store(&tm_dct_out, dct, 2, ldc, pl.chunk_classes, ldc)) return rc;
     if (int32_t rc = make_tmap_store(&tm_dw_out, dw, 4, D, C_local, D)) return rc;
     if (int32_t rc = make_tmap_store(&tm_dx_out, dxhat, 4, D, B, D)) return rc;
 
@@ -1515,7 +1555,24 @@ static int32_t backward_impl(const uint16_t* xhat, const uint16_t* xhat_t, int64
         const int cn = static_cast<int>(C_local - c0 < pl.chunk_classes ? C_local - c0 : pl.chunk_classes);
         const int c_blocks = (cn + BLOCK_M - 1) / BLOCK_M;
         // ---- dC^T (and q) for this chunk
-        if (pl.dc_pair) {
+        if (x3) {
+            BwdDCp3::Params p;
+            pr::core_set_k<BwdDCp3>(p.core, Ds, BwdDCp3::EXTRA_BYTES);
+            p.core.s_blocks = (cn + BwdDCp3::NCOL - 1) / BwdDCp3::NCOL;
+            p.core.s_row0 = static_cast<int>(c0);
+            p.core.n_res = (B + BwdDCp3::NCOL - 1) / BwdDCp3::NCOL;
+            p.core.contiguous = 0;
+            p.core.prefetch_tiles = 2;
+            p.B = B; p.C = C; p.Bp = pl.Bp;
+            p.s_log2e = s * LOG2E_B; p.coef = s * grad_scale; p.grad_dev = grad_loss_dev;
+            p.lse = lse; p.one_minus_p = one_minus_p; p.dphi = dphi; p.label_local = label_local;
+            p.q = q;
+            int groups = (nsm / 2) / p.core.n_res;
+            if (groups < 1) groups = 1;
+            if (groups > p.core.s_blocks) groups = p.core.s_blocks;
+            if (int32_t rc = pr::launch_pair<BwdDCp3>(tm_w_k, tm_x_k, tm_dct_out, p, groups, BwdDCp3::EXTRA_BYTES, st))
+                return rc;
+        } else if (pl.dc_pair) {
             BwdDCp::Params p;
             pr::core_set_k<BwdDCp>(p.core, Ds, BwdDCp::EXTRA_BYTES);
             p.core.s_blocks = (cn + BwdDCp::NCOL - 1) / BwdDCp::NCOL;
@@ -1562,7 +1619,7 @@ static int32_t backward_impl(const uint16_t* xhat, const uint16_t* xhat_t, int64
         // ---- dW rows of this chunk
         if (pl.dw_pair) {
             BwdDWp::Params p;
-            pr::core_set_k<BwdDWp>(p.core, pl.Bp, BwdDWp::EXTRA_BYTES);
+            pr::core_set_k<BwdDWp>(p.core, pl.Bp * pl.kx, BwdDWp::EXTRA_BYTES);
             p.core.s_blocks = (cn + BwdDWp::NCOL - 1) / BwdDWp::NCOL;
             p.core.s_row0 = 0;  // the scratch is chunk-relative
             p.core.n_res = (D + BwdDWp::NCOL - 1) / BwdDWp::NCOL;
@@ -1618,7 +1675,21 @@ static int32_t backward_impl(const uint16_t* xhat, const uint16_t* xhat_t, int64
             p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
             const int total = p.m_tiles * dn_tiles * p.splits;
             const int grid = total < nsm ? total : nsm;
-            if (int32_t rc = launch_gemm<BwdDX2>(tm_dct_mn, tm_w_mn, tm_dx_out, p, grid, 0, st)) return rc;
+            if (x3) {
+                // dXhat += dC_hi . W_hi + dC_hi . W_lo + dC_lo . W_hi: three launches over column-block views of the
+                // scratch ([hi | hi | lo]) and of what ([hi | lo | hi]), all reduce-adding into the same dXhat
+                const __nv_bfloat16* wb = reinterpret_cast<const __nv_bfloat16*>(what);
+                const __nv_bfloat16* a_view[3] = {dct, dct, dct + 2 * pl.Bp};
+                const __nv_bfloat16* b_view[3] = {wb, wb + D, wb};
+                for (int v = 0; v < 3; ++v) {
+                    CUtensorMap ta, tb;
+                    if (int32_t rc = make_tmap_mnmajor(&ta, a_view[v], B, pl.chunk_classes, ldc)) return rc;
+                    if (int32_t rc = make_tmap_mnmajor(&tb, b_view[v], D, C_local, ldw)) return rc;
+                    if (int32_t rc = launch_gemm<BwdDX2>(ta, tb, tm_dx_out, p, grid, 0, st)) return rc;
+                }
+            } else if (int32_t rc = launch_gemm<BwdDX2>(tm_dct_mn, tm_w_mn, tm_dx_out, p, grid, 0, st)) {
+                return rc;
+            }
         } else {
             BwdDX::Params p;
             p.B = B; p.D = D; p.c_begin = static_cast<int>(c0);
@@ -1634,5 +1705,7 @@ static int32_t backward_impl(const uint16_t* xhat, const uint16_t* xhat_t, int64
             if (int32_t rc = launch_gemm<BwdDX>(tm_dct_mn, tm_w_mn, tm_dx_out, p, grid, 0, st)) return rc;
         }
     }
+    if (x3)   // the dW epilogue projected with what_hi only: add the lo part
+        return launch_dw_lo_correction(dw, what, q, pl.q_slots, inv_nw, C_local, D, st);
     return ARCFACE_B200_OK;
 }

@@ -152,11 +152,45 @@ __global__ void __launch_bounds__(256) normalize_cast3_kernel(const float* __res
         *reinterpret_cast<uint2*>(op + off_hi2 + d) = hi;
         *reinterpret_cast<uint2*>(op + off_lo + d) = lo;
         if (dst_t != nullptr) {
+            // transposed operand of the dW GEMM, three blocks of ld_t columns each: [hi^T | lo^T | hi^T] -- against
+            // dC^T laid out [hi | hi | lo] the contraction over 3 ld_t columns is hi.hi + hi.lo + lo.hi again
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dst_t[static_cast<int64_t>(d + j) * ld_t + row] = __float2bfloat16_rn(h[j]);
+            for (int j = 0; j < 4; ++j) {
+                __nv_bfloat16* tp = dst_t + static_cast<int64_t>(d + j) * (3 * ld_t) + row;
+                const __nv_bfloat16 hb = __float2bfloat16_rn(h[j]);
+                tp[0] = hb;
+                tp[ld_t] = __float2bfloat16_rn(l[j]);
+                tp[2 * ld_t] = hb;
+            }
         }
     }
 }
+
+// bf16x3 mode: the dW epilogue subtracts q[c] * what_hi[c] only; this adds the lo part of the projection,
+//   dW[c, :] -= inv_nw[c] * q[c] * what_lo[c, :],   what3 rows laid out [hi | lo | hi] (3 D wide), q = sum of q_slots slots.
+__global__ void __launch_bounds__(256)
+dw_lo_correction_kernel(float* __restrict__ dw, const __nv_bfloat16* __restrict__ what3, const float* __restrict__ q,
+                        int q_slots, const float* __restrict__ inv_nw, int64_t C, int D) {
+    const int lane = threadIdx.x & 31;
+    const int64_t c = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= C) return;
+    float qc = 0.f;
+    for (int sl = 0; sl < q_slots; ++sl) qc += q[static_cast<int64_t>(sl) * C + c];
+    const float f = -qc * inv_nw[c];
+    const __nv_bfloat16* lo = what3 + c * 3 * static_cast<int64_t>(D) + D;
+    float* row = dw + c * static_cast<int64_t>(D);
+    for (int d = lane * 4; d < D; d += 128) {
+        const uint2 w = *reinterpret_cast<const uint2*>(lo + d);
+        float4 v = *reinterpret_cast<float4*>(row + d);
+        v.x = fmaf(f, __uint_as_float(w.x << 16), v.x);
+        v.y = fmaf(f, __uint_as_float(w.x & 0xffff0000u), v.y);
+        v.z = fmaf(f, __uint_as_float(w.y << 16), v.z);
+        v.w = fmaf(f, __uint_as_float(w.y & 0xffff0000u), v.w);
+        *reinterpret_cast<float4*>(row + d) = v;
+    }
+}
+
+
 
 // The step before the head in the two-stream model (multimodal_classifier.py:50-56):
 //   emb = cat(F.normalize(img_emb), F.normalize(title_emb), dim = 1)
@@ -652,13 +686,22 @@ extern "C" int32_t arcface_b200_normalize_cast3(const float* src, int64_t rows, 
     AB_REQUIRE(rows >= 0 && D >= 8 && D % 8 == 0, ARCFACE_B200_E_SHAPE, "normalize_cast3: D=%d must be a positive multiple of 8", D);
     AB_REQUIRE(order == 0 || order == 1, ARCFACE_B200_E_ARG, "normalize_cast3: order must be 0 (hi|hi|lo) or 1 (hi|lo|hi)");
     AB_REQUIRE(aligned16(src) && aligned16(dst3), ARCFACE_B200_E_LAYOUT, "normalize_cast3: pointers must be 16-byte aligned");
-    AB_REQUIRE(dst_t == nullptr || ld_t >= rows, ARCFACE_B200_E_LAYOUT, "normalize_cast3: ld_t < rows");
+    AB_REQUIRE(dst_t == nullptr || ld_t >= rows, ARCFACE_B200_E_LAYOUT, "normalize_cast3: ld_t < rows (dst_t is [D][3 * ld_t])");
     if (rows == 0) return ARCFACE_B200_OK;
     const int wpb = 8;
     const int64_t nblk = (rows + wpb - 1) / wpb;
     AB_REQUIRE(nblk < (1ll << 31), ARCFACE_B200_E_SHAPE, "normalize_cast3: too many rows");
     normalize_cast3_kernel<<<static_cast<unsigned>(nblk), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
         src, rows, D, order, reinterpret_cast<__nv_bfloat16*>(dst3), inv_norm, reinterpret_cast<__nv_bfloat16*>(dst_t), ld_t);
+    AB_CHECK_CUDA(cudaGetLastError());
+    return ARCFACE_B200_OK;
+}
+
+int32_t ab::launch_dw_lo_correction(float* dw, const void* what3, const float* q, int q_slots, const float* inv_nw,
+                                    int64_t C, int D, cudaStream_t st) {
+    if (C == 0) return ARCFACE_B200_OK;
+    dw_lo_correction_kernel<<<static_cast<unsigned>((C + 7) / 8), 256, 0, st>>>(
+        dw, static_cast<const __nv_bfloat16*>(what3), q, q_slots, inv_nw, C, D);
     AB_CHECK_CUDA(cudaGetLastError());
     return ARCFACE_B200_OK;
 }

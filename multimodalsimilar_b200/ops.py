@@ -69,7 +69,8 @@ PREC = {"bf16": 0, "bf16x3": 1}   # ARCFACE_B200_PREC_* (include/arcface_b200.h)
 
 def normalize_cast3(src: torch.Tensor, order: int, want_transpose: bool = False):
     """K1 of the bf16x3 mode.  src [R, D] fp32 -> (bf16 [R, 3 D] laid out [hi|hi|lo] (order 0, embeddings) or
-    [hi|lo|hi] (order 1, class weights), inv_norm fp32 [R], optional transposed hi part bf16 [D, ld_t])."""
+    [hi|lo|hi] (order 1, class weights), inv_norm fp32 [R], optional transposed operand of the dW GEMM: bf16
+    [D, 3 ld_t] = [hi^T | lo^T | hi^T] with ld_t = R rounded up to 64 and zero padding)."""
     _req(src, torch.float32, "src")
     R, D = src.shape
     dst = torch.empty((R, 3 * D), dtype=torch.bfloat16, device=src.device)
@@ -78,7 +79,7 @@ def normalize_cast3(src: torch.Tensor, order: int, want_transpose: bool = False)
     ld_t = 0
     if want_transpose:
         ld_t = round_up(R, 64)
-        dst_t = torch.empty((D, ld_t), dtype=torch.bfloat16, device=src.device)
+        dst_t = torch.zeros((D, 3 * ld_t), dtype=torch.bfloat16, device=src.device)   # the padding columns are contracted
     _lib.call("arcface_b200_normalize_cast3", _ptr(src), R, D, int(order), _ptr(dst), _ptr(inv), _ptr(dst_t), ld_t,
               _stream())
     return dst, inv, dst_t
@@ -329,7 +330,7 @@ def backward(xhat, xhat_t, what, inv_nw, lse, one_minus_p, dphi, label_local, s:
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     if grad_loss_dev is not None:
         grad_loss_dev = _req(grad_loss_dev.reshape(1), torch.float32, "grad_loss")
-    _lib.call("arcface_b200_backward_prec", _ptr(xhat), _ptr(xhat_t), xhat_t.shape[1], _ptr(what), _ptr(inv_nw),
+    _lib.call("arcface_b200_backward_prec", _ptr(xhat), _ptr(xhat_t), xhat_t.shape[1] // (3 if prec else 1), _ptr(what), _ptr(inv_nw),
               _ptr(lse), _ptr(one_minus_p), _ptr(dphi), _ptr(label_local), B, D, C, s, grad_scale, _ptr(grad_loss_dev),
               _ptr(dxhat), _ptr(dw), _ptr(ws), nbytes, int(prec), _stream())
     return dxhat, dw

@@ -34,13 +34,14 @@ def _worker(rank, world, port, case, out_dir):
     from multimodalsimilar_b200 import engine
     from oracle import arcface_numpy as onp
 
-    B, D, C, s, m, graph, p2p = case
+    B, D, C, s, m, graph, p2p = case[:7]
+    prec = case[7] if len(case) > 7 else "bf16"
     _, w, _ = onp.synthetic_inputs(B, D, C, seed=11, trained_like=False)
-    head = mm.ShardedArcMarginProduct(D, C, s=s, m=m, use_cuda_graph=graph, use_p2p=p2p).to(dev)
+    head = mm.ShardedArcMarginProduct(D, C, s=s, m=m, use_cuda_graph=graph, use_p2p=p2p, precision=prec).to(dev)
     head.load_full_weight(torch.from_numpy(w))
     dense = None
     if rank == 0:
-        dense = mm.ArcMarginProduct(D, C, s=s, m=m, use_cuda_graph=False).to(dev)
+        dense = mm.ArcMarginProduct(D, C, s=s, m=m, use_cuda_graph=False, precision=prec).to(dev)
         with torch.no_grad():
             dense.weight.copy_(torch.from_numpy(w))
     b_loc = B // world
@@ -116,7 +117,8 @@ def _worker(rank, world, port, case, out_dir):
     (64, 128, 3001, 64.0, 0.4, False, True),    # eager, peer-memory exchanges (csrc/p2p.cu)
     (64, 128, 3001, 64.0, 0.4, True, True),     # graph replay over peer memory
     (128, 512, 20000, 64.0, 0.5, True, False),  # bench-like D, graph replay over NCCL
-    (64, 1024, 5001, 64.0, 0.4, True, True),    # BASELINE config 3 width (D > 512: generic kernels)
+    (64, 1024, 5001, 64.0, 0.4, True, True),    # BASELINE config 3 width (D > 512: both operands streamed)
+    (64, 256, 3001, 64.0, 0.4, True, True, "bf16x3"),   # the parity mode, class-sharded, graph replay over peer memory
 ])
 def test_two_gpu_sharded_head_matches_dense(case, tmp_path):
     if torch.cuda.device_count() < 2:
