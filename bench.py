@@ -58,7 +58,10 @@ CONFIGS = {
     "c5_1m": {"B": 1024, "D": 512, "C": 1000000, "s": 64.0, "m": 0.5, "what": "BASELINE config 5: class sweep, C=1M"},
     "c5_10m": {"B": 1024, "D": 512, "C": 10000000, "s": 64.0, "m": 0.5, "what": "BASELINE config 5: class sweep, C=10M"},
 }
-EXTRA_CONFIGS = ["c2", "c3", "c4", "c5_100k", "c5_1m", "c5_10m"]
+CONFIGS["ns_bf16x3"] = dict(CONFIGS["ns"], precision="bf16x3",
+                            what="north-star shape in the high-precision mode (precision='bf16x3': the north star's "
+                                 "'1e-4 under a TF32 mode' gates)")
+EXTRA_CONFIGS = ["c2", "c3", "c4", "c5_100k", "c5_1m", "c5_10m", "ns_bf16x3"]
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of the north-star
 # workload on one B200; only meaningful for the single-GPU north-star shape.
 NCU_TRAFFIC = {"fwd": 2.300311e9 + 0.995569e9, "k3": 1.401256e9 + 2.114588e9,
@@ -229,13 +232,15 @@ class Job:
         gen = torch.Generator(device="cpu").manual_seed(0)
         self.x_host = torch.randn(B, D, generator=gen).pin_memory()
         self.y_host = torch.randint(0, C, (B,), generator=gen).pin_memory()
+        prec = cfg.get("precision", "bf16")
         if world == 1:
-            head = mm.ArcMarginProduct(D, 8, s=s, m=m)
+            head = mm.ArcMarginProduct(D, 8, s=s, m=m, precision=prec)
             head.out_feature = C
             self.c_lo, self.c_hi = 0, C
         else:
             # ARCFACE_B200_P2P=0: exchanges through NCCL instead of peer-mapped memory (A/B measurements)
-            head = mm.ShardedArcMarginProduct(D, world, s=s, m=m, use_p2p=os.environ.get("ARCFACE_B200_P2P", "1") != "0")
+            head = mm.ShardedArcMarginProduct(D, world, s=s, m=m, precision=prec,
+                                              use_p2p=os.environ.get("ARCFACE_B200_P2P", "1") != "0")
             head.out_feature = C
             head.class_lo, head.class_hi = mm.shard_range(C, world, rank)
             self.c_lo, self.c_hi = head.class_lo, head.class_hi
@@ -362,7 +367,8 @@ class Job:
         ref_loss = float(ref["loss"])
         # bf16 noise floor of a logit: rows whose reference winner leads by less cannot be
         # expected to keep their argmax under ANY bf16 evaluation
-        noise = LOGIT_ATOL * (s / 30.0) * max(1.0, math.sqrt(512.0 / D))
+        x3 = cfg.get("precision", "bf16") == "bf16x3"
+        noise = 1e-3 if x3 else LOGIT_ATOL * (s / 30.0) * max(1.0, math.sqrt(512.0 / D))
         sep = ref["top2_gap"][rows] > 2.0 * noise
         mism_sep = int((got_pred[sep] != ref["argmax"][rows][sep]).sum())
         match_all = float((got_pred == ref["argmax"][rows]).float().mean())
@@ -372,6 +378,8 @@ class Job:
             "loss_rel": abs(got_loss - ref_loss) / max(1.0, abs(ref_loss)),
             "dx_max_abs": float(ddx.abs().max()), "dx_rel_fro": float(ddx.norm() / ref["dx"][rows].norm().clamp_min(1e-30)),
             "dw_max_abs": float(ddw.abs().max()), "dw_rel_fro": float(ddw.norm() / ref["dw"].norm().clamp_min(1e-30)),
+            "dx_max_rel": float(ddx.abs().max() / ref["dx"][rows].abs().max().clamp_min(1e-30)),
+            "dw_max_rel": float(ddw.abs().max() / ref["dw"].abs().max().clamp_min(1e-30)),
             "argmax_mismatch_separated_rows": float(mism_sep), "argmax_mismatch_all_rows_frac": 1.0 - match_all,
         }
         n_sep = int(sep.sum())
@@ -385,8 +393,13 @@ class Job:
         gates = {"loss_rel<=1e-3": vals["loss_rel"] <= LOSS_RTOL,
                  "argmax_exact_on_separated_rows": vals["argmax_mismatch_separated_rows"] == 0,
                  "dx_max_abs<=2e-2": vals["dx_max_abs"] <= GRAD_ATOL, "dw_max_abs<=2e-2": vals["dw_max_abs"] <= GRAD_ATOL}
+        if x3:   # the high-precision mode: gradients within 1e-4 (absolute, and relative to their largest element)
+            gates.update({"loss_rel<=2e-5": vals["loss_rel"] <= 2e-5,
+                          "dx_max_abs<=1e-4": vals["dx_max_abs"] <= 1e-4, "dw_max_abs<=1e-4": vals["dw_max_abs"] <= 1e-4,
+                          "dx_max_rel<=1e-4": vals["dx_max_rel"] <= 1e-4, "dw_max_rel<=1e-4": vals["dw_max_rel"] <= 1e-4})
         out = {"vs": "fp32 restatement of arcface.py:45-63 + CrossEntropyLoss + backward on the same GPU, identical "
                      "inputs (oracle/arcface_torch_chunked.py); max over ranks",
+               "precision": cfg.get("precision", "bf16"), "argmax_gap_floor": 2.0 * noise,
                "loss": got_loss, "loss_ref": ref_loss, "separated_rows_per_rank_min": n_sep}
         out.update(vals)
         out["argmax_mismatch_separated_rows"] = int(out["argmax_mismatch_separated_rows"])
@@ -663,7 +676,7 @@ def main():
                      "value": c["B"] / (tt["ms_per_step"] * 1e-3), "unit": "samples/s", "steps": 10, "warmup": 6,
                      "clocks": tt["clocks"], "roofline_step": j.roofline_step(tt["ms_per_step"], peaks, tt["clocks"]),
                      "exchange": j.exchange(), "k3_launches": ops.backward_launches(c["B"], c["D"], j.c_hi - j.c_lo),
-                     "workload": c["what"]}
+                     "precision": c.get("precision", "bf16"), "workload": c["what"]}
                 if not args.no_parity:
                     r["parity"] = j.parity()
                 extra[name] = r
