@@ -144,8 +144,12 @@ class ShardedArcMarginProduct(nn.Module):
         x = x.to(torch.float32).contiguous()
         b_loc = x.shape[0]
         x_all = _all_gather_rows(x, group)
-        xhat, _, _ = K.normalize_cast(x_all)
-        what, _, _ = K.normalize_cast(self.weight.detach().contiguous())
+        if engine.precision_code(getattr(self, "precision", "bf16")):
+            xhat, _, _ = K.normalize_cast3(x_all, 0)
+            what, _, _ = K.normalize_cast3(self.weight.detach().contiguous(), 1)
+        else:
+            xhat, _, _ = K.normalize_cast(x_all)
+            what, _, _ = K.normalize_cast(self.weight.detach().contiguous())
         v, i = K.cosine_topk(xhat, what, k, 1.0, self.class_lo)            # [B, k] over the local classes
         B = x_all.shape[0]
         vs = _all_gather_rows(v.unsqueeze(0), group)                       # [R, B, k]
