@@ -175,7 +175,10 @@ __device__ __forceinline__ float4 ldg_stream4_hint(const float* p, uint64_t pol)
 
 template <bool NORM>
 struct FwdStatsPairT : pr::PairDefaults {
-    static constexpr int STAGES = 4;
+#ifndef AB_FWD_STAGES
+#define AB_FWD_STAGES 4
+#endif
+    static constexpr int STAGES = AB_FWD_STAGES;
     static constexpr bool STAGING = false;
     static constexpr bool RES_A = true;
     static constexpr int NROW = 2 * pr::ROWS;
@@ -369,15 +372,21 @@ struct FwdStatsPairT : pr::PairDefaults {
 
     __device__ static void aux(const Params& p, int u, int nu, int lane) {
         if constexpr (NORM) {
+#ifndef AB_FWD_LEAN
             if (p.D > 512) {
                 aux_row1024(p, u, nu, lane);
                 return;
             }
+#endif
             const int64_t n_runs = (static_cast<int64_t>(p.C) + RUN - 1) / RUN;
             if (u >= n_runs) return;
             const int64_t n_pairs = ((n_runs - u + nu - 1) / nu) * PPR;  // of this warp (even)
             auto row_of = [&](int64_t j) { return (u + (j / PPR) * nu) * RUN + (j % PPR) * 2; };
+#ifdef AB_FWD_LEAN
+            const uint64_t pol = 0ull;
+#else
             const uint64_t pol = p.evict_first ? l2_policy_evict_first() : 0ull;
+#endif
             auto fetch = [&](int64_t j, RowPair& rp) {
                 if (j < n_pairs) load_pair(p, row_of(j), lane, rp, pol);
             };
@@ -396,7 +405,11 @@ struct FwdStatsPairT : pr::PairDefaults {
             };
             // DRAM -> L2 prefetch of the pair `pf_dist` ahead: the bytes in flight beyond the two register pairs
             // live in L2, so the loads below see L2 latency instead of queued-DRAM latency
+#ifdef AB_FWD_LEAN
+            const int pfd = 0;
+#else
             const int pfd = p.pf_dist;
+#endif
             const uint32_t pair_bytes = static_cast<uint32_t>(2 * p.D * sizeof(float));
             auto ahead = [&](int64_t j) {
                 if (pfd > 0 && lane == 0 && j + pfd < n_pairs) {
