@@ -1,5 +1,7 @@
 """Times the backward (K3) alone with CUDA events under several ARCFACE_B200_BWD_* settings."""
+import os
 import math, os, sys
+os.environ.setdefault("ARCFACE_B200_DIAG", "1")   # the ARCFACE_B200_* knobs exist in the diagnostic library only
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch

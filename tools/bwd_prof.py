@@ -1,5 +1,7 @@
 """Runs the single-launch backward once per given role split with ARCFACE_B200_BWD_PROF=1 (wait-time report on stderr)."""
+import os
 import math, os, sys
+os.environ.setdefault("ARCFACE_B200_DIAG", "1")   # the ARCFACE_B200_* knobs exist in the diagnostic library only
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch

@@ -1,5 +1,7 @@
 """Times the fused forward (K1(w)+K2) alone with CUDA events; ARCFACE_B200_FWD_DEBUG selects measurement modes."""
+import os
 import math, os, sys
+os.environ.setdefault("ARCFACE_B200_DIAG", "1")   # the ARCFACE_B200_* knobs exist in the diagnostic library only
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch

@@ -3,7 +3,9 @@ is limited by the 1000 W cap (time = energy / power) or by stalls.
 
     python tools/power_probe.py            # fused forward, helpers only, split GEMM, backward, cuBLAS bf16 GEMM
 """
+import os
 import math, os, sys, threading, time
+os.environ.setdefault("ARCFACE_B200_DIAG", "1")   # the ARCFACE_B200_* knobs exist in the diagnostic library only
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import pynvml
