@@ -159,3 +159,36 @@ def test_stand_in_shard_merge_equals_global_statistics():
                                                   torch.stack([t[3] for t in rows]), torch.stack([t[2] for t in rows]), yt)
         assert abs(float(loss) - onp.cross_entropy(z, y)) <= 1e-5
         np.testing.assert_array_equal(arg.numpy(), onp.argmax(z))
+
+
+def test_bench_weights_do_not_depend_on_the_rank_count():
+    """bench.py's synthetic weight matrix is a function of (seed, class id) only: any rank's shard is a slice of the
+    matrix a single GPU generates, which is what lets the driver compare losses and parity across N = 1, 2, 4, 8."""
+    import bench
+    import multimodalsimilar_b200 as mm
+
+    C, D = 3 * bench.WEIGHT_BLOCK + 1234, 16
+    cpu = torch.device("cpu")
+    full = bench.class_weights(torch, C, D, 0, C, cpu)
+    assert full.shape == (C, D)
+    assert float(full.abs().max()) <= (6.0 / (C + D)) ** 0.5 * (1 + 1e-6)
+    for world in (2, 3, 8):
+        for rank in range(world):
+            lo, hi = mm.shard_range(C, world, rank)
+            assert torch.equal(bench.class_weights(torch, C, D, lo, hi, cpu), full[lo:hi])
+    # ragged slices that start and end inside a block
+    assert torch.equal(bench.class_weights(torch, C, D, 70000, 140001, cpu), full[70000:140001])
+
+
+def test_bench_config_table_matches_baseline():
+    """The configurations bench.py measures are BASELINE.json's."""
+    import bench
+
+    assert bench.CONFIGS["ns"] == dict(bench.CONFIGS["ns"], B=512, D=512, C=1000000, s=64.0, m=0.5)
+    assert (bench.CONFIGS["c1"]["B"], bench.CONFIGS["c1"]["D"], bench.CONFIGS["c1"]["C"], bench.CONFIGS["c1"]["s"]) == (64, 512, 1000, 30.0)
+    assert (bench.CONFIGS["c2"]["B"], bench.CONFIGS["c2"]["D"], bench.CONFIGS["c2"]["C"]) == (256, 1792, 100000)
+    assert (bench.CONFIGS["c3"]["B"], bench.CONFIGS["c3"]["D"], bench.CONFIGS["c3"]["C"]) == (512, 1024, 1000000)
+    assert (bench.CONFIGS["c4"]["B"], bench.CONFIGS["c4"]["D"], bench.CONFIGS["c4"]["C"]) == (512, 2816, 1000000)
+    assert [bench.CONFIGS[k]["C"] for k in ("c5_100k", "c5_1m", "c5_10m")] == [100000, 1000000, 10000000]
+    assert all(bench.CONFIGS[k]["B"] == 1024 and bench.CONFIGS[k]["D"] == 512 for k in ("c5_100k", "c5_1m", "c5_10m"))
+    assert set(bench.EXTRA_CONFIGS) <= set(bench.CONFIGS)
