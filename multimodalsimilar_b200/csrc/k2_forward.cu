@@ -424,11 +424,34 @@ struct FwdStatsPairT : pr::PairDefaults {
                 }
             if constexpr (WIDE) {
                 RowPair a;
+#ifdef AB_FWD_LATEPUB
+                // the fence + counter update that ends a run is issued AFTER the next pair's loads: its latency
+                // (every store of the run acknowledged) overlaps the loads' instead of preceding them
+                int64_t pending = -1;
+                auto publish = [&](int64_t jl) {
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int64_t r0 = row_of(jl) - (RUN - 2);
+                        const int rows = static_cast<int>(min(static_cast<int64_t>(RUN), p.C - r0));
+                        if (rows > 0) red_relaxed_gpu_add(p.ready + (r0 / pr::ROWS), rows);
+                    }
+                };
+                for (int64_t j = 0; j < n_pairs; ++j) {
+                    fetch(j, a);
+                    ahead(j);
+                    if (pending >= 0) { publish(pending); pending = -1; }
+                    store_pair(p, row_of(j), lane, a);
+                    if (j % PPR == PPR - 1) pending = j;
+                }
+                if (pending >= 0) publish(pending);
+#else
                 for (int64_t j = 0; j < n_pairs; ++j) {
                     fetch(j, a);
                     ahead(j);
                     retire(j, a);
                 }
+#endif
                 return;
             }
             RowPair a, b;

@@ -33,6 +33,11 @@ __device__ __forceinline__ uint4 ldg_nc_u4(const void* p) {
     asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
+__device__ __forceinline__ void ldg_nc_u8(const void* p, uint4& a, uint4& b) {  // 32-byte aligned
+    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
+}
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
@@ -891,6 +896,7 @@ struct BwdDWpT : pr::PairDefaults {
         float inwn;
         const volatile int* acquired;  // FUSED: see EXTRA_BYTES
         bool have_scalars;
+        bool w256;  // the rows of what are 32-byte aligned: the correction term's weights are fetched with 256-bit loads
         uint64_t pol;
         unsigned long long* prof;  // measurements only: [0] scalars [1] tmem load [2] math [3] staging wait [4] store issue
         unsigned long long pacc[5];
@@ -901,6 +907,7 @@ struct BwdDWpT : pr::PairDefaults {
               have_scalars(false), prof(c.prof) {
             for (int k = 0; k < 5; ++k) pacc[k] = 0;
             pol = p.evict_first ? l2_policy_evict_first() : 0ull;
+            w256 = ((reinterpret_cast<uintptr_t>(p.what) | static_cast<uintptr_t>(p.ldw * 2)) & 31u) == 0;
         }
         __device__ __forceinline__ int class_of(int i) const {
             return p.c_begin + i * NCOL + rank * pr::ROWS + quad * 32 + lane;
@@ -910,11 +917,32 @@ struct BwdDWpT : pr::PairDefaults {
             const int c = class_of(i);
             const bool cvalid = c < p.C;
             const __nv_bfloat16* wrow = p.what + static_cast<int64_t>(cvalid ? c : 0) * p.ldw;
+#ifdef AB_EXP_DW_NOW   // timing experiment only (wrong gradients): no loads for the correction term
+#pragma unroll
+            for (int g = 0; g < 4; ++g) w[g] = make_uint4(0, 0, 0, static_cast<uint32_t>(reinterpret_cast<uintptr_t>(wrow)) & 1u);
+#else
+#ifndef AB_DW_NO_W256
+            // one full 32-byte sector per lane and instruction (LDG.256) instead of two half sectors: a lane's row is 1 KB
+            // away from its neighbour's, so every 16-byte load costs the L1 a whole sector request
+            if (w256) {
+#pragma unroll
+                for (int g = 0; g < 4; g += 2) {
+                    const int d = d0 + grp * 32 + g * 8;
+                    if (cvalid && d + 16 <= p.D) ldg_nc_u8(wrow + d, w[g], w[g + 1]);
+                    else {
+                        w[g] = (cvalid && d < p.D) ? ldg_nc_u4(wrow + d) : make_uint4(0, 0, 0, 0);
+                        w[g + 1] = (cvalid && d + 8 < p.D) ? ldg_nc_u4(wrow + d + 8) : make_uint4(0, 0, 0, 0);
+                    }
+                }
+                return;
+            }
+#endif
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 const int d = d0 + grp * 32 + g * 8;
                 w[g] = (cvalid && d < p.D) ? ldg_nc_u4(wrow + d) : make_uint4(0, 0, 0, 0);
             }
+#endif
         }
         __device__ __forceinline__ void fetch_scalars(int i) {
             const int c = class_of(i);
@@ -963,6 +991,13 @@ struct BwdDWpT : pr::PairDefaults {
                 o[g * 8 + 7] = fmaf(nq, bf16_hi(ww.w), __uint_as_float(v[g * 8 + 7])) * inw;
             }
             const unsigned long long t2 = tick();
+#ifdef AB_EXP_DW_NOSTORE   // timing experiment only (dW is not written): the epilogue without its store path
+            float acc_x = 0.f;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) acc_x += o[k];
+            if (acc_x == 1.2345e-30f) stager.put(0, __float_as_uint(acc_x), 0, 0, 0);
+            const unsigned long long t3 = tick();
+#else
             stager.acquire();  // only now: the previous box has had the tcgen05.ld and the math above to leave
             const unsigned long long t3 = tick();
 #pragma unroll
@@ -970,6 +1005,7 @@ struct BwdDWpT : pr::PairDefaults {
                 stager.put(k, __float_as_uint(o[4 * k]), __float_as_uint(o[4 * k + 1]), __float_as_uint(o[4 * k + 2]),
                            __float_as_uint(o[4 * k + 3]));
             stager.commit(tm_out, dg, crow0, pol);  // rows >= C / columns >= D are clipped by the TMA
+#endif
             if (prof != nullptr) { pacc[1] += t1 - t0; pacc[2] += t2 - t1; pacc[3] += t3 - t2; pacc[4] += tick() - t3; }
         }
         __device__ void tile(int i, int i_next, uint32_t taddr) {
