@@ -61,7 +61,10 @@ CONFIGS = {
 CONFIGS["ns_bf16x3"] = dict(CONFIGS["ns"], precision="bf16x3",
                             what="north-star shape in the high-precision mode (precision='bf16x3': the north star's "
                                  "'1e-4 under a TF32 mode' gates)")
-EXTRA_CONFIGS = ["c2", "c3", "c4", "c5_100k", "c5_1m", "c5_10m", "ns_bf16x3"]
+CONFIGS["c5_10m_pfc10"] = dict(CONFIGS["c5_10m"], sample_rate=0.1, sparse_grad=True,
+                               what="BASELINE config 5 at C=10M with PartialFC-style class sampling (sample_rate=0.1: "
+                                    "the batch's label classes + uniform negatives, 1M rows per step; sparse dW)")
+EXTRA_CONFIGS = ["c2", "c3", "c4", "c5_100k", "c5_1m", "c5_10m", "c5_10m_pfc10", "ns_bf16x3"]
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of the north-star
 # workload on one B200; only meaningful for the single-GPU north-star shape.
 NCU_TRAFFIC = {"fwd": 2.300311e9 + 0.995569e9, "k3": 1.401256e9 + 2.114588e9,
@@ -233,14 +236,16 @@ class Job:
         self.x_host = torch.randn(B, D, generator=gen).pin_memory()
         self.y_host = torch.randint(0, C, (B,), generator=gen).pin_memory()
         prec = cfg.get("precision", "bf16")
+        samp = {"sample_rate": cfg.get("sample_rate", 1.0), "sparse_grad": cfg.get("sparse_grad", False), "sample_seed": 4321}
+        self.sampled = samp["sample_rate"] < 1.0
         if world == 1:
-            head = mm.ArcMarginProduct(D, 8, s=s, m=m, precision=prec)
+            head = mm.ArcMarginProduct(D, 8, s=s, m=m, precision=prec, **samp)
             head.out_feature = C
             self.c_lo, self.c_hi = 0, C
         else:
             # ARCFACE_B200_P2P=0: exchanges through NCCL instead of peer-mapped memory (A/B measurements)
             head = mm.ShardedArcMarginProduct(D, world, s=s, m=m, precision=prec,
-                                              use_p2p=os.environ.get("ARCFACE_B200_P2P", "1") != "0")
+                                              use_p2p=os.environ.get("ARCFACE_B200_P2P", "1") != "0", **samp)
             head.out_feature = C
             head.class_lo, head.class_hi = mm.shard_range(C, world, rank)
             self.c_lo, self.c_hi = head.class_lo, head.class_hi
@@ -324,6 +329,8 @@ class Job:
         cfg = self.cfg
         B, D = cfg["B"], cfg["D"]
         c_loc = self.c_hi - self.c_lo
+        if self.sampled:   # the step's work is the sampled sub-matrix (engine.sample_classes: the size is fixed on the host)
+            c_loc = min(c_loc, max(int(round(cfg["sample_rate"] * c_loc)), min(B, c_loc)))
         flops_alg = 6.0 * B * D * c_loc
         bytes_alg = 8.0 * c_loc * D + 8.0 * B * D + 24.0 * B
         t_hbm = bytes_alg / (peaks["hbm_gbs"] * 1e9)
@@ -352,6 +359,8 @@ class Job:
 
         cfg = self.cfg
         B, D, C, s, m = cfg["B"], cfg["D"], cfg["C"], cfg["s"], cfg["m"]
+        if self.sampled:
+            return self.parity_sampled()
         loss = self.step()
         torch.cuda.synchronize()
         got_loss = float(loss.detach())
@@ -405,6 +414,47 @@ class Job:
         out["argmax_mismatch_separated_rows"] = int(out["argmax_mismatch_separated_rows"])
         out["gates"] = gates
         out["ok"] = all(gates.values())
+        torch.cuda.empty_cache()
+        return out
+
+    def parity_sampled(self):
+        """Class sampling: the step against the fp32 restatement evaluated on the rows the step sampled (one GPU)."""
+        torch = self.torch
+        if self.world > 1:
+            return None   # every rank draws its own sample; the 2-rank case is covered by tests/test_sampling.py
+        from oracle import arcface_torch_chunked as och  # the checker
+
+        cfg = self.cfg
+        B, s, m = cfg["B"], cfg["s"], cfg["m"]
+        loss = self.step()
+        torch.cuda.synchronize()
+        index = self.head.last_sample_index()
+        y_all = self.y_host.to(self.dev)
+        pos = torch.searchsorted(index, y_all)
+        labels_in = bool((index[pos] == y_all).all())
+        ref = och.head_step_chunked(self.x_host.to(self.dev), self.head.weight.detach()[index], pos, s, m, False,
+                                    chunk=32768, dw_range=(0, index.numel()))
+        g = self.head.weight.grad
+        got_dw = g.coalesce().values() if g.is_sparse else g[index]
+        ddx = self.x_dev.grad - ref["dx"]
+        ddw = got_dw - ref["dw"]
+        noise = LOGIT_ATOL * (s / 30.0) * max(1.0, math.sqrt(512.0 / cfg["D"]))
+        sep = ref["top2_gap"] > 2.0 * noise
+        got_arg = torch.searchsorted(index, self.pred)
+        vals = {"loss_rel": abs(float(loss.detach()) - float(ref["loss"])) / max(1.0, abs(float(ref["loss"]))),
+                "dx_max_abs": float(ddx.abs().max()), "dx_rel_fro": float(ddx.norm() / ref["dx"].norm().clamp_min(1e-30)),
+                "dw_max_abs": float(ddw.abs().max()), "dw_rel_fro": float(ddw.norm() / ref["dw"].norm().clamp_min(1e-30)),
+                "argmax_mismatch_separated_rows": int((got_arg[sep] != ref["argmax"][sep]).sum())}
+        gates = {"every_label_in_sample": labels_in, "loss_rel<=1e-3": vals["loss_rel"] <= LOSS_RTOL,
+                 "argmax_exact_on_separated_rows": vals["argmax_mismatch_separated_rows"] == 0,
+                 "dx_max_abs<=2e-2": vals["dx_max_abs"] <= GRAD_ATOL, "dw_max_abs<=2e-2": vals["dw_max_abs"] <= GRAD_ATOL}
+        out = {"vs": "fp32 restatement of arcface.py:45-63 + CrossEntropyLoss + backward on the rows the step sampled "
+                     "(oracle/arcface_torch_chunked.py on weight[index])", "sampled_classes": int(index.numel()),
+               "loss": float(loss.detach()), "loss_ref": float(ref["loss"]), "separated_rows": int(sep.sum())}
+        out.update(vals)
+        out["gates"] = gates
+        out["ok"] = all(gates.values())
+        del ref, ddx, ddw
         torch.cuda.empty_cache()
         return out
 
@@ -655,11 +705,12 @@ def main():
 
     stages = roofline = gpu_ref = cpu_baseline = None
     if world == 1:
-        stages = stage_times(torch, ops, job.head, job.x_host, job.y_host, dev, cfg["s"], cfg["m"], 0, C,
-                             max(5, min(args.steps, 30)))
-        roofline = dominant_kernel_roofline(job, ops, peaks, stages, roof_step["regime"],
-                                            head_name == "ns" and not args.classes)
-        gpu_ref = gpu_reference(job)
+        if not job.sampled:   # (the per-stage breakdown and the dense GPU reference run on every class)
+            stages = stage_times(torch, ops, job.head, job.x_host, job.y_host, dev, cfg["s"], cfg["m"], 0, C,
+                                 max(5, min(args.steps, 30)))
+            roofline = dominant_kernel_roofline(job, ops, peaks, stages, roof_step["regime"],
+                                                head_name == "ns" and not args.classes)
+            gpu_ref = gpu_reference(job)
     job.close()
     del job
 
@@ -676,6 +727,7 @@ def main():
                      "value": c["B"] / (tt["ms_per_step"] * 1e-3), "unit": "samples/s", "steps": 10, "warmup": 6,
                      "clocks": tt["clocks"], "roofline_step": j.roofline_step(tt["ms_per_step"], peaks, tt["clocks"]),
                      "exchange": j.exchange(), "k3_launches": ops.backward_launches(c["B"], c["D"], j.c_hi - j.c_lo),
+                     "sample_rate": c.get("sample_rate", 1.0),
                      "precision": c.get("precision", "bf16"), "workload": c["what"]}
                 if not args.no_parity:
                     r["parity"] = j.parity()

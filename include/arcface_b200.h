@@ -74,6 +74,17 @@ int32_t arcface_b200_normalize_cast(const float* src, int64_t rows, int32_t D, u
 int32_t arcface_b200_normalize_cast3(const float* src, int64_t rows, int32_t D, int32_t order, uint16_t* dst3,
                                      float* inv_norm, uint16_t* dst_t, int64_t ld_t, void* stream);
 
+/* Class sampling (PartialFC-style; SURVEY.md section 8f row N4 -- the reference always trains all classes, the rule
+ * restated in oracle/arcface_numpy.py:partial_fc_sample is insightface's partial_fc_v2 `sample`).
+ * normalize_cast_gather: K1 over the sampled rows, dst[r, :] = bf16 normalise of src[index[r], :] (index sorted or not,
+ * values in [0, src_rows)); the forward / backward kernels then run on the `rows`-class sub-matrix.
+ * scatter_rows: dst[index[r], :] = src[r, :] -- the sampled rows' gradient back into the full-size dW (the caller
+ * zeroes the rest). */
+int32_t arcface_b200_normalize_cast_gather(const float* src, int64_t src_rows, const int64_t* index, int64_t rows,
+                                           int32_t D, uint16_t* dst, float* inv_norm, void* stream);
+int32_t arcface_b200_scatter_rows(const float* src, const int64_t* index, int64_t rows, int32_t D, float* dst,
+                                  int64_t dst_rows, void* stream);
+
 /* Label column in fp32 + margin (arcface.py:49-55 restricted to the label column, the only place the
  * reference's one-hot blend at :58-60 uses phi).  For every row b whose label falls in this shard:
  *   t = <x_b, w_y> * inv_nx[b] * inv_nw[y];  sine = sqrt(max(0, 1 - t^2));  phi = t cos_m - sine sin_m

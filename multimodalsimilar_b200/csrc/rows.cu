@@ -29,11 +29,14 @@ template <int NCH>
 __global__ void __launch_bounds__(256) normalize_cast_kernel(const float* __restrict__ src, int64_t rows, int D,
                                                              __nv_bfloat16* __restrict__ dst,
                                                              float* __restrict__ inv_norm,
-                                                             __nv_bfloat16* __restrict__ dst_t, int64_t ld_t) {
+                                                             __nv_bfloat16* __restrict__ dst_t, int64_t ld_t,
+                                                             const int64_t* __restrict__ index = nullptr) {
     const int lane = threadIdx.x & 31;
     const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
-    const float* rp = src + row * D;
+    // index != nullptr: output row `row` is source row index[row] (class sampling: the sampled rows are normalised
+    // straight out of the full weight matrix, no fp32 copy of the sub-matrix is ever made)
+    const float* rp = src + (index != nullptr ? index[row] : row) * D;
     float4 v[NCH][2];
     float ss = 0.f;
 #pragma unroll
@@ -79,11 +82,12 @@ __global__ void __launch_bounds__(256) normalize_cast_kernel(const float* __rest
 __global__ void __launch_bounds__(256) normalize_cast_generic_kernel(const float* __restrict__ src, int64_t rows, int D,
                                                                      __nv_bfloat16* __restrict__ dst,
                                                                      float* __restrict__ inv_norm,
-                                                                     __nv_bfloat16* __restrict__ dst_t, int64_t ld_t) {
+                                                                     __nv_bfloat16* __restrict__ dst_t, int64_t ld_t,
+                                                                     const int64_t* __restrict__ index = nullptr) {
     const int lane = threadIdx.x & 31;
     const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
-    const float* rp = src + row * D;
+    const float* rp = src + (index != nullptr ? index[row] : row) * D;
     float ss = 0.f;
     for (int d = lane * 4; d < D; d += 128) {
         const float4 a = *reinterpret_cast<const float4*>(rp + d);
@@ -675,6 +679,64 @@ extern "C" int32_t arcface_b200_normalize_cast(const float* src, int64_t rows, i
     else if (nch <= 8) normalize_cast_kernel<8><<<grid, block, 0, st>>>(src, rows, D, d, inv_norm, dt, ld_t);
     else if (nch <= 12) normalize_cast_kernel<12><<<grid, block, 0, st>>>(src, rows, D, d, inv_norm, dt, ld_t);
     else normalize_cast_generic_kernel<<<grid, block, 0, st>>>(src, rows, D, d, inv_norm, dt, ld_t);
+    AB_CHECK_CUDA(cudaGetLastError());
+    return ARCFACE_B200_OK;
+}
+
+// Class sampling (PartialFC-style): K1 over the sampled rows of the full weight matrix.
+extern "C" int32_t arcface_b200_normalize_cast_gather(const float* src, int64_t src_rows, const int64_t* index,
+                                                      int64_t rows, int32_t D, uint16_t* dst, float* inv_norm,
+                                                      void* stream) {
+    if (int32_t rc = check_arch()) return rc;
+    AB_REQUIRE(src && index && dst && inv_norm, ARCFACE_B200_E_ARG, "normalize_cast_gather: null pointer");
+    AB_REQUIRE(rows >= 0 && src_rows >= 0 && D >= 8 && D % 8 == 0, ARCFACE_B200_E_SHAPE,
+               "normalize_cast_gather: D=%d must be a positive multiple of 8", D);
+    AB_REQUIRE(aligned16(src) && aligned16(dst) && (reinterpret_cast<uintptr_t>(index) & 7u) == 0, ARCFACE_B200_E_LAYOUT,
+               "normalize_cast_gather: src / dst must be 16-byte aligned, index 8-byte aligned");
+    if (rows == 0) return ARCFACE_B200_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int wpb = 8;
+    const int64_t nblk = (rows + wpb - 1) / wpb;
+    AB_REQUIRE(nblk < (1ll << 31), ARCFACE_B200_E_SHAPE, "normalize_cast_gather: too many rows");
+    dim3 grid(static_cast<unsigned>(nblk)), block(wpb * 32);
+    __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst);
+    const int nch = (D + 255) / 256;
+    if (nch <= 1) normalize_cast_kernel<1><<<grid, block, 0, st>>>(src, rows, D, d, inv_norm, nullptr, 0, index);
+    else if (nch <= 2) normalize_cast_kernel<2><<<grid, block, 0, st>>>(src, rows, D, d, inv_norm, nullptr, 0, index);
+    else if (nch <= 4) normalize_cast_kernel<4><<<grid, block, 0, st>>>(src, rows, D, d, inv_norm, nullptr, 0, index);
+    else if (nch <= 8) normalize_cast_kernel<8><<<grid, block, 0, st>>>(src, rows, D, d, inv_norm, nullptr, 0, index);
+    else if (nch <= 12) normalize_cast_kernel<12><<<grid, block, 0, st>>>(src, rows, D, d, inv_norm, nullptr, 0, index);
+    else normalize_cast_generic_kernel<<<grid, block, 0, st>>>(src, rows, D, d, inv_norm, nullptr, 0, index);
+    AB_CHECK_CUDA(cudaGetLastError());
+    return ARCFACE_B200_OK;
+}
+
+// dst[index[r]] = src[r] for r < rows (fp32 rows of D floats, D % 4 == 0): the gradient of the sampled class rows back
+// into the full-size gradient.  One warp per row, 128-bit copies.
+__global__ void __launch_bounds__(256) scatter_rows_kernel(const float4* __restrict__ src, const int64_t* __restrict__ index,
+                                                           int64_t rows, int d4, float4* __restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float4* s = src + row * d4;
+    float4* d = dst + index[row] * d4;
+    for (int i = lane; i < d4; i += 32) d[i] = ldg_stream(s + i);
+}
+
+extern "C" int32_t arcface_b200_scatter_rows(const float* src, const int64_t* index, int64_t rows, int32_t D, float* dst,
+                                             int64_t dst_rows, void* stream) {
+    if (int32_t rc = check_arch()) return rc;
+    AB_REQUIRE(src && index && dst, ARCFACE_B200_E_ARG, "scatter_rows: null pointer");
+    AB_REQUIRE(rows >= 0 && rows <= dst_rows && D >= 4 && D % 4 == 0, ARCFACE_B200_E_SHAPE,
+               "scatter_rows: %lld rows into %lld, D=%d (multiple of 4)", static_cast<long long>(rows),
+               static_cast<long long>(dst_rows), D);
+    AB_REQUIRE(aligned16(src) && aligned16(dst) && (reinterpret_cast<uintptr_t>(index) & 7u) == 0, ARCFACE_B200_E_LAYOUT,
+               "scatter_rows: src / dst must be 16-byte aligned, index 8-byte aligned");
+    if (rows == 0) return ARCFACE_B200_OK;
+    const int64_t nblk = (rows + 7) / 8;
+    AB_REQUIRE(nblk < (1ll << 31), ARCFACE_B200_E_SHAPE, "scatter_rows: too many rows");
+    scatter_rows_kernel<<<static_cast<unsigned>(nblk), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(src), index, rows, D / 4, reinterpret_cast<float4*>(dst));
     AB_CHECK_CUDA(cudaGetLastError());
     return ARCFACE_B200_OK;
 }

@@ -63,6 +63,8 @@ class FwdState:
     dphi: torch.Tensor
     label_local: torch.Tensor
     argmax_all: Any = None   # argmax of every row of the global batch (argmax_local is a view of it)
+    sample: Any = None       # class sampling: int64 [S] sorted local class ids the step ran on (what / inv_nw are theirs)
+    c_local: int = 0         # class rows of the full local weight (the shape of dW)
 
 
 class LabelGuard:
@@ -161,10 +163,42 @@ def reduce_scatter_rows(full: torch.Tensor, group) -> torch.Tensor:
     return out
 
 
-def _rows(K, xhat, w, label_local, cfg, w_cache, out=None):
+def sample_classes(label_local: torch.Tensor, c_local: int, num_sample: int, generator=None) -> torch.Tensor:
+    """Sorted int64 [S] class ids of this step's sub-matrix: every class that is a label of the batch plus uniformly
+    drawn negatives.  The rule of PartialFC (insightface recognition/arcface_torch/partial_fc_v2.py `sample`: random
+    scores, positives forced to the top, top-k, sort; restated in oracle/arcface_numpy.py:partial_fc_sample), with
+    S = max(num_sample, min(B, c_local)) fixed on the host, so that the positives always fit and no device value has to
+    be read back (PartialFC falls back to "positives only" when they outnumber num_sample).
+    `label_local`: int [B], label - class_lo or -1 for labels of other ranks."""
+    B = label_local.numel()
+    S = min(c_local, max(int(num_sample), min(B, c_local)))
+    dev = label_local.device
+    perm = torch.rand(c_local + 1, device=dev, generator=generator)   # slot c_local swallows the rows without a label here
+    idx = label_local.to(torch.int64)
+    idx = torch.where(idx >= 0, idx, torch.full_like(idx, c_local))
+    perm.scatter_(0, idx, 2.0)
+    return torch.topk(perm[:c_local], S).indices.sort().values
+
+
+def remap_labels(label_local: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
+    """Position of every local label inside the sorted sample `index` (int32 [B]; -1 stays -1)."""
+    lab = label_local.to(torch.int64)
+    pos = torch.searchsorted(index, lab.clamp(min=0))
+    return torch.where(lab >= 0, pos, torch.full_like(pos, -1)).to(torch.int32)
+
+
+def _rows(K, xhat, w, label_local, cfg, w_cache, out=None, sample=None):
     """(what, inv_nw, max, sum, arg): K1 (w) fused into K2, or K2 alone on the rows a fused optimiser step left
-    behind (`w_cache` = (what, inv_nw), optim.FusedHeadAdamW)."""
+    behind (`w_cache` = (what, inv_nw), optim.FusedHeadAdamW).  `sample`: K1 gathers the sampled rows, K2 runs on
+    them (`label_local` already remapped), the argmax comes back as a global class id."""
     kw = {} if out is None else {"out": out}
+    if sample is not None:
+        if cfg.prec:
+            raise NotImplementedError("class sampling runs in precision='bf16' only")
+        what, inv_nw = K.normalize_cast_gather(w, sample)
+        rmax, rsum, rarg = K.forward_rows(xhat, what, label_local, cfg.s, 0, **kw)
+        rarg.copy_(sample[rarg] + cfg.class_lo)   # sampled position -> global class id (B values)
+        return what, inv_nw, rmax, rsum, rarg
     if cfg.prec:   # bf16x3: K1 writes the three-part rows, K2 contracts over 3 D
         what, inv_nw, _ = K.normalize_cast3(w, 1)
         return (what, inv_nw) + tuple(K.forward_rows(xhat, what, label_local, cfg.s, cfg.class_lo, **kw))
@@ -175,7 +209,7 @@ def _rows(K, xhat, w, label_local, cfg, w_cache, out=None):
 
 
 def forward_eager(K, group, x_local, w, y_local, cfg: StepConfig, packed_xy=None, w_cache=None, peer=None,
-                  guard=None) -> FwdState:
+                  guard=None, num_sample=0, generator=None) -> FwdState:
     """K1 (x) -> label margin -> K1 (w) + K2 -> combine -> [exchange] -> finalize.  arcface.py:45-63 + the mean
     CrossEntropyLoss + argmax of the call sites, for the global batch against the local class rows."""
     R, rank = _world(group), _rank(group)
@@ -192,7 +226,8 @@ def forward_eager(K, group, x_local, w, y_local, cfg: StepConfig, packed_xy=None
         buf, v_max, v_sum, v_z, v_arg = K.packed_stats(B, x_all.device)
         lm = K.label_margin(x_all, w, inv_nx, None, y_all, cfg.class_lo, cfg.c_total, cfg.s, cfg.m, cfg.easy_margin,
                             z_out=v_z, **gk)
-        what, inv_nw, _, _, _ = _rows(K, xhat, w, lm.label_local, cfg, w_cache, out=(v_max, v_sum, v_arg))
+        sample, label_k = _sample_for(lm.label_local, w.shape[0], num_sample, generator)
+        what, inv_nw, _, _, _ = _rows(K, xhat, w, label_k, cfg, w_cache, out=(v_max, v_sum, v_arg), sample=sample)
         if peer is not None and buf.numel() % 16 == 0:
             allp = peer.all_gather_bytes(1, buf)
         else:
@@ -200,17 +235,27 @@ def forward_eager(K, group, x_local, w, y_local, cfg: StepConfig, packed_xy=None
         lse, argmax, _z, omp, loss = K.finalize_rows_packed(allp, y_all)
     else:
         lm = K.label_margin(x_all, w, inv_nx, None, y_all, cfg.class_lo, cfg.c_total, cfg.s, cfg.m, cfg.easy_margin, **gk)
-        what, inv_nw, rmax, rsum, rarg = _rows(K, xhat, w, lm.label_local, cfg, w_cache)
+        sample, label_k = _sample_for(lm.label_local, w.shape[0], num_sample, generator)
+        what, inv_nw, rmax, rsum, rarg = _rows(K, xhat, w, label_k, cfg, w_cache, sample=sample)
         rows_max, rows_sum, rows_z, rows_arg = exchange_rows(rmax, rsum, lm.z_label, rarg, group)
         lse, argmax, _z, omp, loss = K.finalize_rows(rows_max, rows_sum, rows_arg, rows_z, y_all)
     argmax_local = argmax if R == 1 else argmax[rank * b_loc:(rank + 1) * b_loc]
-    st = FwdState(loss, argmax_local, lm.bad_flag, B, inv_nx, xhat, xhat_t, what, inv_nw, lse, omp, lm.dphi,
-                  lm.label_local)
+    st = FwdState(loss, argmax_local, lm.bad_flag, B, inv_nx, xhat, xhat_t, what, inv_nw, lse, omp, lm.dphi, label_k)
     st.argmax_all = argmax   # (with `loss`: one packed buffer, ops.packed_outputs)
+    st.sample, st.c_local = sample, w.shape[0]
     return st
 
 
-def backward_eager(K, group, x_local, st: FwdState, grad_loss, cfg: StepConfig, need_dx: bool = True, peer=None):
+def _sample_for(label_local, c_local, num_sample, generator):
+    """(sample index or None, the labels the GEMM kernels see)."""
+    if not num_sample or num_sample >= c_local:
+        return None, label_local
+    sample = sample_classes(label_local, c_local, num_sample, generator)
+    return sample, remap_labels(label_local, sample)
+
+
+def backward_eager(K, group, x_local, st: FwdState, grad_loss, cfg: StepConfig, need_dx: bool = True, peer=None,
+                   sparse_dw: bool = False):
     """K3 -> [reduce-scatter] -> normalise backward.  Returns (dx for the local rows or None, dW of the local
     class rows)."""
     R, rank = _world(group), _rank(group)
@@ -219,6 +264,13 @@ def backward_eager(K, group, x_local, st: FwdState, grad_loss, cfg: StepConfig, 
     kw = {"prec": cfg.prec} if cfg.prec else {}
     dxhat_part, dw = K.backward(st.xhat, st.xhat_t, st.what, st.inv_nw, st.lse, st.omp, st.dphi, st.label_local,
                                 cfg.s, 1.0 / st.B, grad_loss_dev=g, **kw)
+    if st.sample is not None:
+        # class sampling: the rows that were not drawn took no part in the softmax -- their gradient is exactly zero
+        if sparse_dw:
+            dw = torch.sparse_coo_tensor(st.sample.view(1, -1), dw, (st.c_local, dw.shape[1]), check_invariants=False,
+                                         is_coalesced=True)   # the sample is sorted and free of duplicates
+        else:
+            dw = K.scatter_rows(dw, st.sample, torch.zeros((st.c_local, dw.shape[1]), dtype=dw.dtype, device=dw.device))
     dx = None
     if need_dx:
         inv_loc = st.inv_nx if R == 1 else st.inv_nx[rank * b_loc:(rank + 1) * b_loc].contiguous()
@@ -349,8 +401,12 @@ class ArcFaceCEFunction(torch.autograd.Function):
     `cfg` a StepConfig."""
 
     @staticmethod
-    def forward(ctx, x, w, label, K, group, cfg, validate_labels, w_cache=None, peer=None, guard=None):
-        st = forward_eager(K, group, x, w, label, cfg, None, w_cache, peer, None if validate_labels else guard)
+    def forward(ctx, x, w, label, K, group, cfg, validate_labels, w_cache=None, peer=None, guard=None, sampling=None):
+        num_sample, generator, sparse_dw, owner = (tuple(sampling) + (None,))[:4] if sampling is not None else (0, None, False, None)
+        st = forward_eager(K, group, x, w, label, cfg, None, w_cache, peer, None if validate_labels else guard,
+                           num_sample, generator)
+        if owner is not None and owner() is not None and st.sample is not None:
+            _LAST_SAMPLE[owner()] = st.sample
         if validate_labels:
             if int(st.bad_flag.item()) != 0:
                 raise IndexError("ArcMarginProduct: a label is outside [0, %d)" % cfg.c_total)
@@ -358,22 +414,23 @@ class ArcFaceCEFunction(torch.autograd.Function):
             guard.mark()
         ctx.save_for_backward(x, st.inv_nx, st.xhat, st.xhat_t, st.what, st.inv_nw, st.lse, st.omp, st.dphi,
                               st.label_local)
-        ctx.meta = (K, group, cfg, st.B, peer)
+        ctx.meta = (K, group, cfg, st.B, peer, st.sample, st.c_local, sparse_dw)
         ctx.mark_non_differentiable(st.argmax_local)
         return st.loss, st.argmax_local
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_argmax):
         x, inv_nx, xhat, xhat_t, what, inv_nw, lse, omp, dphi, label_local = ctx.saved_tensors
-        K, group, cfg, B, peer = ctx.meta
+        K, group, cfg, B, peer, sample, c_local, sparse_dw = ctx.meta
         st = FwdState(None, None, None, B, inv_nx, xhat, xhat_t, what, inv_nw, lse, omp, dphi, label_local)
+        st.sample, st.c_local = sample, c_local
         if peer is not None and not ctx.needs_input_grad[0]:
             # the exchange is a rendezvous of all ranks: it cannot be skipped by one of them
-            dx, dw = backward_eager(K, group, x, st, grad_loss, cfg, True, peer)
+            dx, dw = backward_eager(K, group, x, st, grad_loss, cfg, True, peer, sparse_dw)
             dx = None
         else:
-            dx, dw = backward_eager(K, group, x, st, grad_loss, cfg, ctx.needs_input_grad[0], peer)
-        return dx, (dw if ctx.needs_input_grad[1] else None), None, None, None, None, None, None, None, None
+            dx, dw = backward_eager(K, group, x, st, grad_loss, cfg, ctx.needs_input_grad[0], peer, sparse_dw)
+        return dx, (dw if ctx.needs_input_grad[1] else None), None, None, None, None, None, None, None, None, None
 
 
 _EagerCE = ArcFaceCEFunction
@@ -424,6 +481,36 @@ def _peer_for(head, group, x):
 ENGAGE_AFTER = 2  # eager calls with an unchanged signature before a graph is captured
 
 
+# head -> torch.Generator of its class sampling (created from head.sample_seed on first use)
+_SAMPLERS: "weakref.WeakKeyDictionary[Any, Any]" = weakref.WeakKeyDictionary()
+
+
+def _sampling_for(head, c_local: int, device):
+    """(num_sample, generator, sparse_grad) when the head samples classes in this call, else None.  Sampling applies in
+    training mode only (`head.training`), like PartialFC; evaluation always sees every class."""
+    rate = float(getattr(head, "sample_rate", 1.0))
+    if rate >= 1.0 or not getattr(head, "training", True) or not torch.is_grad_enabled():
+        return None
+    if not rate > 0.0:
+        raise ValueError("sample_rate must be in (0, 1], got %r" % rate)
+    num = max(1, int(round(rate * c_local)))
+    gen = _SAMPLERS.get(head)
+    seed = getattr(head, "sample_seed", None)
+    if gen is None and seed is not None:
+        gen = _SAMPLERS[head] = torch.Generator(device=device)
+        gen.manual_seed(int(seed))
+    return num, gen, bool(getattr(head, "sparse_grad", False)), weakref.ref(head)
+
+
+# head -> sorted int64 [S] local class ids its most recent training step ran on (PartialFC calls this `weight_index`)
+_LAST_SAMPLE: "weakref.WeakKeyDictionary[Any, torch.Tensor]" = weakref.WeakKeyDictionary()
+
+
+def last_sample(head):
+    """The class sample of `head`'s most recent sampled step (sorted local class ids), or None."""
+    return _LAST_SAMPLE.get(head)
+
+
 def run_step(head, K, group, x, w, label, cfg: StepConfig, validate_labels: bool):
     """loss, argmax = one forward of `head` (autograd-connected).  Graph replay when `head.use_cuda_graph` and the
     signature has repeated; the eager kernel sequence otherwise."""
@@ -439,6 +526,10 @@ def run_step(head, K, group, x, w, label, cfg: StepConfig, validate_labels: bool
         if guard is None:
             guard = _GUARDS[head] = LabelGuard()
         guard.check(cfg.c_total)   # raises for a bad label of the previous step
+    sampling = _sampling_for(head, w.shape[0], x.device)
+    if sampling is not None:
+        # a fresh sample every step (torch RNG + top-k): eager launches; the weight cache covers all rows, not the sample
+        return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels, None, peer, guard, sampling)
     use_graph = bool(getattr(head, "use_cuda_graph", False)) and x.is_cuda and not validate_labels
     if not use_graph:
         return _EagerCE.apply(x, w, label, K, group, cfg, validate_labels, w_cache, peer, guard)

@@ -142,9 +142,13 @@ class ArcMarginProduct(nn.Module):
     validate_labels = False
     use_cuda_graph = True
     precision = "bf16"
+    sample_rate = 1.0
+    sample_seed = None
+    sparse_grad = False
 
     def __init__(self, in_feature=128, out_feature=10575, s=64.0, m=0.40, easy_margin=False, *,
-                 in_features=None, out_features=None, validate_labels=False, use_cuda_graph=True, precision="bf16"):
+                 in_features=None, out_features=None, validate_labels=False, use_cuda_graph=True, precision="bf16",
+                 sample_rate=1.0, sample_seed=None, sparse_grad=False):
         super().__init__()
         if in_features is not None:
             in_feature = in_features
@@ -163,6 +167,15 @@ class ArcMarginProduct(nn.Module):
         # tensor-core products per cosine -- cosines within 1e-5 of the reference's fp32 head, ~3x the GEMM work)
         engine.precision_code(precision)
         self.precision = precision
+        # PartialFC-style class sampling (the reference always trains every class): in training
+        # mode each step runs on the batch's label classes plus uniformly drawn negatives, round(sample_rate * C) rows
+        # in all -- GEMM work and weight traffic scale with the rate; the rows that were not drawn get a zero gradient
+        # (dense `weight.grad` by default, a torch.sparse_coo gradient with sparse_grad=True).  Eval paths see all classes.
+        if not 0.0 < float(sample_rate) <= 1.0:
+            raise ValueError("sample_rate must be in (0, 1], got %r" % (sample_rate,))
+        self.sample_rate = float(sample_rate)
+        self.sample_seed = sample_seed
+        self.sparse_grad = bool(sparse_grad)
         self.cos_m, self.sin_m, self.th, self.mm = ops.margin_constants(m)
 
     def update_m(self, delta):
@@ -245,6 +258,10 @@ class ArcMarginProduct(nn.Module):
         x = x.to(torch.float32).contiguous()
         xhat, _, what, _ = self._operands(x)
         return ops.cosine_topk(xhat, what, k)
+
+    def last_sample_index(self):
+        """Sorted class ids (int64) the most recent sampled training step ran on, or None (sample_rate == 1)."""
+        return engine.last_sample(self)
 
     def invalidate_weight_cache(self) -> None:
         """Forget everything derived from `weight`: the normalised rows a fused optimiser step left behind and the

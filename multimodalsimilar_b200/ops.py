@@ -85,6 +85,30 @@ def normalize_cast3(src: torch.Tensor, order: int, want_transpose: bool = False)
     return dst, inv, dst_t
 
 
+def normalize_cast_gather(src: torch.Tensor, index: torch.Tensor):
+    """K1 over sampled rows.  src [R, D] fp32, index int64 [S] -> (bf16 [S, D] rows normalise(src[index]), inv_norm [S])."""
+    _req(src, torch.float32, "src")
+    _req(index, torch.int64, "index")
+    R, D = src.shape
+    S = index.numel()
+    dst = torch.empty((S, D), dtype=torch.bfloat16, device=src.device)
+    inv = torch.empty((S,), dtype=torch.float32, device=src.device)
+    _lib.call("arcface_b200_normalize_cast_gather", _ptr(src), R, _ptr(index), S, D, _ptr(dst), _ptr(inv), _stream())
+    return dst, inv
+
+
+def scatter_rows(src: torch.Tensor, index: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """dst[index[r]] = src[r] (fp32 rows): the sampled classes' gradient into the full-size dW."""
+    _req(src, torch.float32, "src")
+    _req(index, torch.int64, "index")
+    _req(dst, torch.float32, "dst")
+    if src.shape[1] != dst.shape[1] or index.numel() != src.shape[0]:
+        raise ValueError("scatter_rows: %s rows by %s indices into %s" % (tuple(src.shape), tuple(index.shape), tuple(dst.shape)))
+    _lib.call("arcface_b200_scatter_rows", _ptr(src), _ptr(index), src.shape[0], src.shape[1], _ptr(dst), dst.shape[0],
+              _stream())
+    return dst
+
+
 @dataclass
 class LabelMargin:
     t_label: torch.Tensor      # fp32 [B] exact label cosine (0 where the label is on another rank)

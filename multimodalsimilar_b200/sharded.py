@@ -56,7 +56,7 @@ class ShardedArcMarginProduct(nn.Module):
 
     def __init__(self, in_feature=128, out_feature=10575, s=64.0, m=0.40, easy_margin=False, *, in_features=None,
                  out_features=None, process_group=None, kernels=None, use_cuda_graph=True, use_p2p=True,
-                 precision="bf16"):
+                 precision="bf16", sample_rate=1.0, sample_seed=None, sparse_grad=False):
         super().__init__()
         if in_features is not None:
             in_feature = in_features
@@ -69,9 +69,17 @@ class ShardedArcMarginProduct(nn.Module):
         self.use_p2p = use_p2p      # exchanges through peer-mapped memory (p2p.py) instead of NCCL when available
         engine.precision_code(precision)
         self.precision = precision  # 'bf16' | 'bf16x3' (see ArcMarginProduct)
+        # PartialFC-style class sampling of the LOCAL shard (see ArcMarginProduct): every rank draws its own negatives
+        if not 0.0 < float(sample_rate) <= 1.0:
+            raise ValueError("sample_rate must be in (0, 1], got %r" % (sample_rate,))
+        self.sample_rate = float(sample_rate)
+        self.sample_seed = None if sample_seed is None else int(sample_seed)   # offset by the rank below
+        self.sparse_grad = bool(sparse_grad)
         self.process_group = process_group if process_group is not None else dist.group.WORLD
         self.world_size = dist.get_world_size(self.process_group)
         self.rank = dist.get_rank(self.process_group)
+        if self.sample_seed is not None:
+            self.sample_seed += 7919 * self.rank   # one seed for the job, a different stream per rank
         if out_feature < self.world_size:
             raise ValueError("need at least one class per rank")
         self.in_feature = in_feature
@@ -177,6 +185,10 @@ class ShardedArcMarginProduct(nn.Module):
             raise ValueError("expected weight of shape %s" % ((self.out_feature, self.in_feature),))
         self.weight.copy_(weight[self.class_lo:self.class_hi].to(self.weight.device, self.weight.dtype))
         self.invalidate_weight_cache()
+
+    def last_sample_index(self):
+        """Sorted LOCAL class ids (add class_lo for global ids) of the most recent sampled training step, or None."""
+        return engine.last_sample(self)
 
     def invalidate_weight_cache(self) -> None:
         """See ArcMarginProduct.invalidate_weight_cache."""

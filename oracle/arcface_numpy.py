@@ -198,3 +198,40 @@ def cosine_topk(x, w, k):
         order = np.concatenate([order, np.full((B, k - C), -1, dtype=order.dtype)], axis=1)
     return vals, order.astype(np.int64)
 
+
+
+# ---------------------------------------------------------------------------------------------- class sampling
+# SURVEY.md section 8f row N4.  The reference always trains every class; the sampling rule is PartialFC's
+# (insightface, recognition/arcface_torch/partial_fc_v2.py `PartialFC_V2.sample`, not vendored in /root/reference --
+# "parity unpinned" for the RULE; the head evaluated on the sampled rows is arcface.py itself and is pinned by the
+# goldens like everything above):
+#     positive = unique(labels of this shard);  perm = rand(num_local);  perm[positive] = 2.0
+#     index = sort(topk(perm, num_sample).indices);  labels = searchsorted(index, labels)
+#     sub_weight = weight[index]  -> normalised, multiplied with the embeddings, margin + softmax over these rows only
+def partial_fc_sample(label_local, c_local: int, num_sample: int, scores: np.ndarray) -> np.ndarray:
+    """Sorted class ids of the sample given the random scores `scores` [c_local] in [0, 1): the labels' classes
+    (score forced to 2) and the best-scoring negatives, S = max(num_sample, min(B, c_local)) rows (the product fixes S
+    on the host; PartialFC's fallback for num_sample < #positives is 'positives only').  label_local: -1 = not here."""
+    label_local = np.asarray(label_local).reshape(-1)
+    S = min(c_local, max(int(num_sample), min(label_local.size, c_local)))
+    perm = np.array(scores, dtype=np.float64, copy=True)
+    perm[label_local[label_local >= 0]] = 2.0
+    # top-S by score; ties (only among the 2.0s, all of which are taken) do not matter
+    index = np.argsort(-perm, kind="stable")[:S]
+    return np.sort(index).astype(np.int64)
+
+
+def sampled_head(x, w, label, index, s=64.0, m=0.40, easy_margin=False, grad_loss=1.0, dtype=np.float64):
+    """The reference head (arcface.py:45-63 + CrossEntropyLoss + argmax + backward) on the sampled rows w[index] with
+    the labels remapped into the sample (every label must be in `index`).  Returns (loss, argmax as ORIGINAL class
+    ids, dx, dw of the full weight: zero rows outside the sample)."""
+    index = np.asarray(index, dtype=np.int64)
+    label = np.asarray(label).reshape(-1)
+    pos = np.searchsorted(index, label)
+    assert np.array_equal(index[pos], label), "a label is missing from the sample"
+    ws = w[index]
+    z = forward_logits(x, ws, pos, s, m, easy_margin, dtype=dtype)
+    dx, dws = backward(x, ws, pos, s, m, easy_margin, grad_loss, dtype=dtype)
+    dw = np.zeros(w.shape, dtype=dws.dtype)
+    dw[index] = dws
+    return cross_entropy(z, pos), index[argmax(z)], dx, dw

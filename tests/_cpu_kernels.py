@@ -94,3 +94,13 @@ def normalize_bwd_x(x, inv_nx, dxhat):
     xh = x.double() * inv_nx[:, None]
     g = dxhat.double()
     return ((g - xh * (xh * g).sum(1, keepdim=True)) * inv_nx[:, None]).float()
+
+
+def normalize_cast_gather(src, index):
+    vh, inv, _ = normalize_cast(src[index])
+    return vh, inv
+
+
+def scatter_rows(src, index, dst):
+    dst[index] = src
+    return dst
