@@ -145,6 +145,8 @@ class ClockSampler(threading.Thread):
                "reasons": [n for b, n in self.REASONS.items() if self.mask & b]}
         if self.power:
             out["power_w_max"] = max(self.power)
+            tail = self.power[len(self.power) // 2:]   # NVML's power reading lags the load by ~100 ms: the settled half
+            out["power_w_mean_settled"] = sum(tail) / len(tail)
         return out
 
 
@@ -697,6 +699,18 @@ def main():
                      "value": B / (ts["ms_per_step"] * 1e-3), "clocks": ts["clocks"],
                      "frac_sustained": roof_step["t_roof_sustained_ms"] / ts["ms_per_step"],
                      "note": "the same step looped back to back for >= 1 s right after the timed region"}
+        pw = (ts["clocks"] or {}).get("power_w_mean_settled")
+        if pw and world == 1 and head_name == "ns" and not args.classes:
+            # Board energy of one step, and what the step's executed work costs at the energy per flop / per DRAM byte of
+            # the two pure kernels measured at the same power cap (profiles/README.md, tools/power_probe.py: cuBLAS bf16
+            # 8192^3 0.69 pJ/flop, K1 streaming 0.13 nJ/byte): under the cap, time = energy / power.
+            exe_flops, dram = roof_step["executed_flops"], NCU_TRAFFIC["fwd"] + NCU_TRAFFIC["k3"]
+            sustained["energy"] = {
+                "power_w_mean": pw, "j_per_step": pw * ts["ms_per_step"] * 1e-3,
+                "model_j_per_step": exe_flops * 0.69e-12 + dram * 0.13e-9,
+                "model_j_algorithmic_floor": roof_step["algorithmic_flops"] * 0.69e-12 + roof_step["algorithmic_bytes"] * 0.13e-9,
+                "note": "model = executed flops x 0.69 pJ + ncu DRAM bytes x 0.13 nJ; floor = the same for 6 B D C flops "
+                        "and 8 C D bytes (no recompute, no bf16 copy of the weights)"}
 
     parity = None if args.no_parity else job.parity()
     gpu_launches = launches_per_step(job, ops) * args.steps
