@@ -24,6 +24,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#ifndef AB_DXP_COST
+#define AB_DXP_COST 2300.0   // pair-cycles per 256-class block and 256 x 256 of dX output on the CTA-pair role
+#endif
+
 namespace ab {
 
 constexpr float LOG2E_B = 1.4426950408889634f;
@@ -1138,6 +1142,7 @@ struct BwdPlan {
     bool dc_pair, dw_pair;   // ... on CTA pairs (cta_group::2) instead of single CTAs
     // single-launch backward (k3_fused.cuh): role split in CTA pairs, ring slots, counters
     bool fused;
+    bool dx_pairs;           // single-launch backward: the dX role runs on CTA pairs
     int n_dc, n_dw, n_dx, ring_slots, n_blocks;
     size_t cnt_off, cnt_bytes;
     int q_slots;             // partial-sum slots of q per class
@@ -1153,6 +1158,7 @@ static size_t fused_smem_bytes() {
     static_assert(pr::smem_bytes<BwdDCpT<true>>(pr::MAX_KBLOCKS, BwdDCpT<true>::EXTRA_BYTES) <= 227 * 1024, "dC^T role");
     static_assert(pr::smem_bytes<BwdDWpT<true>>(pr::MAX_KBLOCKS, BwdDWpT<true>::EXTRA_BYTES) <= 227 * 1024, "dW role");
     static_assert(fz::dx_smem_bytes() <= 227 * 1024, "dX role");
+    static_assert(fz::dxp_smem_bytes() <= 227 * 1024, "dX role on CTA pairs");
     return 227 * 1024;
 }
 static int fused_max_pairs(int nsm) {
@@ -1221,6 +1227,7 @@ static BwdPlan plan_backward(int B, int D, int64_t C, int nsm, int Ds = 0) {
     // ---- single-launch backward: every role needs its resident operand to fit (D, B <= 512) and the launch
     // needs enough co-resident CTA pairs to give each role a few
     pl.fused = false;
+    pl.dx_pairs = false;
     pl.n_dc = pl.n_dw = pl.n_dx = pl.ring_slots = 0;
     pl.n_blocks = static_cast<int>((C + 255) / 256);
     // bf16x3 mode (Ds = 3 D) on CTA pairs: hi/lo dC through a three-block scratch, three launches per chunk (the ring
@@ -1229,7 +1236,10 @@ static BwdPlan plan_backward(int B, int D, int64_t C, int nsm, int Ds = 0) {
     if (pl.dc_pair && pl.dw_pair && pl.kx == 1 && !env_is("ARCFACE_B200_BWD_IMPL", "split")) {
         const int n_res_dc = (B + 255) / 256, n_res_dw = (D + 255) / 256;
         const int tiles = n_res_dc * n_res_dw;         // dX output tiles (256 x 256)
-        const int dx_unit = (tiles + 1) / 2;           // CTA pairs per dX split
+        // dX role: a CTA pair per 256 x 512 tile (k3_fused.cuh dx_pair_body), or -- diagnostic builds,
+        // ARCFACE_B200_BWD_DX=cta -- the round-1 role with one CTA per 256 x 256 tile
+        pl.dx_pairs = !env_is("ARCFACE_B200_BWD_DX", "cta");
+        const int dx_unit = pl.dx_pairs ? n_res_dc * ((D + 511) / 512) : (tiles + 1) / 2;   // CTA pairs per dX split
         const int pairs = fused_max_pairs(nsm);
         int a = 0, b = 0, c = 0;
         if (const char* v = diag_env("ARCFACE_B200_BWD_SPLIT")) sscanf(v, "%d,%d,%d", &a, &b, &c);
@@ -1249,7 +1259,8 @@ static BwdPlan plan_backward(int B, int D, int64_t C, int nsm, int Ds = 0) {
             const double mma_dw = 8.0 * pl.Bp / (pl.Bp / 64 > pr::MAX_KBLOCKS ? 0.7 : 1.0);
             const double cost_dc = n_res_dc * (mma_dc > 6650.0 ? mma_dc : 6650.0);
             const double cost_dw = n_res_dw * (mma_dw > 8950.0 ? mma_dw : 8950.0);
-            const double cost_dx = tiles * 5053.0 / 2.0;
+            // dX: ~5.05k cycles per block and 256 x 256 tile on one CTA; on a pair ~2.3k pair-cycles per 256 x 256 of output
+            const double cost_dx = pl.dx_pairs ? tiles * AB_DXP_COST : tiles * 5053.0 / 2.0;
             double best = 1e300;
             for (int aa = n_res_dc; aa <= pairs; aa += n_res_dc)
                 for (int bb = n_res_dw; aa + bb <= pairs; bb += n_res_dw) {
@@ -1457,8 +1468,11 @@ static int32_t backward_impl(const uint16_t* xhat, const uint16_t* xhat_t, int64
         ring.done = counters + pl.n_blocks;
         const int n_res_dc = (B + 255) / 256, n_res_dw = (D + 255) / 256;
         ring.ready_target = n_res_dc * 2;  // one arrival per producer CTA (its publisher warp)
-        ring.done_target = n_res_dw + n_res_dc * n_res_dw;
+        const int dn512 = (D + 511) / 512;
+        // consumers of a block: one dW pair per 256 embedding columns + the dX CTAs / pairs of the block's split
+        ring.done_target = n_res_dw + (pl.dx_pairs ? n_res_dc * dn512 : n_res_dc * n_res_dw);
         fz::FusedParams fp;
+        fp.dx_pairs = pl.dx_pairs ? 1 : 0;
         fp.n_dc = pl.n_dc;
         fp.n_dw = pl.n_dw;
         fp.n_dx = pl.n_dx;
@@ -1515,8 +1529,14 @@ static int32_t backward_impl(const uint16_t* xhat, const uint16_t* xhat_t, int64
             fz::DXParams& p = fp.dx;
             p.B = B; p.D = D;
             p.n_blocks = pl.n_blocks;
-            p.m_tiles = n_res_dc; p.dn_tiles = n_res_dw;
-            p.splits = (2 * pl.n_dx) / (n_res_dc * n_res_dw);
+            p.m_tiles = n_res_dc;
+            if (pl.dx_pairs) {
+                p.dn_tiles = dn512;
+                p.splits = pl.n_dx / (n_res_dc * dn512);
+            } else {
+                p.dn_tiles = n_res_dw;
+                p.splits = (2 * pl.n_dx) / (n_res_dc * n_res_dw);
+            }
             p.ring = ring;
         }
         // the ring replaces the full-size scratch: [slots * 256][Bp] bf16
