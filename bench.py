@@ -64,7 +64,20 @@ CONFIGS["ns_bf16x3"] = dict(CONFIGS["ns"], precision="bf16x3",
 CONFIGS["c5_10m_pfc10"] = dict(CONFIGS["c5_10m"], sample_rate=0.1, sparse_grad=True,
                                what="BASELINE config 5 at C=10M with PartialFC-style class sampling (sample_rate=0.1: "
                                     "the batch's label classes + uniform negatives, 1M rows per step; sparse dW)")
-EXTRA_CONFIGS = ["c2", "c3", "c4", "c5_100k", "c5_1m", "c5_10m", "c5_10m_pfc10", "ns_bf16x3"]
+# "the realistic PartialFC regime (per-rank B = 512 => global B = 512 R), separately, labelled": weak scaling
+# in the batch, run at N > 1 only (at N = 1 it is the north-star shape).  B is resolved in resolve_config().
+CONFIGS["ns_weak"] = dict(CONFIGS["ns"], B_per_rank=512, scaling="weak",
+                          what="PartialFC regime: north-star head with a per-rank batch of 512 rows (global batch 512 x N; "
+                               "above 1024 rows the GEMM kernels run once per row chunk)")
+EXTRA_CONFIGS = ["c2", "c3", "c4", "c5_100k", "c5_1m", "c5_10m", "c5_10m_pfc10", "ns_bf16x3", "ns_weak"]
+
+
+def resolve_config(name, world):
+    """CONFIGS[name] with the world-size dependent entries filled in."""
+    c = dict(CONFIGS[name])
+    if "B_per_rank" in c:
+        c["B"] = c["B_per_rank"] * world
+    return c
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of the north-star
 # workload on one B200; only meaningful for the single-GPU north-star shape.
 NCU_TRAFFIC = {"fwd": 2.300311e9 + 0.995569e9, "k3": 1.401256e9 + 2.114588e9,
@@ -677,7 +690,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     head_name = args.config or "ns"
-    cfg = dict(CONFIGS[head_name])
+    cfg = resolve_config(head_name, world)
     if args.classes:
         cfg["C"] = args.classes
     peaks = load_peaks()
@@ -732,7 +745,9 @@ def main():
     if args.config is None and not args.no_extra and not args.classes:
         extra = {}
         for name in EXTRA_CONFIGS:
-            c = CONFIGS[name]
+            c = resolve_config(name, world)
+            if "B_per_rank" in c and world == 1:
+                continue   # identical to the north-star shape on one GPU
             try:
                 j = Job(torch, dist, mm, name, c, world, rank, dev)
                 tt = j.timed(10, 6, sample_clocks=True)
@@ -741,7 +756,7 @@ def main():
                      "value": c["B"] / (tt["ms_per_step"] * 1e-3), "unit": "samples/s", "steps": 10, "warmup": 6,
                      "clocks": tt["clocks"], "roofline_step": j.roofline_step(tt["ms_per_step"], peaks, tt["clocks"]),
                      "exchange": j.exchange(), "k3_launches": ops.backward_launches(c["B"], c["D"], j.c_hi - j.c_lo),
-                     "sample_rate": c.get("sample_rate", 1.0),
+                     "sample_rate": c.get("sample_rate", 1.0), "scaling": c.get("scaling", "strong"),
                      "precision": c.get("precision", "bf16"), "workload": c["what"]}
                 if not args.no_parity:
                     r["parity"] = j.parity()
@@ -764,7 +779,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "ms_per_step_median": t["ms_per_step_median"],
             "ms_per_step_best": t["ms_per_step_best"], "ms_per_step_worst": t["ms_per_step_worst"],
-            "higher_is_better": True, "scaling": "strong",
+            "higher_is_better": True, "scaling": cfg.get("scaling", "strong"),
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(head_name, cfg, world, exchange),
             "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline_step": roof_step, "loss": t["loss"],

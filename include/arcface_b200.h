@@ -85,6 +85,10 @@ int32_t arcface_b200_normalize_cast_gather(const float* src, int64_t src_rows, c
 int32_t arcface_b200_scatter_rows(const float* src, const int64_t* index, int64_t rows, int32_t D, float* dst,
                                   int64_t dst_rows, void* stream);
 
+/* dst[i] += src[i], i < n (fp32; n % 4 == 0, 16-byte aligned).  A global batch above 1024 rows runs the GEMM kernels once
+ * per chunk of rows (the row statistics and the exchanges stay one pass); this sums the chunks' dW. */
+int32_t arcface_b200_accumulate(float* dst, const float* src, int64_t n, void* stream);
+
 /* Label column in fp32 + margin (arcface.py:49-55 restricted to the label column, the only place the
  * reference's one-hot blend at :58-60 uses phi).  For every row b whose label falls in this shard:
  *   t = <x_b, w_y> * inv_nx[b] * inv_nw[y];  sine = sqrt(max(0, 1 - t^2));  phi = t cos_m - sine sin_m

@@ -30,6 +30,7 @@ SIGNATURES = {
     "arcface_b200_normalize_cast": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "arcface_b200_normalize_cast3": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "arcface_b200_normalize_cast_gather": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
+    "arcface_b200_accumulate": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p]),
     "arcface_b200_scatter_rows": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int64, c_void_p]),
     "arcface_b200_label_margin": (
         c_int32,

@@ -741,6 +741,31 @@ extern "C" int32_t arcface_b200_scatter_rows(const float* src, const int64_t* in
     return ARCFACE_B200_OK;
 }
 
+__global__ void __launch_bounds__(256) accumulate_kernel(float4* __restrict__ dst, const float4* __restrict__ src, int64_t n4) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float4 a = dst[i];
+        const float4 b = ldg_stream(src + i);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        dst[i] = a;
+    }
+}
+
+extern "C" int32_t arcface_b200_accumulate(float* dst, const float* src, int64_t n, void* stream) {
+    if (int32_t rc = check_arch()) return rc;
+    AB_REQUIRE(dst && src, ARCFACE_B200_E_ARG, "accumulate: null pointer");
+    AB_REQUIRE(n >= 0 && n % 4 == 0, ARCFACE_B200_E_SHAPE, "accumulate: n must be a non-negative multiple of 4");
+    AB_REQUIRE(aligned16(dst) && aligned16(src), ARCFACE_B200_E_LAYOUT, "accumulate: pointers must be 16-byte aligned");
+    if (n == 0) return ARCFACE_B200_OK;
+    const int64_t n4 = n / 4;
+    const int64_t want = (n4 + 255) / 256;
+    const int grid = static_cast<int>(want < 148 * 16 ? want : 148 * 16);
+    accumulate_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<float4*>(dst),
+                                                                        reinterpret_cast<const float4*>(src), n4);
+    AB_CHECK_CUDA(cudaGetLastError());
+    return ARCFACE_B200_OK;
+}
+
 extern "C" int32_t arcface_b200_normalize_cast3(const float* src, int64_t rows, int32_t D, int32_t order, uint16_t* dst3,
                                                 float* inv_norm, uint16_t* dst_t, int64_t ld_t, void* stream) {
     if (int32_t rc = check_arch()) return rc;

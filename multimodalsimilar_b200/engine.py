@@ -187,25 +187,61 @@ def remap_labels(label_local: torch.Tensor, index: torch.Tensor) -> torch.Tensor
     return torch.where(lab >= 0, pos, torch.full_like(pos, -1)).to(torch.int32)
 
 
+# Rows of the (gathered) batch one GEMM launch takes.  The CTA-pair kernels and the single-launch backward cover B <= 1024
+# (include/arcface_b200.h); a larger global batch -- the PartialFC regime, per-rank batch x ranks -- runs K2 and K3 once
+# per chunk of <= 1024 rows against the same normalised weights.  Rows are independent up to the mean of the loss and the
+# sum over rows in dW, so the row kernels, the three exchanges and the softmax statistics stay one pass over the whole
+# batch and only dW is accumulated over the chunks.
+BATCH_CHUNK = 1024
+
+
+def batch_chunks(B: int, prec: int = 0):
+    """[(b0, b1)] row ranges of the GEMM launches: one range for B <= BATCH_CHUNK (and in the bf16x3 mode, whose
+    transposed operand is laid out per launch), else equal chunks whose starts are multiples of 64."""
+    if prec or B <= BATCH_CHUNK:
+        return [(0, B)]
+    n = -(-B // BATCH_CHUNK)
+    size = -(-(-(-B // n)) // 64) * 64
+    return [(b0, min(B, b0 + size)) for b0 in range(0, B, size)]
+
+
 def _rows(K, xhat, w, label_local, cfg, w_cache, out=None, sample=None):
     """(what, inv_nw, max, sum, arg): K1 (w) fused into K2, or K2 alone on the rows a fused optimiser step left
     behind (`w_cache` = (what, inv_nw), optim.FusedHeadAdamW).  `sample`: K1 gathers the sampled rows, K2 runs on
-    them (`label_local` already remapped), the argmax comes back as a global class id."""
-    kw = {} if out is None else {"out": out}
+    them (`label_local` already remapped), the argmax comes back as a global class id.  `out`: (max fp32 [B], sum fp32 [B],
+    arg int64 [B]) to fill."""
+    B = xhat.shape[0]
+    chunks = batch_chunks(B, cfg.prec)
+    class_lo = cfg.class_lo
+    what = inv_nw = None
     if sample is not None:
         if cfg.prec:
             raise NotImplementedError("class sampling runs in precision='bf16' only")
         what, inv_nw = K.normalize_cast_gather(w, sample)
-        rmax, rsum, rarg = K.forward_rows(xhat, what, label_local, cfg.s, 0, **kw)
-        rarg.copy_(sample[rarg] + cfg.class_lo)   # sampled position -> global class id (B values)
-        return what, inv_nw, rmax, rsum, rarg
-    if cfg.prec:   # bf16x3: K1 writes the three-part rows, K2 contracts over 3 D
+        class_lo = 0
+    elif cfg.prec:   # bf16x3: K1 writes the three-part rows, K2 contracts over 3 D
         what, inv_nw, _ = K.normalize_cast3(w, 1)
-        return (what, inv_nw) + tuple(K.forward_rows(xhat, what, label_local, cfg.s, cfg.class_lo, **kw))
-    if w_cache is not None:
+    elif w_cache is not None:
         what, inv_nw = w_cache
-        return (what, inv_nw) + tuple(K.forward_rows(xhat, what, label_local, cfg.s, cfg.class_lo, **kw))
-    return K.forward_rows_fused(xhat, w, label_local, cfg.s, cfg.class_lo, **kw)
+    if len(chunks) > 1 and out is None:
+        dev = xhat.device
+        out = (torch.empty(B, dtype=torch.float32, device=dev), torch.empty(B, dtype=torch.float32, device=dev),
+               torch.empty(B, dtype=torch.int64, device=dev))
+    rmax = rsum = rarg = None
+    for b0, b1 in chunks:
+        whole = (b0, b1) == (0, B)
+        kw = {} if out is None else {"out": out if whole else tuple(o[b0:b1] for o in out)}
+        xs = xhat if whole else xhat[b0:b1]
+        ls = label_local if (whole or label_local is None) else label_local[b0:b1]
+        if what is None:   # first launch: the forward kernel normalises the weights itself and leaves them behind
+            what, inv_nw, rmax, rsum, rarg = K.forward_rows_fused(xs, w, ls, cfg.s, class_lo, **kw)
+        else:
+            rmax, rsum, rarg = K.forward_rows(xs, what, ls, cfg.s, class_lo, **kw)
+    if out is not None:
+        rmax, rsum, rarg = out
+    if sample is not None:
+        rarg.copy_(sample[rarg] + cfg.class_lo)   # sampled position -> global class id (B values)
+    return what, inv_nw, rmax, rsum, rarg
 
 
 def forward_eager(K, group, x_local, w, y_local, cfg: StepConfig, packed_xy=None, w_cache=None, peer=None,
@@ -262,8 +298,24 @@ def backward_eager(K, group, x_local, st: FwdState, grad_loss, cfg: StepConfig, 
     b_loc = x_local.shape[0]
     g = grad_loss.to(torch.float32).contiguous()
     kw = {"prec": cfg.prec} if cfg.prec else {}
-    dxhat_part, dw = K.backward(st.xhat, st.xhat_t, st.what, st.inv_nw, st.lse, st.omp, st.dphi, st.label_local,
-                                cfg.s, 1.0 / st.B, grad_loss_dev=g, **kw)
+    chunks = batch_chunks(st.B, cfg.prec)
+    if len(chunks) == 1:
+        dxhat_part, dw = K.backward(st.xhat, st.xhat_t, st.what, st.inv_nw, st.lse, st.omp, st.dphi, st.label_local,
+                                    cfg.s, 1.0 / st.B, grad_loss_dev=g, **kw)
+    else:
+        # one K3 launch per row chunk (batch_chunks): dX rows land in their slice, dW is summed over the chunks
+        dxhat_part = torch.empty((st.B, st.xhat.shape[1]), dtype=torch.float32, device=st.xhat.device)
+        dw = tmp = None
+        for b0, b1 in chunks:
+            if dw is not None and tmp is None:
+                tmp = torch.empty_like(dw)
+            _, dwi = K.backward(st.xhat[b0:b1], st.xhat_t[:, b0:b1], st.what, st.inv_nw, st.lse[b0:b1], st.omp[b0:b1],
+                                st.dphi[b0:b1], st.label_local[b0:b1], cfg.s, 1.0 / st.B, grad_loss_dev=g,
+                                dxhat_out=dxhat_part[b0:b1], dw_out=tmp)
+            if dw is None:
+                dw = dwi
+            else:
+                K.accumulate(dw, tmp)
     if st.sample is not None:
         # class sampling: the rows that were not drawn took no part in the softmax -- their gradient is exactly zero
         if sparse_dw:

@@ -354,10 +354,22 @@ def backward(xhat, xhat_t, what, inv_nw, lse, one_minus_p, dphi, label_local, s:
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     if grad_loss_dev is not None:
         grad_loss_dev = _req(grad_loss_dev.reshape(1), torch.float32, "grad_loss")
-    _lib.call("arcface_b200_backward_prec", _ptr(xhat), _ptr(xhat_t), xhat_t.shape[1] // (3 if prec else 1), _ptr(what), _ptr(inv_nw),
+    # xhat_t may be a column slice [D, b0:b1] of the full transpose (batch chunks): its leading dimension is the stride
+    ld_t = xhat_t.stride(0) // (3 if prec else 1)
+    _lib.call("arcface_b200_backward_prec", _ptr(xhat), _ptr(xhat_t), ld_t, _ptr(what), _ptr(inv_nw),
               _ptr(lse), _ptr(one_minus_p), _ptr(dphi), _ptr(label_local), B, D, C, s, grad_scale, _ptr(grad_loss_dev),
               _ptr(dxhat), _ptr(dw), _ptr(ws), nbytes, int(prec), _stream())
     return dxhat, dw
+
+
+def accumulate(dst: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
+    """dst += src (fp32, same shape): dW of a further batch chunk onto the first one's."""
+    _req(dst, torch.float32, "dst")
+    _req(src, torch.float32, "src")
+    if dst.shape != src.shape:
+        raise ValueError("accumulate: %s += %s" % (tuple(dst.shape), tuple(src.shape)))
+    _lib.call("arcface_b200_accumulate", _ptr(dst), _ptr(src), dst.numel(), _stream())
+    return dst
 
 
 def two_stream_concat(a, b):

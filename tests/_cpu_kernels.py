@@ -39,7 +39,15 @@ def label_margin(x, w, inv_nx, inv_nw, label, class_offset, c_total, s, m, easy_
     )
 
 
-def forward_rows(xhat, what, label_local, s, class_offset=0):
+def _fill(out, vals):
+    if out is None:
+        return vals
+    for o, v in zip(out, vals):
+        o.copy_(v)
+    return tuple(out)
+
+
+def forward_rows(xhat, what, label_local, s, class_offset=0, out=None):
     """Statistics over every local column except the row's label column (merged later by finalize_rows)."""
     z = (xhat @ what.t()) * s
     if label_local is not None:
@@ -48,12 +56,12 @@ def forward_rows(xhat, what, label_local, s, class_offset=0):
     rmax = z.max(dim=1).values
     rarg = (z == rmax[:, None]).int().argmax(dim=1)  # first maximum
     rsum = torch.where(torch.isinf(rmax), torch.zeros_like(rmax), (z - rmax[:, None]).exp().sum(1))
-    return rmax.float(), rsum.float(), (rarg + class_offset).long()
+    return _fill(out, (rmax.float(), rsum.float(), (rarg + class_offset).long()))
 
 
-def forward_rows_fused(xhat, weight, label_local, s, class_offset=0):
+def forward_rows_fused(xhat, weight, label_local, s, class_offset=0, out=None):
     what, inv_nw, _ = normalize_cast(weight)
-    return (what, inv_nw) + forward_rows(xhat, what, label_local, s, class_offset)
+    return (what, inv_nw) + forward_rows(xhat, what, label_local, s, class_offset, out)
 
 
 def finalize_rows(rows_max, rows_sum, rows_arg, rows_z, label):
@@ -74,8 +82,13 @@ def finalize_rows(rows_max, rows_sum, rows_arg, rows_z, label):
     return lse.float(), arg, Z.float(), omp.float(), (lse - Z).mean().float()
 
 
+def accumulate(dst, src):
+    dst += src
+    return dst
+
+
 def backward(xhat, xhat_t, what, inv_nw, lse, one_minus_p, dphi, label_local, s, grad_scale, grad_loss_dev=None,
-             dw_out=None):
+             dw_out=None, dxhat_out=None):
     g = grad_scale * (float(grad_loss_dev) if grad_loss_dev is not None else 1.0)
     cos = xhat @ what.t()
     p = (cos * s - lse.double()[:, None]).exp()
@@ -87,7 +100,12 @@ def backward(xhat, xhat_t, what, inv_nw, lse, one_minus_p, dphi, label_local, s,
     dwh = dc.t() @ xhat
     q = (dc * cos).sum(0)
     dw = (dwh - q[:, None] * what) * inv_nw[:, None]
-    return dxhat.float(), dw.float()
+    dxhat, dw = dxhat.float(), dw.float()
+    if dxhat_out is not None:
+        dxhat = dxhat_out.copy_(dxhat)
+    if dw_out is not None:
+        dw = dw_out.copy_(dw)
+    return dxhat, dw
 
 
 def normalize_bwd_x(x, inv_nx, dxhat):

@@ -354,6 +354,36 @@ def test_full_size_against_gpu_oracle_and_invariants(B, D, C, s, m, trained):
     assert float((head.weight.grad - 3.0 * dw).norm() / (3.0 * dw.norm())) <= 6e-3
 
 
+@pytest.mark.parametrize("B,D,C,s,m,trained,graph", [
+    (2304, 256, 20000, 64.0, 0.4, True, False),    # > ARCFACE_B200_MAX_BATCH: three chunks of 768 rows
+    (1100, 512, 30000, 64.0, 0.5, False, False),   # two ragged chunks (576 + 524)
+    (4096, 512, 125000, 64.0, 0.5, True, True),    # the PartialFC regime of one of 8 ranks (8 x 512 rows), graph replay
+])
+def test_large_batch_runs_in_row_chunks(B, D, C, s, m, trained, graph):
+    """A global batch above one GEMM launch: K2 / K3 once per chunk of <= 1024 rows (engine.batch_chunks), statistics and
+    loss in one pass, dW summed over the chunks -- against the fp32 oracle on the whole batch."""
+    from multimodalsimilar_b200 import engine
+
+    assert len(engine.batch_chunks(B)) >= 2
+    x, w, y = onp.synthetic_inputs(B, D, C, seed=5, trained_like=trained)
+    head = _make_head(w, s, m, False)
+    head.use_cuda_graph = graph
+    yt = _t(y)
+    for _ in range(4 if graph else 1):     # graph mode engages after two eager calls with the same signature
+        head.weight.grad = None
+        xt = _t(x).requires_grad_(True)
+        loss, pred = head.loss(xt, yt)
+        loss.backward()
+    rloss, rpred, top2, rdx, rdw = torch_oracle(_t(x), head.weight.detach(), yt, s, m, False)
+    assert abs(float(loss.detach()) - float(rloss)) <= LOSS_RTOL * max(1.0, abs(float(rloss)))
+    sep = (top2[:, 0] - top2[:, 1]) > 2 * logit_atol(s, D)
+    assert torch.equal(pred[sep], rpred[sep])
+    check_grad(xt.grad.cpu().numpy(), rdx.cpu().numpy(), s, D, "dx")
+    dw = head.weight.grad
+    assert float((dw - rdw).abs().max()) <= GRAD_ATOL * max(1.0, float(rdw.abs().max()))
+    assert float((dw - rdw).norm() / rdw.norm()) <= max(3e-2, 0.5 * logit_atol(s, D))
+
+
 # ----------------------------------------------------------------------------- host-buffer C-ABI step
 def test_step_host_matches_module():
     from multimodalsimilar_b200 import ops
