@@ -1238,7 +1238,10 @@ static BwdPlan plan_backward(int B, int D, int64_t C, int nsm, int Ds = 0) {
         const int tiles = n_res_dc * n_res_dw;         // dX output tiles (256 x 256)
         // dX role: a CTA pair per 256 x 512 tile (k3_fused.cuh dx_pair_body), or -- diagnostic builds,
         // ARCFACE_B200_BWD_DX=cta -- the round-1 role with one CTA per 256 x 256 tile
-        pl.dx_pairs = !env_is("ARCFACE_B200_BWD_DX", "cta");
+        // (measured per BASELINE shape, profiles/r2_dx_pair_exp.log: pairs 1-5 % faster except at D = 2816, whose eleven
+        // 256-column slices leave the sixth pair tile half empty and make a split twelve pairs coarse: 0.900 vs 0.862 ms)
+        pl.dx_pairs = !env_is("ARCFACE_B200_BWD_DX", "cta") && !(n_res_dw % 2 == 1 && n_res_dw > 8);
+        if (env_is("ARCFACE_B200_BWD_DX", "pair")) pl.dx_pairs = true;
         const int dx_unit = pl.dx_pairs ? n_res_dc * ((D + 511) / 512) : (tiles + 1) / 2;   // CTA pairs per dX split
         const int pairs = fused_max_pairs(nsm);
         int a = 0, b = 0, c = 0;

@@ -42,7 +42,7 @@ def timed(fn, n=10, warm=3):
 
 def setenv(**kw):
     for k in ("ARCFACE_B200_FWD_IMPL", "ARCFACE_B200_BWD_IMPL", "ARCFACE_B200_BWD_SPLIT", "ARCFACE_B200_BWD_PROF",
-              "ARCFACE_B200_FWD_PROF"):
+              "ARCFACE_B200_FWD_PROF", "ARCFACE_B200_BWD_DX"):
         os.environ.pop(k, None)
     for k, v in kw.items():
         os.environ["ARCFACE_B200_" + k] = v
@@ -75,7 +75,8 @@ for spec in args:
     def bwd():
         ops.backward(xhat, xhat_t, what, inv_nw, lse, omp, lm.dphi, lm.label_local, 64.0, 1.0 / B, dw_out=dw)
 
-    variants = [("fused default", {})] + [("fused " + sp, {"BWD_SPLIT": sp}) for sp in shape_splits] + \
+    variants = [("fused default", {}), ("fused, dX on single CTAs", {"BWD_DX": "cta"})] + \
+               [("fused " + sp, {"BWD_SPLIT": sp}) for sp in shape_splits] + \
                [("3 pair launches", {"BWD_IMPL": "split"}), ("generic", {"BWD_IMPL": "generic"})]
     for name, env in variants:
         setenv(**env)
