@@ -200,6 +200,8 @@ struct PairDefaults {
     // warp 3 (otherwise idle), all lanes: (prm, extra, i_begin, i_end, i_step, rank, lane) = this pair's tile walk
     template <class Prm>
     __device__ static void side_warp(const Prm&, uint8_t*, int, int, int, int, int) {}
+    // L2 eviction-priority policy for the TMA loads of the streamed operand (0 = none)
+    __device__ static uint64_t stream_policy() { return 0ull; }
     // TMA row coordinate of tile i of the streamed operand (the CTA adds rank * ROWS)
     template <class Prm>
     __device__ static int stream_row(const Prm& p, int i) { return p.core.s_row0 + i * 2 * ROWS; }
@@ -309,6 +311,7 @@ __device__ __forceinline__ void pair_gemm_body(const CUtensorMap& tmS, const CUt
         int stage = 0;
         uint32_t phase = 0;
         WaitProf wp_a(prof_on), wp_b(prof_on);
+        const uint64_t s_pol = P::stream_policy();   // L2 eviction priority of the streamed operand's lines (0 = default)
         for (int i = i_begin; i < i_end; i += i_step) {
             const int row = P::stream_row(prm, i) + rank * ROWS;
             wp_a.begin();
@@ -323,7 +326,8 @@ __device__ __forceinline__ void pair_gemm_body(const CUtensorMap& tmS, const CUt
                 if (elect_one()) {
                     const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
                     mbar_expect_tx_cluster(full_leader, STAGE_BYTES);
-                    tma_load_2d_pair(sStage + stage * STAGE_BYTES, &tmS, full_leader, kb * BK, row);
+                    if (s_pol != 0) tma_load_2d_pair_hint(sStage + stage * STAGE_BYTES, &tmS, full_leader, kb * BK, row, s_pol);
+                    else tma_load_2d_pair(sStage + stage * STAGE_BYTES, &tmS, full_leader, kb * BK, row);
                     if (stream) tma_load_2d_pair(sStage + stage * STAGE_BYTES + TILE_BYTES, &tmR, full_leader, kb * BK, res_row);
                     // the n_res pairs that stream the same block share the L2 prefetch work
                     if (pf && (kb % co.n_res) == res)

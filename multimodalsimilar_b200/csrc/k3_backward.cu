@@ -606,6 +606,11 @@ struct BwdDCpT : pr::PairDefaults {
         float* q;  // [2 * n_res][C]: one slot per (batch slice, column half)
         Ring ring;  // FUSED only
     };
+#ifdef AB_K3_L2HINTS
+    // experiment (measured 1.2 % SLOWER, profiles/r2_l2hint_exp.log): FUSED: the What rows this role streams are read
+    // again a ring depth later (dW correction term, dX operand) -- ask L2 to keep them
+    __device__ static uint64_t stream_policy() { return FUSED ? l2_policy_evict_last() : 0ull; }
+#endif
     static constexpr int BLOOM_WORDS = 128;  // 4096 bits, one per 128-class block (mod 4096)
     static constexpr int PUB_BAR_OFF = NCOL * 12 + BLOOM_WORDS * 4;  // FUSED: mbarrier epilogue warps -> publisher warp
     static constexpr int EXTRA_BYTES = PUB_BAR_OFF + 16;
@@ -1525,7 +1530,9 @@ static int32_t backward_impl(const uint16_t* xhat, const uint16_t* xhat_t, int64
             p.what = reinterpret_cast<const __nv_bfloat16*>(what);
             p.ldw = ldw;
             p.dw = dw;
-            p.evict_first = env_is("ARCFACE_B200_BWD_EVICT", "1") ? 1 : 0;
+            // dW lines are never read back by this kernel: evict-first keeps them from pushing the ring and the What
+            // rows out of L2 (1.481 -> 1.472 ms, alternated twice; ARCFACE_B200_BWD_EVICT=0 in diagnostic builds: off)
+            p.evict_first = env_is("ARCFACE_B200_BWD_EVICT", "0") ? 0 : 1;
             p.ring = ring;
         }
         {
@@ -1689,7 +1696,9 @@ static int32_t backward_impl(const uint16_t* xhat, const uint16_t* xhat_t, int64
             p.what = reinterpret_cast<const __nv_bfloat16*>(what);
             p.ldw = ldw;
             p.dw = dw;
-            p.evict_first = env_is("ARCFACE_B200_BWD_EVICT", "1") ? 1 : 0;
+            // dW lines are never read back by this kernel: evict-first keeps them from pushing the ring and the What
+            // rows out of L2 (1.481 -> 1.472 ms, alternated twice; ARCFACE_B200_BWD_EVICT=0 in diagnostic builds: off)
+            p.evict_first = env_is("ARCFACE_B200_BWD_EVICT", "0") ? 0 : 1;
             int groups = (nsm / 2) / p.core.n_res;
             if (groups < 1) groups = 1;
             if (groups > p.core.s_blocks) groups = p.core.s_blocks;
