@@ -80,8 +80,8 @@ def resolve_config(name, world):
     return c
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of the north-star
 # workload on one B200; only meaningful for the single-GPU north-star shape.
-NCU_TRAFFIC = {"fwd": 2.300311e9 + 0.995569e9, "k3": 1.401256e9 + 2.114588e9,
-               "source": "profiles/r2_fwd_bwd_full_raw.csv (ncu --set full, per launch)"}
+NCU_TRAFFIC = {"fwd": 2.315111e9 + 0.997995e9, "k3": 1.197121e9 + 2.134192e9,
+               "source": "profiles/r2b_fwd_bwd_full_raw.csv (ncu --set full, per launch)"}
 METRIC = "arcface_head_fwd_bwd_samples_per_sec_1M_classes"
 WEIGHT_SEED = 1234
 WEIGHT_BLOCK = 65536
