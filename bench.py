@@ -636,12 +636,30 @@ def dominant_kernel_roofline(job, ops, peaks, stages, regime, traffic_ok):
             "share_of_step": stages[top] / comp_ms, "peak_source": peaks["source"]}
 
 
+def batch_chunks_of(cfg):
+    from multimodalsimilar_b200 import engine
+
+    return engine.batch_chunks(cfg["B"], 1 if cfg.get("precision", "bf16") == "bf16x3" else 0)
+
+
+def k3_launches(job, ops):
+    """Backward kernels per step: per row chunk of the batch, 1 (single-launch backward) or 3 per scratch chunk; for a
+    sampled head over the sampled class count."""
+    cfg = job.cfg
+    c_loc = job.c_hi - job.c_lo
+    if job.sampled:
+        c_loc = min(c_loc, max(int(round(cfg["sample_rate"] * c_loc)), min(cfg["B"], c_loc)))
+    return sum(ops.backward_launches(b1 - b0, cfg["D"], c_loc) for b0, b1 in batch_chunks_of(cfg))
+
+
 def launches_per_step(job, ops):
     """Our kernels per step (memset / copy / NCCL nodes not counted): pack_xy, then -- replayed from one CUDA graph --
     K1(x), label, K1(w)+K2, combine, finalize, K3, bwd-x, then scale_copy; plus the three peer-memory exchange kernels
     when used."""
     cfg = job.cfg
-    n = 1 + 1 + 1 + 1 + 1 + 1 + ops.backward_launches(cfg["B"], cfg["D"], job.c_hi - job.c_lo) + 1 + 1
+    n = 1 + 1 + 1 + 1 + 1 + 1 + k3_launches(job, ops) + 1 + 1
+    chunks = len(batch_chunks_of(cfg))
+    n += 3 * (chunks - 1)   # a batch above one GEMM launch: K2 + combine and the dW accumulate once more per further chunk
     if cfg["D"] > 512:
         n += 1   # K1 of the class weights is its own launch when the in-kernel normaliser does not cover D
     if job.exchange() == "p2p":
@@ -755,7 +773,7 @@ def main():
                      "ms_per_step_median": tt["ms_per_step_median"], "ms_per_step_best": tt["ms_per_step_best"],
                      "value": c["B"] / (tt["ms_per_step"] * 1e-3), "unit": "samples/s", "steps": 10, "warmup": 6,
                      "clocks": tt["clocks"], "roofline_step": j.roofline_step(tt["ms_per_step"], peaks, tt["clocks"]),
-                     "exchange": j.exchange(), "k3_launches": ops.backward_launches(c["B"], c["D"], j.c_hi - j.c_lo),
+                     "exchange": j.exchange(), "k3_launches": k3_launches(j, ops),
                      "sample_rate": c.get("sample_rate", 1.0), "scaling": c.get("scaling", "strong"),
                      "precision": c.get("precision", "bf16"), "workload": c["what"]}
                 if not args.no_parity:
