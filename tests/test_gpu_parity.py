@@ -457,9 +457,14 @@ def test_shape_and_label_errors():
     head = mm.ArcMarginProduct(12, 32).to(dev())   # D % 8 != 0
     with pytest.raises(_lib.ArcfaceB200Error, match="E_SHAPE"):
         head.loss(torch.randn(4, 12, device=dev()), torch.zeros(4, dtype=torch.int64, device=dev()))
-    head = mm.ArcMarginProduct(16, 32).to(dev())
+    # one GEMM launch takes at most ARCFACE_B200_MAX_BATCH rows (the modules run larger batches in row chunks:
+    # test_large_batch_runs_in_row_chunks)
+    from multimodalsimilar_b200 import ops
+
+    xhat, _, _ = ops.normalize_cast(torch.randn(4096, 16, device=dev()))
+    what, _, _ = ops.normalize_cast(torch.randn(32, 16, device=dev()))
     with pytest.raises(_lib.ArcfaceB200Error, match="E_SHAPE"):
-        head.loss(torch.randn(4096, 16, device=dev()), torch.zeros(4096, dtype=torch.int64, device=dev()))
+        ops.forward_rows(xhat, what, None, 64.0, 0)
     head = mm.ArcMarginProduct(16, 32, validate_labels=True).to(dev())
     with pytest.raises(IndexError):
         head.loss(torch.randn(4, 16, device=dev()), torch.tensor([0, 1, 32, 3], device=dev()))
