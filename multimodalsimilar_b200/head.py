@@ -248,8 +248,9 @@ class ArcMarginProduct(nn.Module):
         forward_test's output, nlp_classifier_train.py:143-156).  Returns (argmax int64 [B], max cosine [B])."""
         x = x.to(torch.float32).contiguous()
         xhat, _, what, _ = self._operands(x)
-        rmax, _, rarg = ops.forward_rows(xhat, what, None, 1.0, 0)
-        return rarg, rmax
+        outs = [ops.forward_rows(xhat[lo:lo + ops.MAX_BATCH], what, None, 1.0, 0)     # MAX_BATCH rows per launch
+                for lo in range(0, xhat.shape[0], ops.MAX_BATCH)]
+        return torch.cat([o[2] for o in outs]), torch.cat([o[0] for o in outs])
 
     @torch.no_grad()
     def predict_topk(self, x, k: int):

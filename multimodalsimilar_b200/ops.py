@@ -283,8 +283,11 @@ def logits(xhat, what, z_label, label_local, scale: float) -> torch.Tensor:
     B, D = xhat.shape
     C = what.shape[0]
     out = torch.empty((B, C), dtype=torch.float32, device=xhat.device)
-    _lib.call("arcface_b200_logits", _ptr(xhat), _ptr(what), _ptr(z_label), _ptr(label_local), B, D, C, scale,
-              _ptr(out), C, _stream())
+    for lo in range(0, B, MAX_BATCH):   # one launch takes MAX_BATCH rows
+        hi = min(B, lo + MAX_BATCH)
+        _lib.call("arcface_b200_logits", _ptr(xhat[lo:hi]), _ptr(what), _ptr(None if z_label is None else z_label[lo:hi]),
+                  _ptr(None if label_local is None else label_local[lo:hi]), hi - lo, D, C, scale, _ptr(out[lo:hi]), C,
+                  _stream())
     return out
 
 
@@ -293,6 +296,9 @@ def cosine_topk(xhat, what, k: int, scale: float = 1.0, class_offset: int = 0):
     _req(xhat, torch.bfloat16, "xhat")
     _req(what, torch.bfloat16, "what")
     B, D = xhat.shape
+    if B > MAX_BATCH:   # one launch takes MAX_BATCH query rows
+        parts = [cosine_topk(xhat[lo:lo + MAX_BATCH], what, k, scale, class_offset) for lo in range(0, B, MAX_BATCH)]
+        return torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
     C = what.shape[0]
     dev = xhat.device
     n = ctypes.c_size_t(0)

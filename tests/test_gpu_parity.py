@@ -448,6 +448,16 @@ def test_eval_path(golden):
     arg, mx = head.predict(_t(x))
     assert torch.equal(arg, torch.argmax(cos, dim=-1))
     assert torch.equal(mx, cos.max(dim=1).values)
+    # more query rows than one launch takes (ARCFACE_B200_MAX_BATCH): the eval paths run in row blocks
+    big = _t(np.tile(x, (2048 // x.shape[0] + 2, 1)))
+    assert big.shape[0] > 2048
+    cosb = head.forward_test(big)
+    assert torch.equal(cosb[:x.shape[0]], cos) and torch.equal(cosb[-x.shape[0]:], cos)
+    argb, mxb = head.predict(big)
+    assert torch.equal(argb, torch.argmax(cosb, dim=-1)) and torch.equal(mxb, cosb.max(dim=1).values)
+    tv, ti = head.predict_topk(big, 3)
+    rv, ri = head.predict_topk(_t(x), 3)
+    assert torch.equal(tv[-x.shape[0]:], rv) and torch.equal(ti[-x.shape[0]:], ri)
 
 
 def test_shape_and_label_errors():

@@ -119,6 +119,7 @@ def _worker(rank, world, port, case, out_dir):
     (128, 512, 20000, 64.0, 0.5, True, False),  # bench-like D, graph replay over NCCL
     (64, 1024, 5001, 64.0, 0.4, True, True),    # BASELINE config 3 width (D > 512: both operands streamed)
     (64, 256, 3001, 64.0, 0.4, True, True, "bf16x3"),   # the parity mode, class-sharded, graph replay over peer memory
+    (2304, 128, 3001, 64.0, 0.4, True, True),   # global batch above one GEMM launch: row chunks (engine.batch_chunks)
 ])
 def test_two_gpu_sharded_head_matches_dense(case, tmp_path):
     if torch.cuda.device_count() < 2:
@@ -128,6 +129,95 @@ def test_two_gpu_sharded_head_matches_dense(case, tmp_path):
     ctx = mp.get_context("spawn")
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, case, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+    for p in procs:
+        if p.is_alive():
+            p.kill()
+            pytest.fail("worker timed out")
+    res = open(os.path.join(str(tmp_path), "result.txt")).read()
+    assert res == "OK", res
+
+
+def _sampled_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import multimodalsimilar_b200 as mm
+    from oracle import arcface_numpy as onp
+
+    B, D, C, s, m = 64, 128, 6001, 64.0, 0.4
+    x, w, y = onp.synthetic_inputs(B, D, C, seed=21, trained_like=True)
+    head = mm.ShardedArcMarginProduct(D, C, s=s, m=m, sample_rate=0.1, sample_seed=3).to(dev)
+    head.load_full_weight(torch.from_numpy(w))
+    b_loc = B // world
+    xl = torch.from_numpy(x[rank * b_loc:(rank + 1) * b_loc]).to(dev).requires_grad_(True)
+    yl = torch.from_numpy(y[rank * b_loc:(rank + 1) * b_loc]).to(dev)
+    ok, msg = True, ""
+    for it in range(3):
+        xl.grad = None
+        head.weight.grad = None
+        loss, pred = head.loss(xl, yl)
+        loss.backward()
+        idx = (head.last_sample_index() + head.class_lo).cpu()
+        got = [loss.detach().cpu(), pred.cpu(), xl.grad.cpu(), head.weight.grad.cpu(), idx, head.class_lo]
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(got, gathered, dst=0)
+        if rank == 0:
+            union = torch.cat([g[4] for g in gathered])          # rank order = ascending class ranges
+            assert bool((union[1:] > union[:-1]).all())
+            sub = mm.ArcMarginProduct(D, union.numel(), s=s, m=m, use_cuda_graph=False).to(dev)
+            with torch.no_grad():
+                sub.weight.copy_(torch.from_numpy(w)[union])
+            xt = torch.from_numpy(x).to(dev).requires_grad_(True)
+            pos = torch.searchsorted(union, torch.from_numpy(y))
+            assert torch.equal(union[pos], torch.from_numpy(y)), "a label is missing from the union of the samples"
+            dl, dp = sub.loss(xt, pos.to(dev))
+            dl.backward()
+            for r in range(world):
+                l_r, p_r, dx_r, dw_r, idx_r, lo_r = gathered[r]
+                try:
+                    assert abs(float(l_r) - float(dl)) <= 1e-5 * max(1.0, abs(float(dl))), "loss"
+                    assert torch.equal(p_r, union[dp.cpu()][r * b_loc:(r + 1) * b_loc]), "argmax"
+                    rdx = xt.grad[r * b_loc:(r + 1) * b_loc].cpu()
+                    torch.testing.assert_close(dx_r, rdx, rtol=2e-3, atol=4e-3 * float(rdx.abs().max()))
+                    rows = torch.searchsorted(union, idx_r)
+                    rdw = sub.weight.grad[rows].cpu()
+                    torch.testing.assert_close(dw_r[idx_r - lo_r], rdw, rtol=2e-3, atol=4e-3 * float(rdw.abs().max()))
+                    mask = torch.ones(dw_r.shape[0], dtype=torch.bool)
+                    mask[idx_r - lo_r] = False
+                    assert float(dw_r[mask].abs().max()) == 0.0, "rows outside the sample must have a zero gradient"
+                except AssertionError as e:
+                    ok = False
+                    msg += "iteration %d rank %d: %s\n" % (it, r, str(e)[:300])
+    if rank == 0:
+        with open(os.path.join(out_dir, "result.txt"), "w") as f:
+            f.write("OK" if ok else "FAIL\n" + msg)
+    torch.cuda.synchronize()
+    dist.barrier()
+    sys.stdout.flush()
+    os._exit(0)
+
+
+def test_two_gpu_sampled_sharded_head_matches_dense_head_on_the_union_of_samples(tmp_path):
+    """PartialFC-style class sampling with every rank drawing from its own shard: loss / argmax / dx / dW against the
+    dense head built from the union of the ranks' samples (the same kernels; the sampling rule itself is checked against
+    its oracle in tests/test_sampling.py)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    port = _free_port()
+    procs = [ctx.Process(target=_sampled_worker, args=(r, 2, port, str(tmp_path))) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
