@@ -642,8 +642,11 @@ static void fwd_partition(int B, int64_t C, int nsm, int* m_tiles, int* n_tiles,
 static bool fwd_use_pairs(int D, int nsm) {
     const char* v = diag_env("ARCFACE_B200_FWD_IMPL");
     if (v != nullptr && strcmp(v, "generic") == 0) return false;
-    (void)D;
-    return nsm >= 2;
+    if (v != nullptr && strcmp(v, "pairs") == 0) return nsm >= 2;
+    // D <= 512: the batch slice is parked in shared memory and the pair kernel wins by 13-19 %.  Wider embeddings stream
+    // both operands, and there the one-CTA streaming kernel measured faster at every BASELINE width (forward of configs
+    // 2 / 3-shard / 4: 0.248 / 0.219 / 0.463 ms against 0.268 / 0.223 / 0.476 ms, profiles/r2_dx_pair_exp.log)
+    return nsm >= 2 && D <= 512;
 }
 // The in-kernel weight normaliser holds a row pair (D <= 512) or one row (D <= 1024) in registers.  Wider rows run K1
 // as its own launch: a one-row-at-a-time, two-pass helper (second pass from L2) was measured at 0.52 / 0.35 / 0.80 ms for
