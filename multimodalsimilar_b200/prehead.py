@@ -210,6 +210,10 @@ class MultiHeadArcFace(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("multimodalsimilar_b200.MultiHeadArcFace runs on a B200 only; there is no CPU path")
         x = x.to(torch.float32).contiguous()
+        if x.shape[0] > ops.MAX_BATCH:
+            # (the single heads run larger batches in row chunks, engine.batch_chunks; the shared-K1 multi-head step does
+            # not: its backward is one launch group per head)
+            raise ValueError("MultiHeadArcFace takes up to %d rows per call, got %d" % (ops.MAX_BATCH, x.shape[0]))
         ys = [y.reshape(-1).to(device=x.device, dtype=torch.int64).contiguous() for y in labels]
         heads = list(self.heads)
         ws = [h.weight if h.weight.is_contiguous() else h.weight.contiguous() for h in heads]
