@@ -80,7 +80,7 @@ def resolve_config(name, world):
     return c
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of the north-star
 # workload on one B200; only meaningful for the single-GPU north-star shape.
-NCU_TRAFFIC = {"fwd": 2.315111e9 + 0.997995e9, "k3": 1.197121e9 + 2.134192e9,
+NCU_TRAFFIC = {"fwd": 2.390748e9 + 1.001045e9, "k3": 1.169525e9 + 2.130180e9,
                "source": "profiles/r2b_fwd_bwd_full_raw.csv (ncu --set full, per launch)"}
 METRIC = "arcface_head_fwd_bwd_samples_per_sec_1M_classes"
 WEIGHT_SEED = 1234
@@ -576,46 +576,57 @@ def gpu_reference(job):
 
 
 def stage_times(torch, ops, head, x_host, y_host, dev, s, m, c_lo, c_total, iters):
-    """Average milliseconds of each stage of one rank's step (whole batch, local class shard), timed with
-    CUDA events on the launching stream, after warm-up (eager launches: N = 1 only)."""
+    """Average milliseconds per launch group of each stage of one rank's step (whole batch, local class shard): every
+    stage is issued `iters` times back to back between two CUDA events on the launching stream, after two warm-up
+    launches (eager launches: N = 1 only).  Back to back, so that the host-side cost of an eager launch (workspace
+    allocation, tensor-map encoding) is queued behind the previous launch instead of being timed."""
     x = x_host.to(dev)
     y = y_host.to(dev)
     w = head.weight.detach()
     B, D = x.shape
-    names = ["k1_x", "label", "fwd", "k3", "bwd_x"]
-    acc = {n: 0.0 for n in names}
     dw = torch.empty_like(w)
-    for it in range(iters + 2):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
-        ev[0].record()
-        xhat, inv_nx, xhat_t = ops.normalize_cast(x, want_transpose=True)
-        ev[1].record()
-        lm = ops.label_margin(x, w, inv_nx, None, y, c_lo, c_total, s, m, False)
-        ev[2].record()
-        what, inv_nw, rmax, rsum, rarg = ops.forward_rows_fused(xhat, w, lm.label_local, s, c_lo)
-        lse, arg, zl, omp, loss = ops.finalize_rows(rmax.view(1, B), rsum.view(1, B), rarg.view(1, B),
-                                                    lm.z_label.view(1, B), y)
-        ev[3].record()
-        dxhat, _ = ops.backward(xhat, xhat_t, what, inv_nw, lse, omp, lm.dphi, lm.label_local, s, 1.0 / B, dw_out=dw)
-        ev[4].record()
-        ops.normalize_bwd_x(x, inv_nx, dxhat)
-        ev[5].record()
+    xhat, inv_nx, xhat_t = ops.normalize_cast(x, want_transpose=True)
+    lm = ops.label_margin(x, w, inv_nx, None, y, c_lo, c_total, s, m, False)
+    what, inv_nw, rmax, rsum, rarg = ops.forward_rows_fused(xhat, w, lm.label_local, s, c_lo)
+    lse, arg, zl, omp, loss = ops.finalize_rows(rmax.view(1, B), rsum.view(1, B), rarg.view(1, B), lm.z_label.view(1, B), y)
+    dxhat, _ = ops.backward(xhat, xhat_t, what, inv_nw, lse, omp, lm.dphi, lm.label_local, s, 1.0 / B, dw_out=dw)
+
+    def fwd():
+        r = ops.forward_rows_fused(xhat, w, lm.label_local, s, c_lo)
+        ops.finalize_rows(r[2].view(1, B), r[3].view(1, B), r[4].view(1, B), lm.z_label.view(1, B), y)
+
+    stages = {
+        "k1_x": lambda: ops.normalize_cast(x, want_transpose=True),
+        "label": lambda: ops.label_margin(x, w, inv_nx, None, y, c_lo, c_total, s, m, False),
+        "fwd": fwd,
+        "k3": lambda: ops.backward(xhat, xhat_t, what, inv_nw, lse, omp, lm.dphi, lm.label_local, s, 1.0 / B, dw_out=dw),
+        "bwd_x": lambda: ops.normalize_bwd_x(x, inv_nx, dxhat),
+    }
+    out = {}
+    for name, fn in stages.items():
+        for _ in range(2):
+            fn()
         torch.cuda.synchronize()
-        if it >= 2:
-            for i, n in enumerate(names):
-                acc[n] += ev[i].elapsed_time(ev[i + 1])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = e0.elapsed_time(e1) / iters
     del dw
-    return {n: acc[n] / iters for n in names}
+    return out
 
 
-def dominant_kernel_roofline(job, ops, peaks, stages, regime, traffic_ok):
+def dominant_kernel_roofline(job, ops, peaks, stages, regime, traffic_ok, ms_step=None):
     cfg = job.cfg
     B, D = cfg["B"], cfg["D"]
     c_loc = job.c_hi - job.c_lo
     p_tensor = peaks["bf16_tflops" if regime == "burst" else "bf16_tflops_sustained"]
     _, n_chunks = ops.backward_plan(B, D, c_loc)
     k3_launches = ops.backward_launches(B, D, c_loc)
-    comp_ms = sum(stages.values())
+    # share of the (graph-replayed) step; the small stages are host-bound when launched eagerly, so their sum is not used
+    comp_ms = ms_step if ms_step else sum(stages.values())
     fwd_bytes = c_loc * D * 6.0 + 4.0 * c_loc   # fp32 W in, bf16 What + 1/||w|| out
     fwd_hbm_s = fwd_bytes / (peaks["hbm_gbs"] * 1e9)
     fwd_tensor_s = 2.0 * B * D * c_loc / (p_tensor * 1e12)
@@ -754,7 +765,7 @@ def main():
             stages = stage_times(torch, ops, job.head, job.x_host, job.y_host, dev, cfg["s"], cfg["m"], 0, C,
                                  max(5, min(args.steps, 30)))
             roofline = dominant_kernel_roofline(job, ops, peaks, stages, roof_step["regime"],
-                                                head_name == "ns" and not args.classes)
+                                                head_name == "ns" and not args.classes, ms_step)
             gpu_ref = gpu_reference(job)
     job.close()
     del job
