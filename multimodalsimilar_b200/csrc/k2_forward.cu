@@ -151,7 +151,7 @@ struct FwdStats {
 // keep separate partial rows (slot = 2 * range + half), merged by combine_partials.
 //
 // NORM = true additionally runs K1 for the class weights INSIDE this kernel (arcface.py:47, F.normalize of the
-// weight): eight helper warps per CTA read the fp32 rows, write bf16 what + 1/||w|| and publish one counter
+// weight): sixteen helper warps per CTA read the fp32 rows, write bf16 what + 1/||w|| and publish one counter
 // per 128-row block; the TMA producer of a CTA waits for the counter of the block it is about to fetch, so the
 // bf16 rows are read back from L2 and the fp32 weights cross HBM exactly once per step for the forward.
 __device__ __forceinline__ float4 ldg_stream4(const float* p) {
@@ -296,7 +296,14 @@ struct FwdStatsPairT : pr::PairDefaults {
                     o.y = pack_bf16x2(x.z * inv, x.w * inv);
                     o.z = pack_bf16x2(y.x * inv, y.y * inv);
                     o.w = pack_bf16x2(y.z * inv, y.w * inv);
+#ifdef AB_FWD_WHAT_EVICT_LAST
+                    // experiment: ask L2 to keep the normalised rows until the GEMM's TMA has read them back
+                    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(dst + d), "r"(o.x),
+                                 "r"(o.y), "r"(o.z), "r"(o.w), "l"(l2_policy_evict_last())
+                                 : "memory");
+#else
                     *reinterpret_cast<uint4*>(dst + d) = o;
+#endif
                 }
             }
         }
