@@ -1139,6 +1139,21 @@ struct BwdDX2 {
 #include "k3_fused.cuh"
 namespace ab {
 
+// dXhat = sum over the class splits' partial tiles, in split order (fixed: the result does not depend on which split
+// finished first).  parts: [n_parts][part_stride4 float4], the first n4 float4 of each are the [B][D] rows.
+__global__ void __launch_bounds__(256) sum_dx_parts_kernel(const float4* __restrict__ parts, int n_parts, int64_t part_stride4,
+                                                           int64_t n4, float4* __restrict__ out) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float4 a = parts[i];
+        for (int s = 1; s < n_parts; ++s) {
+            const float4 b = parts[s * part_stride4 + i];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        out[i] = a;
+    }
+}
+
 struct BwdPlan {
     int Bp;             // scratch leading dimension (batch rounded up to 64)
     int chunk_classes;  // classes per scratch chunk (multiple of 128)
@@ -1150,6 +1165,9 @@ struct BwdPlan {
     bool dx_pairs;           // single-launch backward: the dX role runs on CTA pairs
     int n_dc, n_dw, n_dx, ring_slots, n_blocks;
     size_t cnt_off, cnt_bytes;
+    // single-launch backward: per-split dX tiles ([dx_parts][dx_part_rows][D] fp32), summed in split order afterwards
+    int dx_parts, dx_part_rows;
+    size_t dxp_off, dxp_bytes;
     int q_slots;             // partial-sum slots of q per class
     size_t scratch_off, scratch_bytes, q_off, q_bytes, total;
     int kx;                  // column blocks of the dC^T scratch: 1, or 3 = [hi | hi | lo] (bf16x3 mode on CTA pairs)
@@ -1303,10 +1321,20 @@ static BwdPlan plan_backward(int B, int D, int64_t C, int nsm, int Ds = 0) {
         pl.q_bytes = static_cast<size_t>(C) * 4 * pl.q_slots;
         pl.cnt_off = pl.q_off + (pl.q_bytes + 255) / 256 * 256;
         pl.cnt_bytes = static_cast<size_t>(pl.n_blocks) * 2 * sizeof(int);
-        pl.total = pl.cnt_off + (pl.cnt_bytes + 255) / 256 * 256;
+        {
+            const int n_res_dc = (B + 255) / 256, n_res_dw = (D + 255) / 256;
+            const int splits = pl.dx_pairs ? pl.n_dx / (n_res_dc * ((D + 511) / 512)) : (2 * pl.n_dx) / (n_res_dc * n_res_dw);
+            pl.dx_parts = splits < pl.n_blocks ? splits : pl.n_blocks;   // splits beyond the block count have no work
+            pl.dx_part_rows = n_res_dc * 256;
+        }
+        pl.dxp_off = pl.cnt_off + (pl.cnt_bytes + 255) / 256 * 256;
+        pl.dxp_bytes = static_cast<size_t>(pl.dx_parts) * pl.dx_part_rows * D * sizeof(float);
+        pl.total = pl.dxp_off + (pl.dxp_bytes + 255) / 256 * 256;
         return pl;
     }
     pl.cnt_off = pl.cnt_bytes = 0;
+    pl.dx_parts = pl.dx_part_rows = 0;
+    pl.dxp_off = pl.dxp_bytes = 0;
     const int64_t c_round = ((C + 127) / 128) * 128;
     int64_t chunk;
     size_t cap = generic ? (size_t(64) << 20) : (size_t(2048) << 20);
@@ -1441,7 +1469,8 @@ static int32_t backward_impl(const uint16_t* xhat, const uint16_t* xhat_t, int64
     float* q = reinterpret_cast<float*>(ws + pl.q_off);
     const int C = static_cast<int>(C_local);
 
-    AB_CHECK_CUDA(cudaMemsetAsync(dxhat, 0, static_cast<size_t>(B) * D * sizeof(float), st));
+    // (the single-launch backward writes dXhat itself, from per-split tiles summed in a fixed order)
+    if (!pl.fused) AB_CHECK_CUDA(cudaMemsetAsync(dxhat, 0, static_cast<size_t>(B) * D * sizeof(float), st));
 
     CUtensorMap tm_w_k, tm_x_k, tm_dct_k, tm_xt_k, tm_dct_mn, tm_w_mn, tm_dct_out, tm_dw_out, tm_dx_out;
     if (int32_t rc = make_tmap_kmajor(&tm_w_k, what, Ds, C_local, ldw, BLOCK_M)) return rc;
@@ -1547,8 +1576,15 @@ static int32_t backward_impl(const uint16_t* xhat, const uint16_t* xhat_t, int64
                 p.dn_tiles = n_res_dw;
                 p.splits = (2 * pl.n_dx) / (n_res_dc * n_res_dw);
             }
+            p.part_rows = pl.dx_part_rows;
             p.ring = ring;
         }
+        // dX: every class split stores its partial tile; sum_dx_parts adds them in split order (bit-reproducible, and no
+        // zero-fill + fp32 reduce-adds in L2)
+        float* dx_parts = reinterpret_cast<float*>(ws + pl.dxp_off);
+        CUtensorMap tm_dxp_out;
+        if (int32_t rc = make_tmap_store(&tm_dxp_out, dx_parts, 4, D, static_cast<uint64_t>(pl.dx_parts) * pl.dx_part_rows, D))
+            return rc;
         // the ring replaces the full-size scratch: [slots * 256][Bp] bf16
         CUtensorMap tm_ring_out, tm_ring_k, tm_ring_mn;
         const int64_t ring_rows = static_cast<int64_t>(pl.ring_slots) * 256;
@@ -1570,8 +1606,16 @@ static int32_t backward_impl(const uint16_t* xhat, const uint16_t* xhat_t, int64
         }
 #endif
         fz::bwd_fused_kernel<<<grid, pr::THREADS, smem, st>>>(tm_w_k, tm_x_k, tm_ring_out, tm_ring_k, tm_xt_k, tm_dw_out,
-                                                             tm_ring_mn, tm_w_mn, tm_dx_out, fp);
+                                                             tm_ring_mn, tm_w_mn, tm_dxp_out, fp);
         AB_CHECK_CUDA(cudaGetLastError());
+        {
+            const int64_t n4 = static_cast<int64_t>(B) * D / 4;
+            const int64_t want = (n4 + 255) / 256;
+            sum_dx_parts_kernel<<<static_cast<int>(want < 148 * 8 ? want : 148 * 8), 256, 0, st>>>(
+                reinterpret_cast<const float4*>(dx_parts), pl.dx_parts, static_cast<int64_t>(pl.dx_part_rows) * D / 4, n4,
+                reinterpret_cast<float4*>(dxhat));
+            AB_CHECK_CUDA(cudaGetLastError());
+        }
 #ifdef ARCFACE_B200_DIAG
         if (prof) {
             static unsigned long long host[2 * fz::MAX_PAIRS * 16];

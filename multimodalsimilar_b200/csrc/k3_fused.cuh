@@ -40,6 +40,9 @@ struct DXParams {
     int n_blocks;           // 256-class blocks
     int m_tiles, dn_tiles;  // output tiles along batch / embedding
     int splits;             // class splits; CTA x handles tile x % (m_tiles * dn_tiles) of split x / (...)
+    int part_rows;          // > 0: split sp STORES its tile into rows [sp * part_rows, ...) of the output map (a
+                            // [splits * part_rows][D] scratch summed in fixed order afterwards: bit-reproducible dX);
+                            // 0: every split reduce-adds into dXhat [B][D] (order not fixed)
     Ring ring;
     unsigned long long* prof = nullptr;  // measurements only: 16 counters per CTA (pr::WaitProf layout)
     int prof_cta = 0;
@@ -181,7 +184,8 @@ __device__ __forceinline__ void dx_body(const CUtensorMap& tmA, const CUtensorMa
             mbar_wait(tfull_bar, 0);
             tc_fence_after();
             const int row0 = m0 + ms * BLOCK_M + quad * 32;
-            if (row0 < p.B) {  // warp-uniform: otherwise these 32 rows are batch padding
+            if (row0 < p.B || p.part_rows > 0) {  // warp-uniform: otherwise these 32 rows are batch padding (with parts the
+                                                  // padding rows of the split's scratch are written too: zeros)
                 const uint32_t taddr = tmem_base + ms * DX_TILE + (static_cast<uint32_t>(quad * 32) << 16);
 #pragma unroll 1
                 for (int cc = 0; cc < DX_TILE / 32; ++cc) {
@@ -196,7 +200,8 @@ __device__ __forceinline__ void dx_body(const CUtensorMap& tmA, const CUtensorMa
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_reduce_add_2d(&tmC, ctx.staging, d0, row0);  // rows >= B / columns >= D are clipped
+                        if (p.part_rows > 0) tma_store_2d(&tmC, ctx.staging, d0, sp * p.part_rows + row0);
+                        else tma_reduce_add_2d(&tmC, ctx.staging, d0, row0);  // rows >= B / columns >= D are clipped
                         bulk_commit();
                     }
                 }
@@ -363,7 +368,7 @@ __device__ __forceinline__ void dx_pair_body(const CUtensorMap& tmA, const CUten
             mbar_wait(tfull_bar, 0);
             tc_fence_after();
             const int row0 = m0 + quad * 32;
-            if (row0 < p.B && nb < n_nb) {  // warp-uniform: otherwise batch padding / columns past the embedding width
+            if ((row0 < p.B || p.part_rows > 0) && nb < n_nb) {  // warp-uniform: otherwise batch padding / columns past the width
                 const uint32_t taddr = tmem_base + nb * 256 + (static_cast<uint32_t>(quad * 32) << 16);
 #pragma unroll 1
                 for (int cc = 0; cc < 256 / 32; ++cc) {
@@ -378,7 +383,8 @@ __device__ __forceinline__ void dx_pair_body(const CUtensorMap& tmA, const CUten
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_reduce_add_2d(&tmC, ctx.staging, d0, row0);  // rows >= B / columns >= D are clipped
+                        if (p.part_rows > 0) tma_store_2d(&tmC, ctx.staging, d0, sp * p.part_rows + row0);
+                        else tma_reduce_add_2d(&tmC, ctx.staging, d0, row0);  // rows >= B / columns >= D are clipped
                         bulk_commit();
                     }
                 }
