@@ -80,7 +80,7 @@ def resolve_config(name, world):
     return c
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of the north-star
 # workload on one B200; only meaningful for the single-GPU north-star shape.
-NCU_TRAFFIC = {"fwd": 2.390748e9 + 1.001045e9, "k3": 1.169525e9 + 2.130180e9,
+NCU_TRAFFIC = {"fwd": 2.363926e9 + 1.000759e9, "k3": 1.170017e9 + 2.147357e9,
                "source": "profiles/r2b_fwd_bwd_full_raw.csv (ncu --set full, per launch)"}
 METRIC = "arcface_head_fwd_bwd_samples_per_sec_1M_classes"
 WEIGHT_SEED = 1234
@@ -576,46 +576,73 @@ def gpu_reference(job):
 
 
 def stage_times(torch, ops, head, x_host, y_host, dev, s, m, c_lo, c_total, iters):
-    """Average milliseconds per launch group of each stage of one rank's step (whole batch, local class shard): every
-    stage is issued `iters` times back to back between two CUDA events on the launching stream, after two warm-up
-    launches (eager launches: N = 1 only).  Back to back, so that the host-side cost of an eager launch (workspace
-    allocation, tensor-map encoding) is queued behind the previous launch instead of being timed."""
+    """Average milliseconds of each stage of one rank's step (whole batch, local class shard).  The step's kernel
+    sequence is captured as one CUDA graph PER STAGE (the product replays the whole step as one graph; eager launches of
+    the big kernels carry ~0.1 ms of host-side launch work that a replay does not have) and the stage graphs are replayed
+    in step order `iters` times back to back, a CUDA event between them on the launching stream, one synchronize at the
+    end: every kernel runs next to the kernels it runs next to in the real step, in the same clock / power state.
+    N = 1 only."""
     x = x_host.to(dev)
     y = y_host.to(dev)
     w = head.weight.detach()
     B, D = x.shape
+    names = ["k1_x", "label", "fwd", "k3", "bwd_x"]
     dw = torch.empty_like(w)
-    xhat, inv_nx, xhat_t = ops.normalize_cast(x, want_transpose=True)
-    lm = ops.label_margin(x, w, inv_nx, None, y, c_lo, c_total, s, m, False)
-    what, inv_nw, rmax, rsum, rarg = ops.forward_rows_fused(xhat, w, lm.label_local, s, c_lo)
-    lse, arg, zl, omp, loss = ops.finalize_rows(rmax.view(1, B), rsum.view(1, B), rarg.view(1, B), lm.z_label.view(1, B), y)
-    dxhat, _ = ops.backward(xhat, xhat_t, what, inv_nw, lse, omp, lm.dphi, lm.label_local, s, 1.0 / B, dw_out=dw)
+    st = {}
+
+    def k1_x():
+        st["xhat"], st["inv_nx"], st["xhat_t"] = ops.normalize_cast(x, want_transpose=True)
+
+    def label():
+        st["lm"] = ops.label_margin(x, w, st["inv_nx"], None, y, c_lo, c_total, s, m, False)
 
     def fwd():
-        r = ops.forward_rows_fused(xhat, w, lm.label_local, s, c_lo)
-        ops.finalize_rows(r[2].view(1, B), r[3].view(1, B), r[4].view(1, B), lm.z_label.view(1, B), y)
+        lm = st["lm"]
+        st["what"], st["inv_nw"], rmax, rsum, rarg = ops.forward_rows_fused(st["xhat"], w, lm.label_local, s, c_lo)
+        st["lse"], _, _, st["omp"], _ = ops.finalize_rows(rmax.view(1, B), rsum.view(1, B), rarg.view(1, B),
+                                                          lm.z_label.view(1, B), y)
 
-    stages = {
-        "k1_x": lambda: ops.normalize_cast(x, want_transpose=True),
-        "label": lambda: ops.label_margin(x, w, inv_nx, None, y, c_lo, c_total, s, m, False),
-        "fwd": fwd,
-        "k3": lambda: ops.backward(xhat, xhat_t, what, inv_nw, lse, omp, lm.dphi, lm.label_local, s, 1.0 / B, dw_out=dw),
-        "bwd_x": lambda: ops.normalize_bwd_x(x, inv_nx, dxhat),
-    }
-    out = {}
-    for name, fn in stages.items():
+    def k3():
+        lm = st["lm"]
+        st["dxhat"], _ = ops.backward(st["xhat"], st["xhat_t"], st["what"], st["inv_nw"], st["lse"], st["omp"], lm.dphi,
+                                      lm.label_local, s, 1.0 / B, dw_out=dw)
+
+    def bwd_x():
+        ops.normalize_bwd_x(x, st["inv_nx"], st["dxhat"])
+
+    fns = [k1_x, label, fwd, k3, bwd_x]
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
         for _ in range(2):
+            for fn in fns:
+                fn()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize(dev)
+    graphs = []
+    pool = None
+    for fn in fns:   # one pool: a later stage reads what an earlier one left in its static buffers
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, pool=pool):
             fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(iters):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        out[name] = e0.elapsed_time(e1) / iters
-    del dw
-    return out
+        pool = g.pool()
+        graphs.append(g)
+    marks = []
+    for it in range(iters + 2):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+        ev[0].record()
+        for i, g in enumerate(graphs):
+            g.replay()
+            ev[i + 1].record()
+        if it >= 2:
+            marks.append(ev)
+    torch.cuda.synchronize()
+    acc = {n: 0.0 for n in names}
+    for ev in marks:
+        for i, n in enumerate(names):
+            acc[n] += ev[i].elapsed_time(ev[i + 1])
+    del graphs, st, dw
+    return {n: acc[n] / len(marks) for n in names}
 
 
 def dominant_kernel_roofline(job, ops, peaks, stages, regime, traffic_ok, ms_step=None):
