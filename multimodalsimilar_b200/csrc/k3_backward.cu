@@ -1139,21 +1139,6 @@ struct BwdDX2 {
 #include "k3_fused.cuh"
 namespace ab {
 
-// dXhat = sum over the class splits' partial tiles, in split order (fixed: the result does not depend on which split
-// finished first).  parts: [n_parts][part_stride4 float4], the first n4 float4 of each are the [B][D] rows.
-__global__ void __launch_bounds__(256) sum_dx_parts_kernel(const float4* __restrict__ parts, int n_parts, int64_t part_stride4,
-                                                           int64_t n4, float4* __restrict__ out) {
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        float4 a = parts[i];
-        for (int s = 1; s < n_parts; ++s) {
-            const float4 b = parts[s * part_stride4 + i];
-            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-        }
-        out[i] = a;
-    }
-}
-
 struct BwdPlan {
     int Bp;             // scratch leading dimension (batch rounded up to 64)
     int chunk_classes;  // classes per scratch chunk (multiple of 128)
@@ -1320,7 +1305,9 @@ static BwdPlan plan_backward(int B, int D, int64_t C, int nsm, int Ds = 0) {
         pl.q_off = (pl.scratch_bytes + 255) / 256 * 256;
         pl.q_bytes = static_cast<size_t>(C) * 4 * pl.q_slots;
         pl.cnt_off = pl.q_off + (pl.q_bytes + 255) / 256 * 256;
-        pl.cnt_bytes = static_cast<size_t>(pl.n_blocks) * 2 * sizeof(int);
+        // ring counters (two per block) + the dX regions' arrival counters (16 per 256 x 512 of dX at most)
+        pl.cnt_bytes = (static_cast<size_t>(pl.n_blocks) * 2 + static_cast<size_t>(((B + 255) / 256) * ((D + 255) / 256) * 16)) *
+                       sizeof(int);
         {
             const int n_res_dc = (B + 255) / 256, n_res_dw = (D + 255) / 256;
             const int splits = pl.dx_pairs ? pl.n_dx / (n_res_dc * ((D + 511) / 512)) : (2 * pl.n_dx) / (n_res_dc * n_res_dw);
@@ -1577,10 +1564,14 @@ static int32_t backward_impl(const uint16_t* xhat, const uint16_t* xhat_t, int64
                 p.splits = (2 * pl.n_dx) / (n_res_dc * n_res_dw);
             }
             p.part_rows = pl.dx_part_rows;
+            p.n_parts = pl.dx_parts;
+            p.parts = reinterpret_cast<const float*>(ws + pl.dxp_off);
+            p.region_cnt = counters + 2 * pl.n_blocks;
+            p.dx_out = dxhat;
             p.ring = ring;
         }
-        // dX: every class split stores its partial tile; sum_dx_parts adds them in split order (bit-reproducible, and no
-        // zero-fill + fp32 reduce-adds in L2)
+        // dX: every class split stores its partial tile; the last split to arrive at a region adds them in split order
+        // (k3_fused.cuh dx_region_done: bit-reproducible, no zero-fill, no fp32 reduce-adds in L2)
         float* dx_parts = reinterpret_cast<float*>(ws + pl.dxp_off);
         CUtensorMap tm_dxp_out;
         if (int32_t rc = make_tmap_store(&tm_dxp_out, dx_parts, 4, D, static_cast<uint64_t>(pl.dx_parts) * pl.dx_part_rows, D))
@@ -1608,14 +1599,6 @@ static int32_t backward_impl(const uint16_t* xhat, const uint16_t* xhat_t, int64
         fz::bwd_fused_kernel<<<grid, pr::THREADS, smem, st>>>(tm_w_k, tm_x_k, tm_ring_out, tm_ring_k, tm_xt_k, tm_dw_out,
                                                              tm_ring_mn, tm_w_mn, tm_dxp_out, fp);
         AB_CHECK_CUDA(cudaGetLastError());
-        {
-            const int64_t n4 = static_cast<int64_t>(B) * D / 4;
-            const int64_t want = (n4 + 255) / 256;
-            sum_dx_parts_kernel<<<static_cast<int>(want < 148 * 8 ? want : 148 * 8), 256, 0, st>>>(
-                reinterpret_cast<const float4*>(dx_parts), pl.dx_parts, static_cast<int64_t>(pl.dx_part_rows) * D / 4, n4,
-                reinterpret_cast<float4*>(dxhat));
-            AB_CHECK_CUDA(cudaGetLastError());
-        }
 #ifdef ARCFACE_B200_DIAG
         if (prof) {
             static unsigned long long host[2 * fz::MAX_PAIRS * 16];

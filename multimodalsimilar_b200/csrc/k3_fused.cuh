@@ -41,8 +41,14 @@ struct DXParams {
     int m_tiles, dn_tiles;  // output tiles along batch / embedding
     int splits;             // class splits; CTA x handles tile x % (m_tiles * dn_tiles) of split x / (...)
     int part_rows;          // > 0: split sp STORES its tile into rows [sp * part_rows, ...) of the output map (a
-                            // [splits * part_rows][D] scratch summed in fixed order afterwards: bit-reproducible dX);
+                            // [n_parts * part_rows][D] scratch); the warp that completes a 32-row x 256-column region --
+                            // the last of the n_parts splits to arrive there, whichever that is -- adds the splits'
+                            // copies in split order and writes dXhat: bit-reproducible, no zero-fill, no extra launch.
                             // 0: every split reduce-adds into dXhat [B][D] (order not fixed)
+    int n_parts;            // splits that have work (min(splits, n_blocks))
+    const float* parts;     // the scratch behind the output map
+    int* region_cnt;        // [regions] arrivals per region, zeroed before the launch
+    float* dx_out;          // dXhat [B][D]
     Ring ring;
     unsigned long long* prof = nullptr;  // measurements only: 16 counters per CTA (pr::WaitProf layout)
     int prof_cta = 0;
@@ -51,6 +57,40 @@ struct DXParams {
 constexpr size_t dx_smem_bytes() {
     return static_cast<size_t>(DX_STAGES) * 2 * DX_OPER_BYTES + pr::EPI_WARPS * pr::STAGING_PER_WARP +
            (2 * DX_STAGES + 1) * 8 + 16;
+}
+
+// One epilogue warp has stored its 32-row x 256-column region of split `sp`'s tile (TMA stores committed by lane 0).
+// Counts the arrival; the warp that is last at this region sums the n_parts copies in split order into dXhat.
+__device__ __forceinline__ void dx_region_done(const DXParams& p, int region, int row0, int col0, int lane) {
+    int prev = 0;
+    if (lane == 0) {
+        bulk_wait<0>();          // this warp's stores have been performed
+        __threadfence();         // ... and are visible device-wide before the arrival is
+        prev = atomicAdd(p.region_cnt + region, 1);
+    }
+    prev = __shfl_sync(0xffffffffu, prev, 0);
+    if (prev != p.n_parts - 1) return;
+    __threadfence();             // the other splits' stores (published before their arrivals) are visible to the loads below
+    const int64_t part_stride = static_cast<int64_t>(p.part_rows) * p.D;
+    const int c = col0 + lane * 8;
+#pragma unroll 1
+    for (int r = 0; r < 32; ++r) {
+        const int row = row0 + r;
+        if (row >= p.B) break;
+        if (c >= p.D) continue;   // (D % 8 == 0: a lane's eight columns are all inside or all outside)
+        const float* src = p.parts + static_cast<int64_t>(row) * p.D + c;
+        float4 a0 = __ldcg(reinterpret_cast<const float4*>(src));
+        float4 a1 = __ldcg(reinterpret_cast<const float4*>(src + 4));
+        for (int sp = 1; sp < p.n_parts; ++sp) {
+            const float4 b0 = __ldcg(reinterpret_cast<const float4*>(src + sp * part_stride));
+            const float4 b1 = __ldcg(reinterpret_cast<const float4*>(src + sp * part_stride + 4));
+            a0.x += b0.x; a0.y += b0.y; a0.z += b0.z; a0.w += b0.w;
+            a1.x += b1.x; a1.y += b1.y; a1.z += b1.z; a1.w += b1.w;
+        }
+        float* dst = p.dx_out + static_cast<int64_t>(row) * p.D + c;
+        *reinterpret_cast<float4*>(dst) = a0;
+        *reinterpret_cast<float4*>(dst + 4) = a1;
+    }
 }
 
 // dXhat role.  `x` = index of this CTA among the dX CTAs.  cta_group::1 throughout (the two CTAs of a cluster
@@ -184,8 +224,7 @@ __device__ __forceinline__ void dx_body(const CUtensorMap& tmA, const CUtensorMa
             mbar_wait(tfull_bar, 0);
             tc_fence_after();
             const int row0 = m0 + ms * BLOCK_M + quad * 32;
-            if (row0 < p.B || p.part_rows > 0) {  // warp-uniform: otherwise these 32 rows are batch padding (with parts the
-                                                  // padding rows of the split's scratch are written too: zeros)
+            if (row0 < p.B) {  // warp-uniform: otherwise these 32 rows are batch padding
                 const uint32_t taddr = tmem_base + ms * DX_TILE + (static_cast<uint32_t>(quad * 32) << 16);
 #pragma unroll 1
                 for (int cc = 0; cc < DX_TILE / 32; ++cc) {
@@ -205,6 +244,7 @@ __device__ __forceinline__ void dx_body(const CUtensorMap& tmA, const CUtensorMa
                         bulk_commit();
                     }
                 }
+                if (p.part_rows > 0) dx_region_done(p, t * 8 + (warp - 4), row0, n0, lane);
                 stager.drain();
             }
         }
@@ -368,7 +408,7 @@ __device__ __forceinline__ void dx_pair_body(const CUtensorMap& tmA, const CUten
             mbar_wait(tfull_bar, 0);
             tc_fence_after();
             const int row0 = m0 + quad * 32;
-            if ((row0 < p.B || p.part_rows > 0) && nb < n_nb) {  // warp-uniform: otherwise batch padding / columns past the width
+            if (row0 < p.B && nb < n_nb) {  // warp-uniform: otherwise batch padding / columns past the embedding width
                 const uint32_t taddr = tmem_base + nb * 256 + (static_cast<uint32_t>(quad * 32) << 16);
 #pragma unroll 1
                 for (int cc = 0; cc < 256 / 32; ++cc) {
@@ -388,6 +428,7 @@ __device__ __forceinline__ void dx_pair_body(const CUtensorMap& tmA, const CUten
                         bulk_commit();
                     }
                 }
+                if (p.part_rows > 0) dx_region_done(p, (t * 2 + rank) * 8 + (warp - 4), row0, n0 + nb * 256, lane);
                 stager.drain();
             }
         }
