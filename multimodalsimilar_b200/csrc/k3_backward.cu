@@ -24,6 +24,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#ifndef AB_DX_SUM_MODE
+#define AB_DX_SUM_MODE 1
+#endif
 #ifndef AB_DXP_COST
 #define AB_DXP_COST 2300.0   // pair-cycles per 256-class block and 256 x 256 of dX output on the CTA-pair role
 #endif
@@ -1139,6 +1142,21 @@ struct BwdDX2 {
 #include "k3_fused.cuh"
 namespace ab {
 
+// dXhat = sum over the class splits' partial tiles, in split order (fixed: the result does not depend on which split
+// finished first).  parts: [n_parts][part_stride4 float4], the first n4 float4 of each are the [B][D] rows.
+__global__ void __launch_bounds__(256) sum_dx_parts_kernel(const float4* __restrict__ parts, int n_parts, int64_t part_stride4,
+                                                           int64_t n4, float4* __restrict__ out) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float4 a = parts[i];
+        for (int s = 1; s < n_parts; ++s) {
+            const float4 b = parts[s * part_stride4 + i];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        out[i] = a;
+    }
+}
+
 struct BwdPlan {
     int Bp;             // scratch leading dimension (batch rounded up to 64)
     int chunk_classes;  // classes per scratch chunk (multiple of 128)
@@ -1456,8 +1474,12 @@ static int32_t backward_impl(const uint16_t* xhat, const uint16_t* xhat_t, int64
     float* q = reinterpret_cast<float*>(ws + pl.q_off);
     const int C = static_cast<int>(C_local);
 
-    // (the single-launch backward writes dXhat itself, from per-split tiles summed in a fixed order)
-    if (!pl.fused) AB_CHECK_CUDA(cudaMemsetAsync(dxhat, 0, static_cast<size_t>(B) * D * sizeof(float), st));
+    // How the single-launch backward combines the class splits' dX tiles: 0 = fp32 TMA reduce-adds into a zeroed dXhat
+    // (order not fixed), 1 = per-split tiles + a sum kernel in split order, 2 = per-split tiles summed inside the kernel by
+    // the last warp to arrive at a region.  1 and 2 are bit-reproducible.
+    int dx_sum = AB_DX_SUM_MODE;
+    if (const char* v = diag_env("ARCFACE_B200_BWD_DXSUM")) dx_sum = atoi(v);
+    if (!pl.fused || dx_sum == 0) AB_CHECK_CUDA(cudaMemsetAsync(dxhat, 0, static_cast<size_t>(B) * D * sizeof(float), st));
 
     CUtensorMap tm_w_k, tm_x_k, tm_dct_k, tm_xt_k, tm_dct_mn, tm_w_mn, tm_dct_out, tm_dw_out, tm_dx_out;
     if (int32_t rc = make_tmap_kmajor(&tm_w_k, what, Ds, C_local, ldw, BLOCK_M)) return rc;
@@ -1563,10 +1585,10 @@ static int32_t backward_impl(const uint16_t* xhat, const uint16_t* xhat_t, int64
                 p.dn_tiles = n_res_dw;
                 p.splits = (2 * pl.n_dx) / (n_res_dc * n_res_dw);
             }
-            p.part_rows = pl.dx_part_rows;
+            p.part_rows = dx_sum == 0 ? 0 : pl.dx_part_rows;
             p.n_parts = pl.dx_parts;
             p.parts = reinterpret_cast<const float*>(ws + pl.dxp_off);
-            p.region_cnt = counters + 2 * pl.n_blocks;
+            p.region_cnt = dx_sum == 2 ? counters + 2 * pl.n_blocks : nullptr;
             p.dx_out = dxhat;
             p.ring = ring;
         }
@@ -1597,8 +1619,16 @@ static int32_t backward_impl(const uint16_t* xhat, const uint16_t* xhat_t, int64
         }
 #endif
         fz::bwd_fused_kernel<<<grid, pr::THREADS, smem, st>>>(tm_w_k, tm_x_k, tm_ring_out, tm_ring_k, tm_xt_k, tm_dw_out,
-                                                             tm_ring_mn, tm_w_mn, tm_dxp_out, fp);
+                                                             tm_ring_mn, tm_w_mn, dx_sum == 0 ? tm_dx_out : tm_dxp_out, fp);
         AB_CHECK_CUDA(cudaGetLastError());
+        if (dx_sum == 1) {
+            const int64_t n4 = static_cast<int64_t>(B) * D / 4;
+            const int64_t want = (n4 + 255) / 256;
+            sum_dx_parts_kernel<<<static_cast<int>(want < 148 * 8 ? want : 148 * 8), 256, 0, st>>>(
+                reinterpret_cast<const float4*>(dx_parts), pl.dx_parts, static_cast<int64_t>(pl.dx_part_rows) * D / 4, n4,
+                reinterpret_cast<float4*>(dxhat));
+            AB_CHECK_CUDA(cudaGetLastError());
+        }
 #ifdef ARCFACE_B200_DIAG
         if (prof) {
             static unsigned long long host[2 * fz::MAX_PAIRS * 16];

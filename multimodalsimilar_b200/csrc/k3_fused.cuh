@@ -244,7 +244,7 @@ __device__ __forceinline__ void dx_body(const CUtensorMap& tmA, const CUtensorMa
                         bulk_commit();
                     }
                 }
-                if (p.part_rows > 0) dx_region_done(p, t * 8 + (warp - 4), row0, n0, lane);
+                if (p.part_rows > 0 && p.region_cnt != nullptr) dx_region_done(p, t * 8 + (warp - 4), row0, n0, lane);
                 stager.drain();
             }
         }
@@ -428,7 +428,7 @@ __device__ __forceinline__ void dx_pair_body(const CUtensorMap& tmA, const CUten
                         bulk_commit();
                     }
                 }
-                if (p.part_rows > 0) dx_region_done(p, (t * 2 + rank) * 8 + (warp - 4), row0, n0 + nb * 256, lane);
+                if (p.part_rows > 0 && p.region_cnt != nullptr) dx_region_done(p, (t * 2 + rank) * 8 + (warp - 4), row0, n0 + nb * 256, lane);
                 stager.drain();
             }
         }
