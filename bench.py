@@ -80,7 +80,7 @@ def resolve_config(name, world):
     return c
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of the north-star
 # workload on one B200; only meaningful for the single-GPU north-star shape.
-NCU_TRAFFIC = {"fwd": 2.363926e9 + 1.000759e9, "k3": 1.170017e9 + 2.147357e9,
+NCU_TRAFFIC = {"fwd": 2.346882e9 + 0.999903e9, "k3": 1.200321e9 + 2.148333e9,
                "source": "profiles/r2b_fwd_bwd_full_raw.csv (ncu --set full, per launch)"}
 METRIC = "arcface_head_fwd_bwd_samples_per_sec_1M_classes"
 WEIGHT_SEED = 1234
