@@ -33,10 +33,10 @@ def test_chunk_ranges():
         assert all(b0 % 64 == 0 and 0 < b1 - b0 <= engine.BATCH_CHUNK for b0, b1 in ch)
 
 
-@pytest.mark.parametrize("B,sampled", [(200, False), (130, False), (200, True)])
+@pytest.mark.parametrize("B,sampled", [(200, False), (130, False), (200, True), (67, False), (193, True)])
 def test_chunked_step_matches_oracle(monkeypatch, B, sampled):
     monkeypatch.setattr(engine, "BATCH_CHUNK", 64)
-    assert len(engine.batch_chunks(B)) >= 3
+    assert len(engine.batch_chunks(B)) >= 2
     D, C, s, m = 16, 90, 64.0, 0.4
     x, w, y = onp.synthetic_inputs(B, D, C, seed=B, trained_like=True)
     cfg = engine.StepConfig(s, m, False, 0, C)

@@ -42,6 +42,20 @@ def test_sample_rule_matches_oracle(B, C, num):
     np.testing.assert_array_equal(idx.numpy()[remap[lab >= 0]], lab[lab >= 0])
 
 
+def test_sample_without_local_positives_and_with_tiny_shards():
+    # a rank none of whose classes is a label of the batch still samples (pure negatives)
+    lab = torch.full((6,), -1)
+    idx = engine.sample_classes(lab, 50, 10, torch.Generator().manual_seed(1))
+    assert idx.numel() == 10 and np.all(np.diff(idx.numpy()) > 0) and int(idx.min()) >= 0 and int(idx.max()) < 50
+    assert np.all(engine.remap_labels(lab.int(), idx).numpy() == -1)
+    # a shard smaller than the batch: every class is taken
+    lab = torch.tensor([0, 2, 2, 1, -1, 0, 1, 2])
+    idx = engine.sample_classes(lab, 3, 1, torch.Generator().manual_seed(1))
+    assert idx.tolist() == [0, 1, 2]
+    # one class
+    assert engine.sample_classes(torch.tensor([0, 0]), 1, 1).tolist() == [0]
+
+
 def test_sample_draws_change_and_negatives_are_uniform():
     lab = torch.tensor([3, 3, 9])
     g = torch.Generator().manual_seed(5)
